@@ -1,0 +1,194 @@
+// gv_api.cu -- the extern "C" surface of libgvb200.so (include/gvb200.h): argument checks,
+// error reporting, device gate, host-side tile schedule.  No algorithm lives here.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "gv_internal.h"
+
+namespace gv {
+
+static thread_local std::string g_last_error;
+
+int set_error(int code, const char* msg) {
+  g_last_error = msg ? msg : "";
+  return code;
+}
+int set_cuda_error(cudaError_t e, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d", int(e), cudaGetErrorString(e), file, line);
+  g_last_error = buf;
+  return GV_ERR_CUDA;
+}
+
+int device_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+  return sms > 0 ? sms : 1;
+}
+
+static int check_device() {
+  int dev = 0, major = 0, minor = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10 || minor != 0) {
+    char buf[160];
+    snprintf(buf, sizeof(buf),
+             "libgvb200 is built for sm_100a (B200) only; current device is compute capability %d.%d",
+             major, minor);
+    return set_error(GV_ERR_DEVICE, buf);
+  }
+  return GV_OK;
+}
+
+// implemented in gv_tiles.cu
+int mi_tiles_dispatch(const void*, int64_t, int64_t, int, const int32_t*, const int8_t*, int64_t, int,
+                      const int32_t*, int64_t, float*, int64_t, int, cudaStream_t);
+int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, int32_t*, int64_t, int,
+                       cudaStream_t);
+int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
+                          const int32_t*, int64_t, int, const int32_t*, int64_t, int8_t*, int64_t,
+                          float*, int64_t, int, cudaStream_t);
+
+}  // namespace gv
+
+using namespace gv;
+
+extern "C" {
+
+int gv_abi_version(void) { return GV_ABI_VERSION; }
+const char* gv_last_error(void) { return g_last_error.c_str(); }
+int gv_device_check(void) { return check_device(); }
+
+size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype) {
+  return discretize_workspace_bytes(nnz < 0 ? 0 : nnz, n_genes < 0 ? 0 : n_genes, value_dtype);
+}
+
+int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
+                      const int64_t* row_ptr, int64_t n_cells, int n_genes, int64_t nnz, int n_bins,
+                      const double* q_table_host, void* bins_packed, int64_t bins_pitch_bytes,
+                      int32_t* n_bins_per_gene, int32_t* marg, double* edges, int64_t* gsum,
+                      int64_t* gsq, void* val_rows, int64_t val_pitch, int64_t val_rows_alloc,
+                      int val_mode, int val_limbs, int val_limb_bits, uint64_t* data_flags_out_host,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (n_cells < 0 || n_genes <= 0 || nnz < 0) return set_error(GV_ERR_ARG, "bad matrix shape");
+  if (n_cells >= (int64_t(1) << 31)) return set_error(GV_ERR_ARG, "n_cells must be < 2^31");
+  if (!row_ptr || !q_table_host || !bins_packed || !n_bins_per_gene || !marg || !edges || !gsum ||
+      !gsq || !workspace)
+    return set_error(GV_ERR_ARG, "null pointer argument");
+  if (nnz > 0 && (!values || !col_idx)) return set_error(GV_ERR_ARG, "null CSR arrays");
+  if (val_rows && (val_pitch < n_cells || val_pitch % 128 != 0))
+    return set_error(GV_ERR_ARG, "val_pitch must be a multiple of 128 covering n_cells");
+  DiscretizeArgs a;
+  a.values = values; a.value_dtype = value_dtype; a.col_idx = col_idx; a.row_ptr = row_ptr;
+  a.n_cells = n_cells; a.n_genes = n_genes; a.nnz = nnz; a.n_bins = n_bins; a.q_table = q_table_host;
+  a.bins_packed = bins_packed; a.bins_pitch_bytes = bins_pitch_bytes;
+  a.n_bins_per_gene = n_bins_per_gene; a.marg = marg; a.edges = edges; a.gsum = gsum; a.gsq = gsq;
+  a.val_rows = val_rows; a.val_pitch = val_pitch; a.val_rows_alloc = val_rows_alloc;
+  a.val_mode = val_mode; a.val_limbs = val_limbs; a.val_limb_bits = val_limb_bits;
+  a.data_flags_out = data_flags_out_host; a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return discretize_dispatch(a, static_cast<cudaStream_t>(stream));
+}
+
+int gv_rows_per_gene(int n_bins) {
+  if (n_bins < 1 || n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
+  if (n_bins <= 5) return 5;
+  if (n_bins <= 8) return 8;
+  if (n_bins <= 10) return 10;
+  return 16;
+}
+
+int64_t gv_onehot_rows(int n_genes, int rows_per_gene) {
+  if (rows_per_gene != 5 && rows_per_gene != 8 && rows_per_gene != 10 && rows_per_gene != 16)
+    return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10 or 16");
+  const int gpb = 32 / rows_per_gene;
+  return int64_t((n_genes + gpb - 1) / gpb) * 32;
+}
+
+int gv_expand_onehot(const void* bins_packed, int64_t bins_pitch_bytes, int n_genes,
+                     int rows_per_gene, void* onehot, int64_t kp, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!bins_packed || !onehot || n_genes <= 0) return set_error(GV_ERR_ARG, "bad argument");
+  const int64_t rows = gv_onehot_rows(n_genes, rows_per_gene);
+  if (rows < 0) return int(rows);
+  return expand_onehot_dispatch(bins_packed, bins_pitch_bytes, n_genes, rows_per_gene, onehot, kp,
+                                int(rows / 32), static_cast<cudaStream_t>(stream));
+}
+
+int gv_tile_m(int cta_group) {
+  if (cta_group == 1) return 128;
+  if (cta_group == 2) return 256;
+  return set_error(GV_ERR_ARG, "cta_group must be 1 or 2");
+}
+
+int64_t gv_tile_schedule(int64_t op_rows, int tile_m, int band, int32_t* out_pairs_host,
+                         int64_t capacity) {
+  if (op_rows <= 0 || (tile_m != 128 && tile_m != 256) || band < 1)
+    return set_error(GV_ERR_ARG, "bad tile schedule argument");
+  const int64_t tr = (op_rows + tile_m - 1) / tile_m;
+  const int64_t tc = (op_rows + 255) / 256;
+  int64_t n = 0;
+  for (int64_t b0 = 0; b0 < tr; b0 += band) {
+    const int64_t b1 = b0 + band < tr ? b0 + band : tr;
+    for (int64_t c = 0; c < tc; ++c) {
+      for (int64_t r = b0; r < b1; ++r) {
+        // the tile holds some pair (row <= col) iff its first row is not past its last column
+        if (r * tile_m > c * 256 + 255) continue;
+        if (out_pairs_host && n < capacity) {
+          out_pairs_host[2 * n] = int32_t(r * tile_m);
+          out_pairs_host[2 * n + 1] = int32_t(c * 256);
+        }
+        ++n;
+      }
+    }
+  }
+  return n;
+}
+
+int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
+                const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
+                const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
+                void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!onehot || !marg || !tiles || !out || n_genes <= 0 || ld_out < n_genes)
+    return set_error(GV_ERR_ARG, "gv_mi_tiles: bad argument");
+  if (sgn && ld_sgn < n_genes) return set_error(GV_ERR_ARG, "gv_mi_tiles: ld_sgn < n_genes");
+  if (op_rows < gv_onehot_rows(n_genes, rows_per_gene))
+    return set_error(GV_ERR_ARG, "gv_mi_tiles: operand has too few rows");
+  return mi_tiles_dispatch(onehot, op_rows, kp, rows_per_gene, marg, sgn, ld_sgn, n_genes, tiles,
+                           n_tiles, out, ld_out, cta_group, static_cast<cudaStream_t>(stream));
+}
+
+int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
+                 int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!operand || !tiles || !out || ld_out < op_rows) return set_error(GV_ERR_ARG, "gv_gram_dump: bad argument");
+  return gram_dump_dispatch(operand, op_rows, kp, tiles, n_tiles, out, ld_out, cta_group,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
+                    const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
+                    int n_genes, const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
+                    float* out, int64_t ld_out, int cta_group, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!val_rows || !tiles || n_genes <= 0 || op_rows < n_genes)
+    return set_error(GV_ERR_ARG, "gv_moment_tiles: bad argument");
+  if ((sgn && ld_sgn < n_genes) || (out && ld_out < n_genes))
+    return set_error(GV_ERR_ARG, "gv_moment_tiles: leading dimension < n_genes");
+  return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, tiles,
+                               n_tiles, sgn, ld_sgn, out, ld_out, cta_group,
+                               static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,556 @@
+// gv_discretize.cu -- per-gene quantile discretisation of a cells x genes CSR matrix.
+//
+// Reproduces genevector/metrics.py:25-69 (discretize_genes) bit for bit:
+//   bin 0 for x <= 0; k = min(n_bins, #unique positive values); k <= 1 -> every positive value
+//   in bin 1; else k-1 edges = np.percentile(positive values, linspace(0,100,k+1)[1:-1])
+//   (method 'linear': numpy/lib/_function_base_impl.py _quantile/_get_indexes/_lerp) and
+//   bin = 1 + #{edges <= x}  (np.searchsorted(..., side='right') + 1).
+// The arithmetic of the edges (float64, one subtraction in the input dtype, two-branch lerp,
+// separately rounded multiply and add) is restated in SURVEY.md Appendix A.
+//
+// Pipeline (all HBM/L2-bound integer work, no tensor cores):
+//   k_count_positive   CSR values -> per-gene count of x>0 (+ data flags for the co-moment path)
+//   k_scan_counts      exclusive scan -> gene_ptr (gene-major segment offsets)
+//   k_scatter          CSR (cell-major) -> gene-major (cell, value) segments, one warp per cell row
+//   k_gene_bins        one CTA per gene: 11-bit histogram + distinct-value set, multi-target MSD
+//                      radix select of the <= 2(k-1) order statistics, edges, then bin assignment:
+//                      packed 4-bit bins [G][pitch], marginals [G][16], per-gene sums, optional
+//                      INT8 value rows for the co-moment contraction
+//   k_expand_onehot    packed bins -> K-major INT8 one-hot operand rows for the tcgen05 contraction
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cfloat>
+#include "gv_internal.h"
+
+namespace gv {
+
+// ---------------------------------------------------------------- value keys
+template <typename T> struct ValKey;
+template <> struct ValKey<float> {
+  static constexpr int W = 31;   // significant key bits (sign bit of a positive float is 0)
+  __device__ static uint64_t key(float v) { return uint64_t(__float_as_uint(v)); }
+  __device__ static float val(uint64_t k) { return __uint_as_float(uint32_t(k)); }
+  __device__ static float sub(float b, float a) { return __fsub_rn(b, a); }
+};
+template <> struct ValKey<double> {
+  static constexpr int W = 63;
+  __device__ static uint64_t key(double v) { return uint64_t(__double_as_longlong(v)); }
+  __device__ static double val(uint64_t k) { return __longlong_as_double((long long)k); }
+  __device__ static double sub(double b, double a) { return __dsub_rn(b, a); }
+};
+
+// ---------------------------------------------------------------- k_count_positive
+// flags[0] |= 1 if a value is negative, |= 2 if a positive value is not an integer;
+// flags[1] = max over ceil(values) (as uint64).
+template <typename T>
+__global__ void k_count_positive(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+                                 int64_t nnz, uint32_t* __restrict__ cnt,
+                                 unsigned long long* __restrict__ flags) {
+  unsigned f = 0;
+  unsigned long long vmax = 0;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const T v = values[e];
+    if (v > T(0)) {
+      atomicAdd(&cnt[col_idx[e]], 1u);
+      const T c = ceil(v);
+      if (c != v) f |= 2u;
+      const unsigned long long ci = c < T(1.8e19) ? (unsigned long long)c : ~0ull;
+      vmax = ci > vmax ? ci : vmax;
+    } else if (v < T(0)) {
+      f |= 1u;
+    }
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  for (int d = 16; d >= 1; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, vmax, d);
+    vmax = o > vmax ? o : vmax;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (f) atomicOr(&flags[0], (unsigned long long)f);
+    if (vmax) atomicMax(&flags[1], vmax);
+  }
+}
+
+// ---------------------------------------------------------------- k_scan_counts
+// Single CTA exclusive scan of G counts into int64 offsets; also resets the cursors.
+__global__ void k_scan_counts(const uint32_t* __restrict__ cnt, int64_t* __restrict__ gene_ptr,
+                              unsigned long long* __restrict__ cursor, int G) {
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < G; base += blockDim.x) {
+    const int g = base + threadIdx.x;
+    const unsigned long long x = g < G ? cnt[g] : 0ull;
+    unsigned long long inc = x;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += y;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0ull;
+      unsigned long long winc = w;
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += y;
+      }
+      warp_tot[lane] = winc - w;   // exclusive
+    }
+    __syncthreads();
+    const unsigned long long excl = carry + warp_tot[warp] + inc - x;
+    if (g < G) { gene_ptr[g] = (int64_t)excl; cursor[g] = excl; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gene_ptr[G] = (int64_t)carry;
+}
+
+// ---------------------------------------------------------------- k_scatter
+// One warp per CSR row (cell): coalesced reads, scattered 4/8-byte writes into gene segments.
+template <typename T>
+__global__ void k_scatter(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+                          const int64_t* __restrict__ row_ptr, int64_t n_cells,
+                          unsigned long long* __restrict__ cursor, int32_t* __restrict__ g_cell,
+                          T* __restrict__ g_val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < n_cells; r += warps) {
+    const int64_t e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+      const T v = values[e];
+      if (v > T(0)) {
+        const unsigned long long pos = atomicAdd(&cursor[col_idx[e]], 1ull);
+        g_cell[pos] = int32_t(r);
+        g_val[pos] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- k_gene_bins
+constexpr int GB_THREADS = 256;
+constexpr int H0_BITS = 11;
+constexpr int H0_SIZE = 1 << H0_BITS;
+constexpr int MAX_T = 32;            // >= 2*(15-1) order statistics
+constexpr int SET_CAP = 64;          // distinct-value set capacity (n_bins <= 15)
+
+struct GeneSmem {
+  uint32_t h0[H0_SIZE];              // level-0 histogram, then its exclusive scan
+  uint32_t hs[MAX_T][256];           // per-slot digit histograms of a refinement pass
+  unsigned long long set[SET_CAP];   // distinct keys (0 = empty)
+  unsigned long long slot_prefix[MAX_T];
+  unsigned long long slot_min[MAX_T];
+  unsigned long long slot_max[MAX_T];
+  unsigned long long tgt_prefix[MAX_T];
+  unsigned long long tgt_val[MAX_T];
+  uint32_t tgt_rank[MAX_T];
+  int tgt_slot[MAX_T];
+  int tgt_done[MAX_T];
+  double edges[16];
+  uint32_t marg[16];
+  uint32_t scan_tmp[GB_THREADS];
+  unsigned long long red[GB_THREADS / 32][2];
+  int n_distinct;
+  int n_slots;
+  int n_undone;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(GB_THREADS)
+k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_cell,
+            const T* __restrict__ g_val, int G, int n_bins, const double* __restrict__ q_table,
+            uint32_t* __restrict__ bins_packed, int64_t pitch_words,
+            int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
+            double* __restrict__ edges_out, int64_t* __restrict__ gsum, int64_t* __restrict__ gsq,
+            int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode, int limb_bits,
+            int n_limbs) {
+  using K = ValKey<T>;
+  __shared__ GeneSmem sm;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const int64_t e0 = gene_ptr[g], e1 = gene_ptr[g + 1];
+    const int64_t m = e1 - e0;
+    __syncthreads();   // previous gene fully done with smem
+    if (m == 0) {
+      if (tid == 0) {
+        n_bins_per_gene[g] = 1;               // metrics.py:55-57
+        gsum[g] = 0; gsq[g] = 0;
+      }
+      if (tid < MARG_STRIDE_) marg[int64_t(g) * MARG_STRIDE_ + tid] = 0;
+      if (tid < 16) edges_out[int64_t(g) * 16 + tid] = DBL_MAX;
+      continue;
+    }
+    // ---- pass 0: level-0 histogram, distinct set, integer sums
+    for (int i = tid; i < H0_SIZE; i += GB_THREADS) sm.h0[i] = 0;
+    if (tid < SET_CAP) sm.set[tid] = 0;
+    if (tid < 16) sm.marg[tid] = 0;
+    if (tid == 0) sm.n_distinct = 0;
+    __syncthreads();
+    long long s1 = 0, s2 = 0;
+    for (int64_t e = e0 + tid; e < e1; e += GB_THREADS) {
+      const T v = g_val[e];
+      const uint64_t key = K::key(v);
+      atomicAdd(&sm.h0[uint32_t(key >> (K::W - H0_BITS))], 1u);
+      const long long xi = (long long)v;   // exact when the data are counts (flagged otherwise)
+      s1 += xi; s2 += xi * xi;
+      if (*(volatile int*)&sm.n_distinct <= n_bins) {
+        // open-addressing insert; stops mattering once more than n_bins values are known
+        uint32_t h = uint32_t((key * 0x9E3779B97F4A7C15ull) >> 58);   // 6 bits
+        for (int probe = 0; probe < SET_CAP; ++probe) {
+          const unsigned long long cur = *(volatile unsigned long long*)&sm.set[h];
+          if (cur == key) break;
+          if (cur == 0ull) {
+            const unsigned long long old = atomicCAS(&sm.set[h], 0ull, (unsigned long long)key);
+            if (old == 0ull) { atomicAdd(&sm.n_distinct, 1); break; }
+            if (old == key) break;
+          }
+          h = (h + 1) & (SET_CAP - 1);
+        }
+      }
+    }
+    // block-reduce the sums
+    for (int d = 16; d >= 1; d >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) { sm.red[warp][0] = (unsigned long long)s1; sm.red[warp][1] = (unsigned long long)s2; }
+    __syncthreads();
+    if (tid == 0) {
+      long long a = 0, b = 0;
+      for (int w = 0; w < GB_THREADS / 32; ++w) { a += (long long)sm.red[w][0]; b += (long long)sm.red[w][1]; }
+      gsum[g] = a; gsq[g] = b;
+    }
+    const int n_dist = sm.n_distinct;
+    const int k = n_dist < n_bins ? n_dist : n_bins;     // metrics.py:59
+    const int n_edges = k > 1 ? k - 1 : 0;
+    const int nt = 2 * n_edges;
+    if (tid < 16) sm.edges[tid] = DBL_MAX;
+
+    if (n_edges > 0) {
+      // ---- target ranks (numpy _get_indexes: floor(vi), floor(vi)+1, clamped at the top)
+      if (tid < nt) {
+        const int ei = tid >> 1;
+        const double q = q_table[k * 16 + ei];
+        const double vi = __dmul_rn(double(m - 1), q);
+        int64_t rank;
+        if (vi >= double(m - 1)) rank = m - 1;
+        else rank = int64_t(floor(vi)) + (tid & 1);
+        sm.tgt_rank[tid] = uint32_t(rank);
+        sm.tgt_done[tid] = 0;
+      }
+      // ---- exclusive scan of h0 (2048 = 256 threads x 8)
+      uint32_t loc[8]; uint32_t tsum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { loc[i] = sm.h0[tid * 8 + i]; tsum += loc[i]; }
+      uint32_t inc = tsum;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+      }
+      if (lane == 31) sm.scan_tmp[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t w = lane < GB_THREADS / 32 ? sm.scan_tmp[lane] : 0u;
+        uint32_t winc = w;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
+          if (lane >= d) winc += y;
+        }
+        sm.scan_tmp[lane] = winc - w;
+      }
+      __syncthreads();
+      uint32_t run = sm.scan_tmp[warp] + inc - tsum;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sm.h0[tid * 8 + i] = run; run += loc[i]; }
+      __syncthreads();
+      // ---- locate each target's level-0 bucket: largest b with excl[b] <= rank
+      if (tid < nt) {
+        const uint32_t rank = sm.tgt_rank[tid];
+        int lo = 0, hi = H0_SIZE - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (sm.h0[mid] <= rank) lo = mid; else hi = mid - 1;
+        }
+        sm.tgt_prefix[tid] = (unsigned long long)lo;
+        sm.tgt_rank[tid] = rank - sm.h0[lo];
+      }
+      __syncthreads();
+      int shift = K::W - H0_BITS;   // key bits below the current prefixes
+      while (true) {
+        // ---- group undone targets into slots by prefix
+        if (tid == 0) {
+          int ns = 0, undone = 0;
+          for (int t = 0; t < nt; ++t) {
+            if (sm.tgt_done[t]) continue;
+            ++undone;
+            int s = -1;
+            for (int u = 0; u < ns; ++u) if (sm.slot_prefix[u] == sm.tgt_prefix[t]) { s = u; break; }
+            if (s < 0) { s = ns++; sm.slot_prefix[s] = sm.tgt_prefix[t]; }
+            sm.tgt_slot[t] = s;
+          }
+          sm.n_slots = ns; sm.n_undone = undone;
+        }
+        __syncthreads();
+        if (sm.n_undone == 0) break;
+        const int ns = sm.n_slots;
+        const int width = shift < 8 ? shift : 8;
+        const int nshift = shift - width;
+        for (int i = tid; i < ns * 256; i += GB_THREADS) sm.hs[i >> 8][i & 255] = 0;
+        if (tid < ns) { sm.slot_min[tid] = ~0ull; sm.slot_max[tid] = 0ull; }
+        __syncthreads();
+        for (int64_t e = e0 + tid; e < e1; e += GB_THREADS) {
+          const uint64_t key = K::key(g_val[e]);
+          const uint64_t pre = key >> shift;
+          for (int s = 0; s < ns; ++s) {
+            if (sm.slot_prefix[s] == pre) {
+              atomicAdd(&sm.hs[s][uint32_t(key >> nshift) & ((1u << width) - 1u)], 1u);
+              atomicMin(&sm.slot_min[s], (unsigned long long)key);
+              atomicMax(&sm.slot_max[s], (unsigned long long)key);
+              break;
+            }
+          }
+        }
+        __syncthreads();
+        if (tid < nt && !sm.tgt_done[tid]) {
+          const int s = sm.tgt_slot[tid];
+          if (sm.slot_min[s] == sm.slot_max[s]) {          // bucket holds one distinct value
+            sm.tgt_val[tid] = sm.slot_min[s]; sm.tgt_done[tid] = 1;
+          } else {
+            uint32_t rank = sm.tgt_rank[tid], cum = 0; int d = 0;
+            for (; d < 255; ++d) {
+              const uint32_t c = sm.hs[s][d];
+              if (rank < cum + c) break;
+              cum += c;
+            }
+            sm.tgt_rank[tid] = rank - cum;
+            const unsigned long long np = (sm.tgt_prefix[tid] << width) | (unsigned long long)d;
+            sm.tgt_prefix[tid] = np;
+            if (nshift == 0) { sm.tgt_val[tid] = np; sm.tgt_done[tid] = 1; }
+          }
+        }
+        __syncthreads();
+        shift = nshift;
+      }
+      // ---- edges (numpy _lerp)
+      if (tid < n_edges) {
+        const double q = q_table[k * 16 + tid];
+        const double vi = __dmul_rn(double(m - 1), q);
+        const T a = K::val(sm.tgt_val[2 * tid]);
+        const T b = K::val(sm.tgt_val[2 * tid + 1]);
+        double gam;
+        if (vi >= double(m - 1)) gam = __dadd_rn(vi, 1.0);   // previous index is -1 there
+        else gam = __dsub_rn(vi, floor(vi));
+        const T d = K::sub(b, a);                            // subtraction in the input dtype
+        double e;
+        if (gam >= 0.5) e = __dsub_rn(double(b), __dmul_rn(double(d), __dsub_rn(1.0, gam)));
+        else e = __dadd_rn(double(a), __dmul_rn(double(d), gam));
+        sm.edges[tid] = e;
+      }
+    }
+    __syncthreads();
+    // ---- bin assignment: bin = 1 + #{edges <= x}; packed nibbles, marginals, value rows
+    uint32_t* brow = bins_packed + int64_t(g) * pitch_words;
+    for (int64_t e = e0 + tid; e < e1; e += GB_THREADS) {
+      const T v = g_val[e];
+      const int cell = g_cell[e];
+      const double vd = double(v);
+      int bin = 1;
+#pragma unroll
+      for (int t = 0; t < 14; ++t) bin += (t < n_edges && sm.edges[t] <= vd) ? 1 : 0;
+      atomicOr(&brow[cell >> 3], uint32_t(bin) << ((cell & 7) * 4));
+      atomicAdd(&sm.marg[bin], 1u);
+      if (val_rows != nullptr) {
+        if (val_mode == 1) {
+          val_rows[int64_t(g) * val_pitch + cell] = 1;       // detection indicator (jaccard)
+        } else {
+          const unsigned long long xi = (unsigned long long)v;
+          for (int l = 0; l < n_limbs; ++l)
+            val_rows[(int64_t(g) * n_limbs + l) * val_pitch + cell] =
+                int8_t((xi >> (l * limb_bits)) & ((1ull << limb_bits) - 1ull));
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      n_bins_per_gene[g] = (k <= 1) ? 2 : k + 1;             // metrics.py:62,67
+      marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
+    } else if (tid < 16) {
+      marg[int64_t(g) * MARG_STRIDE_ + tid] = int32_t(sm.marg[tid]);
+    }
+    if (tid < 16) edges_out[int64_t(g) * 16 + tid] = sm.edges[tid];
+  }
+}
+
+// ---------------------------------------------------------------- k_expand_onehot
+// bins_packed [G][pitch] (two cells per byte, low nibble first) -> operand rows
+// [n_blocks*32][kp] INT8, block = 32 rows = GPB genes x B bins (+ zero pad rows).
+// One warp covers 1024 cells of one 32-row block per iteration: every lane converts the 32
+// cells of its 16 packed bytes for each gene of the block and writes 32 bytes per row.
+template <int B>
+__global__ void k_expand_onehot(const uint32_t* __restrict__ bins_packed, int64_t pitch_words,
+                                int G, int8_t* __restrict__ onehot, int64_t kp, int n_blocks) {
+  constexpr int GPB = 32 / B;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int64_t chunks = kp / 1024 + ((kp % 1024) ? 1 : 0);
+  for (int blk = blockIdx.y; blk < n_blocks; blk += gridDim.y) {
+    for (int64_t ch = int64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); ch < chunks;
+         ch += int64_t(gridDim.x) * warps_per_cta) {
+      const int64_t cell0 = ch * 1024 + lane * 32;     // first of this lane's 32 cells
+      if (cell0 >= kp) continue;
+      int8_t* obase = onehot + int64_t(blk) * 32 * kp + cell0;
+#pragma unroll
+      for (int sj = 0; sj < GPB; ++sj) {
+        const int g = blk * GPB + sj;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (g < G && (cell0 >> 3) + 3 < pitch_words)
+          w = *reinterpret_cast<const uint4*>(bins_packed + int64_t(g) * pitch_words + (cell0 >> 3));
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        // bytes of 8 cells each, in cell order
+        uint32_t cells[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t lo = ws[i] & 0x0F0F0F0Fu, hi = (ws[i] >> 4) & 0x0F0F0F0Fu;
+          cells[2 * i] = __byte_perm(lo, hi, 0x5140);
+          cells[2 * i + 1] = __byte_perm(lo, hi, 0x7362);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const uint32_t pat = uint32_t(b + 1) * 0x01010101u;
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __vcmpeq4(cells[i], pat) & 0x01010101u;
+          int8_t* orow = obase + int64_t(sj * B + b) * kp;
+          *reinterpret_cast<uint4*>(orow) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(orow + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      // zero pad rows of the block
+#pragma unroll
+      for (int r = GPB * B; r < 32; ++r) {
+        int8_t* orow = obase + int64_t(r) * kp;
+        *reinterpret_cast<uint4*>(orow) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(orow + 16) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+// ================================================================ host-side launchers
+#define GV_LAUNCH_CHECK()                                     \
+  do {                                                        \
+    cudaError_t e_ = cudaGetLastError();                      \
+    if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
+  const int G = a.n_genes;
+  // workspace carve-up (all 256-byte aligned)
+  uint8_t* ws = static_cast<uint8_t*>(a.workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = ws + off; off += (bytes + 255) & ~size_t(255); return p; };
+  uint32_t* cnt = static_cast<uint32_t*>(take(size_t(G) * 4));
+  unsigned long long* cursor = static_cast<unsigned long long*>(take(size_t(G) * 8));
+  int64_t* gene_ptr = static_cast<int64_t*>(take(size_t(G + 1) * 8));
+  unsigned long long* flags = static_cast<unsigned long long*>(take(64));
+  double* qtab = static_cast<double*>(take(16 * 16 * 8));
+  int32_t* g_cell = static_cast<int32_t*>(take(size_t(a.nnz) * 4));
+  T* g_val = static_cast<T*>(take(size_t(a.nnz) * sizeof(T)));
+  if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
+
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(cnt, 0, size_t(G) * 4, st)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  if ((e = cudaMemsetAsync(flags, 0, 64, st)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  if ((e = cudaMemcpyAsync(qtab, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return set_cuda_error(e, __FILE__, __LINE__);
+  if ((e = cudaMemsetAsync(a.bins_packed, 0, size_t(G) * a.bins_pitch_bytes, st)) != cudaSuccess)
+    return set_cuda_error(e, __FILE__, __LINE__);
+
+  const T* values = static_cast<const T*>(a.values);
+  const int sms = device_sm_count();
+  if (a.nnz > 0) {
+    k_count_positive<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, cnt, flags);
+    GV_LAUNCH_CHECK();
+  }
+  k_scan_counts<<<1, 1024, 0, st>>>(cnt, gene_ptr, cursor, G);
+  GV_LAUNCH_CHECK();
+  if (a.nnz > 0) {
+    k_scatter<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, cursor, g_cell, g_val);
+    GV_LAUNCH_CHECK();
+  }
+  // data flags decide the limb layout of the value rows; read them back (one small sync)
+  unsigned long long hflags[2] = {0, 0};
+  if ((e = cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+    return set_cuda_error(e, __FILE__, __LINE__);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
+
+  int8_t* val_rows = static_cast<int8_t*>(a.val_rows);
+  int n_limbs = a.val_limbs, limb_bits = a.val_limb_bits;
+  if (val_rows != nullptr) {
+    if (a.val_mode == 0) {
+      if (hflags[0] != 0)
+        return set_error(GV_ERR_UNSUPPORTED,
+                         "co-moment path needs non-negative integer counts (negative or fractional values found)");
+      if (n_limbs < 1 || limb_bits < 1 || limb_bits > 7 ||
+          (n_limbs * limb_bits < 64 && (hflags[1] >> (n_limbs * limb_bits)) != 0))
+        return set_error(GV_ERR_UNSUPPORTED, "co-moment path: values exceed the configured limb range");
+    }
+    const size_t rows = size_t(G) * (a.val_mode == 1 ? 1 : n_limbs);
+    if ((e = cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st)) != cudaSuccess)
+      return set_cuda_error(e, __FILE__, __LINE__);
+    (void)rows;
+  }
+  k_gene_bins<T><<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, 0, st>>>(
+      gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
+      int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
+      a.val_pitch, a.val_mode, limb_bits, a.val_mode == 1 ? 1 : n_limbs);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
+int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
+  if (a.n_bins < 1 || a.n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
+  if (a.bins_pitch_bytes % 16 != 0 || int64_t(a.bins_pitch_bytes) * 2 < a.n_cells)
+    return set_error(GV_ERR_ARG, "bins pitch must be a multiple of 16 bytes covering n_cells/2");
+  if (a.value_dtype == GV_F32) return discretize_impl<float>(a, st);
+  if (a.value_dtype == GV_F64) return discretize_impl<double>(a, st);
+  return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
+}
+
+size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype) {
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t vs = value_dtype == GV_F64 ? 8 : 4;
+  return al(size_t(G) * 4) + al(size_t(G) * 8) + al(size_t(G + 1) * 8) + al(64) + al(16 * 16 * 8) +
+         al(size_t(nnz) * 4) + al(size_t(nnz) * vs) + 256;
+}
+
+int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
+                           void* onehot, int64_t kp, int n_blocks, cudaStream_t st) {
+  if (kp % 128 != 0) return set_error(GV_ERR_ARG, "expand: K extent must be a multiple of 128");
+  if (pitch_bytes % 16 != 0 || pitch_bytes * 2 < kp)
+    return set_error(GV_ERR_ARG, "expand: bins pitch must cover the padded K extent");
+  const int64_t chunks = (kp + 1023) / 1024;
+  dim3 grid((unsigned)((chunks + 7) / 8), (unsigned)(n_blocks < 65535 ? n_blocks : 65535));
+  const uint32_t* bp = static_cast<const uint32_t*>(bins_packed);
+  int8_t* oh = static_cast<int8_t*>(onehot);
+  switch (rows_per_gene) {
+    case 5:  k_expand_onehot<5><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
+    case 8:  k_expand_onehot<8><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
+    case 10: k_expand_onehot<10><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
+    case 16: k_expand_onehot<16><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
+    default: return set_error(GV_ERR_ARG, "expand: rows_per_gene must be 5, 8, 10 or 16");
+  }
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
+}  // namespace gv

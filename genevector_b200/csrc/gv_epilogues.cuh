@@ -1,0 +1,319 @@
+// gv_epilogues.cuh -- epilogue functors for gram_tiles_kernel (gv_gram.cuh).
+//
+//   DumpEpi      raw INT32 accumulators -> HBM (tests only: bit-exact joint-count check)
+//   MiEpi<B>     joint counts of (gene,bin) x (gene,bin) -> mutual information per gene pair,
+//                fused, counts never leave the SM.  Restates the per-pair body of the reference
+//                (metrics.py:74-81 _mi_from_joint, metrics.py:179-196, src/lib.rs:62-88) on the
+//                recast of SURVEY.md section 7.2: the zero-bin row/column of the joint table and the
+//                normaliser come from the per-gene marginals, only non-zero bins are contracted.
+//   MomentEpi<K> co-moment Sum_c x_ic*x_jc (or co-detection counts) -> Pearson sign / Pearson /
+//                cosine / Jaccard (metrics.py:106-111, 414-420, 452-461, 434-449)
+#pragma once
+#include "gv_gram.cuh"
+
+namespace gv {
+
+constexpr int MARG_STRIDE = 16;  // int32 per gene: [0] = #cells with x>0, [a] = #cells in bin a
+
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(GRAM_EPI_BAR), "n"(GRAM_EPI_WARPS * 32) : "memory");
+}
+
+// ------------------------------------------------------------------ DumpEpi
+struct DumpParams {
+  int32_t* out;     // [rows][ld] accumulators, row/col = operand row indices
+  int64_t ld;
+  int rows;         // operand rows (bounds)
+};
+struct DumpEpi {
+  using Params = DumpParams;
+  static constexpr size_t SMEM_BYTES = 16;
+  const Params& p;
+  __device__ DumpEpi(const Params& p_, uint8_t*) : p(p_) {}
+  __device__ void prepare(const EpiTile&) {}
+  __device__ void run(const EpiTile& et) {
+    const int row = et.row0 + et.quarter * 32 + et.lane;
+#pragma unroll 1
+    for (int cbi = 0; cbi < 4; ++cbi) {
+      const int cb = et.half * 4 + cbi;
+      uint32_t v[32];
+      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
+      tmem_ld_wait();
+      if (row < p.rows) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int col = et.col0 + cb * 32 + c;
+          if (col < p.rows) p.out[int64_t(row) * p.ld + col] = int32_t(v[c]);
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ MiEpi
+struct MiParams {
+  const int32_t* marg;   // [G][MARG_STRIDE]
+  const int8_t* sgn;     // [G][ld_sgn] Pearson sign in {-1,0,+1}, or nullptr (unsigned MI)
+  int64_t ld_sgn;
+  float* out;            // [G][ld_out] scores; (i,j) and (j,i) both written, diagonal 0
+  int64_t ld_out;
+  int G;
+};
+
+// Sum over the lanes [seg0, seg0+B) of a gene segment, result valid in lane seg0.
+template <int B, typename T>
+__device__ __forceinline__ T seg_reduce(T x, int pos) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    if (d < B) {   // compile-time prunable: B <= 16 never needs d == 16
+      const T y = __shfl_down_sync(0xffffffffu, x, d);
+      if (pos + d < B) x += y;
+    }
+  }
+  return x;
+}
+
+template <int B>
+struct MiEpi {
+  using Params = MiParams;
+  static constexpr int GPB = 32 / B;          // genes per 32-row block of the operand
+  static constexpr int ACTIVE = GPB * B;      // rows of a block that carry data
+  static constexpr int CG_PER_TILE = 8 * GPB; // column genes per tile
+  struct Meta {
+    int cm[GRAM_TILE_N];        // marginal count of the (gene,bin) behind each column
+    float cinv[GRAM_TILE_N];    // 1 / cm (0 where cm == 0)
+    int cg_nnz[CG_PER_TILE];    // #cells with x>0 per column gene (0 => skip pair)
+  };
+  static constexpr size_t SCR_INTS = 32 * 33;
+  static constexpr size_t SMEM_BYTES = sizeof(Meta) + GRAM_EPI_WARPS * SCR_INTS * 4 + 16;
+
+  const Params& p;
+  Meta* meta;
+  int* scr_all;
+  __device__ MiEpi(const Params& p_, uint8_t* smem) : p(p_) {
+    meta = reinterpret_cast<Meta*>(smem);
+    scr_all = reinterpret_cast<int*>(smem + sizeof(Meta));
+  }
+
+  // Column metadata of the tile: one epilogue thread per accumulator column.
+  __device__ void prepare(const EpiTile& et) {
+    epi_bar_sync();   // everyone is done with the previous tile's metadata
+    const int c = et.epi_tid;
+    const int within = c & 31;
+    int m = 0;
+    if (within < ACTIVE) {
+      const int sj = within / B, b = within - sj * B;
+      const int gj = ((et.col0 >> 5) + (c >> 5)) * GPB + sj;
+      if (gj < p.G) {
+        m = p.marg[int64_t(gj) * MARG_STRIDE + 1 + b];
+        if (b == 0) meta->cg_nnz[(c >> 5) * GPB + sj] = p.marg[int64_t(gj) * MARG_STRIDE];
+      } else if (b == 0) {
+        meta->cg_nnz[(c >> 5) * GPB + sj] = 0;
+      }
+    }
+    meta->cm[c] = m;
+    meta->cinv[c] = m > 0 ? 1.0f / float(m) : 0.0f;
+    epi_bar_sync();
+  }
+
+  __device__ void run(const EpiTile& et) {
+    const int lane = et.lane;
+    const bool active = lane < ACTIVE;
+    const int si = lane / B;
+    const int pos = lane - si * B;      // bin index a-1 of this row
+    const int seg0 = lane - pos;
+    const int gi = ((et.row0 >> 5) + et.quarter) * GPB + si;
+    const bool row_ok = active && gi < p.G;
+    int nnz_i = 0, m_ia = 0;
+    if (row_ok) {
+      nnz_i = p.marg[int64_t(gi) * MARG_STRIDE];
+      m_ia = p.marg[int64_t(gi) * MARG_STRIDE + 1 + pos];
+    }
+    const float inv_rx = m_ia > 0 ? 1.0f / float(m_ia) : 0.0f;
+    int* scr = scr_all + ((et.quarter + 4 * et.half) * SCR_INTS);
+
+#pragma unroll 1
+    for (int cbi = 0; cbi < 4; ++cbi) {
+      const int cb = et.half * 4 + cbi;
+      uint32_t v[32];
+      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
+      tmem_ld_wait();
+      // stage this warp's 32x32 count block for the column sums (bank = lane + c: no conflicts)
+#pragma unroll
+      for (int c = 0; c < ACTIVE; ++c) scr[lane * 33 + c] = int(v[c]);
+      __syncwarp();
+
+#pragma unroll
+      for (int sj = 0; sj < GPB; ++sj) {
+        const int cgi = cb * GPB + sj;
+        const int gj = ((et.col0 >> 5) + cb) * GPB + sj;
+        const int nnz_j = meta->cg_nnz[cgi];
+        const int colb = cb * 32 + sj * B;    // first accumulator column of gene j
+
+        // row sum over b (this row's bin a against all non-zero bins of gene j)
+        int r = 0;
+#pragma unroll
+        for (int b = 0; b < B; ++b) r += int(v[sj * B + b]);
+        // column sum over a for b = pos+1 (all non-zero bins of gene i against bin b of gene j)
+        int csum = 0;
+        if (active) {
+#pragma unroll
+          for (int a2 = 0; a2 < B; ++a2) csum += scr[(seg0 + a2) * 33 + sj * B + pos];
+        }
+        // S = #cells where both genes are non-zero; T = #cells where either is (metrics.py:124)
+        int S = seg_reduce<B>(r, pos);
+        S = __shfl_sync(0xffffffffu, S, seg0);
+        const int T = nnz_i + nnz_j - S;
+        const float Tf = float(T);
+
+        float acc = 0.0f;
+        // inner cells J[a,b], a,b >= 1: px = m_i[a]/T, py = m_j[b]/T
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const int J = int(v[sj * B + b]);
+          const float Jf = float(J);
+          const float x = (Jf * inv_rx) * (Tf * meta->cinv[colb + b]);
+          const float term = Jf * __log2f(x);
+          acc += J > 0 ? term : 0.0f;
+        }
+        // J[a,0] = m_i[a] - r : gene i in bin a, gene j zero.  py[0] = (nnz_i - S)/T
+        {
+          const int J = m_ia - r;
+          const float Jf = float(J);
+          const float x = (Jf * inv_rx) * __fdividef(Tf, float(nnz_i - S));
+          const float term = Jf * __log2f(x);
+          acc += J > 0 ? term : 0.0f;
+        }
+        // J[0,b] = m_j[b] - csum, b = pos+1 : gene i zero, gene j in bin b.  px[0] = (nnz_j - S)/T
+        {
+          const int J = meta->cm[colb + pos] - csum;
+          const float Jf = float(J);
+          const float x = __fdividef(Jf, float(nnz_j - S)) * (Tf * meta->cinv[colb + pos]);
+          const float term = Jf * __log2f(x);
+          acc += (active && J > 0) ? term : 0.0f;
+        }
+        const float total = seg_reduce<B>(acc, pos);
+
+        if (pos == 0 && row_ok && gj < p.G) {
+          if (gi < gj) {
+            float mi = (nnz_i > 0 && nnz_j > 0 && T > 0) ? total / Tf : 0.0f;
+            if (p.sgn != nullptr) mi *= float(p.sgn[int64_t(gi) * p.ld_sgn + gj]);
+            p.out[int64_t(gi) * p.ld_out + gj] = mi;
+            p.out[int64_t(gj) * p.ld_out + gi] = mi;
+          } else if (gi == gj) {
+            p.out[int64_t(gi) * p.ld_out + gi] = 0.0f;
+          }
+        }
+      }
+      __syncwarp();   // scratch is rewritten by the next column block
+    }
+  }
+};
+
+// ------------------------------------------------------------------ MomentEpi
+enum MomentKind : int { MOM_SIGN = 0, MOM_PEARSON = 1, MOM_COSINE = 2, MOM_JACCARD = 3 };
+
+struct MomentParams {
+  const int64_t* gsum;   // [G] Sum_c x            (sign / pearson / cosine)
+  const int64_t* gsq;    // [G] Sum_c x^2          (sign / pearson / cosine)
+  const int32_t* marg;   // [G][MARG_STRIDE], [0] = #cells with x>0 (jaccard)
+  int8_t* sgn;           // [G][ld_sgn]  (MOM_SIGN)
+  int64_t ld_sgn;
+  float* out;            // [G][ld_out]  (other kinds)
+  int64_t ld_out;
+  int G;
+  int64_t n_cells;
+};
+
+template <int KIND>
+struct MomentEpi {
+  using Params = MomentParams;
+  struct Meta {
+    int64_t csum[GRAM_TILE_N];
+    int64_t csq[GRAM_TILE_N];
+  };
+  static constexpr size_t SMEM_BYTES = sizeof(Meta) + 16;
+  const Params& p;
+  Meta* meta;
+  __device__ MomentEpi(const Params& p_, uint8_t* smem) : p(p_) {
+    meta = reinterpret_cast<Meta*>(smem);
+  }
+  __device__ void prepare(const EpiTile& et) {
+    epi_bar_sync();
+    const int c = et.epi_tid;
+    const int gj = et.col0 + c;
+    if constexpr (KIND == MOM_JACCARD) {
+      meta->csum[c] = gj < p.G ? int64_t(p.marg[int64_t(gj) * MARG_STRIDE]) : 0;
+      meta->csq[c] = 0;
+    } else {
+      meta->csum[c] = gj < p.G ? p.gsum[gj] : 0;
+      meta->csq[c] = gj < p.G ? p.gsq[gj] : 0;
+    }
+    epi_bar_sync();
+  }
+  __device__ void run(const EpiTile& et) {
+    const int gi = et.row0 + et.quarter * 32 + et.lane;
+    const bool row_ok = gi < p.G;
+    int64_t sx = 0, sxx = 0;
+    if (row_ok) {
+      if constexpr (KIND == MOM_JACCARD) {
+        sx = int64_t(p.marg[int64_t(gi) * MARG_STRIDE]);
+      } else {
+        sx = p.gsum[gi];
+        sxx = p.gsq[gi];
+      }
+    }
+    const int64_t n = p.n_cells;
+    const int64_t var_i = n * sxx - sx * sx;
+#pragma unroll 1
+    for (int cbi = 0; cbi < 4; ++cbi) {
+      const int cb = et.half * 4 + cbi;
+      uint32_t v[32];
+      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int cc = cb * 32 + c;
+        const int gj = et.col0 + cc;
+        if (!row_ok || gj >= p.G || gi > gj) continue;
+        const int64_t sxy = int64_t(v[c]);   // accumulators are read as unsigned 32-bit
+        const int64_t sy = meta->csum[cc];
+        if constexpr (KIND == MOM_SIGN) {
+          int8_t s = 0;
+          if (gi != gj) {
+            const int64_t syy = meta->csq[cc];
+            const int64_t var_j = n * syy - sy * sy;
+            const int64_t cov = n * sxy - sx * sy;
+            s = (var_i == 0 || var_j == 0) ? 0 : (cov > 0 ? 1 : (cov < 0 ? -1 : 0));
+          }
+          p.sgn[int64_t(gi) * p.ld_sgn + gj] = s;
+          p.sgn[int64_t(gj) * p.ld_sgn + gi] = s;
+        } else {
+          float r = 0.0f;
+          if (gi != gj) {
+            if constexpr (KIND == MOM_PEARSON) {
+              const int64_t syy = meta->csq[cc];
+              const int64_t var_j = n * syy - sy * sy;
+              const int64_t cov = n * sxy - sx * sy;
+              double q = double(cov) / sqrt(double(var_i) * double(var_j));  // 0/0 -> NaN as np.corrcoef
+              q = q > 1.0 ? 1.0 : (q < -1.0 ? -1.0 : q);
+              r = float(q);
+            } else if constexpr (KIND == MOM_COSINE) {
+              const int64_t syy = meta->csq[cc];
+              r = (sxx == 0 || syy == 0) ? 0.0f
+                                         : float(double(sxy) / sqrt(double(sxx) * double(syy)));
+            } else {  // JACCARD: float32 division of exact integers, as metrics.py:443-447
+              int64_t uni = sx + sy - sxy;
+              if (uni == 0) uni = 1;
+              r = float(sxy) / float(uni);
+            }
+          }
+          p.out[int64_t(gi) * p.ld_out + gj] = r;
+          p.out[int64_t(gj) * p.ld_out + gi] = r;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace gv

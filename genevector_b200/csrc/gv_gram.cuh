@@ -1,0 +1,204 @@
+// gv_gram.cuh -- persistent tcgen05 kernel skeleton for C = P * P^T over tiles of the
+// upper triangle, where P is a K-major INT8 operand (rows = (gene, bin) one-hot rows for the
+// MI path, or one value row per gene for the co-moment path; K = cells).
+//
+// Replaces the per-pair cell loops of the reference (genevector/metrics.py:167-174 Numba,
+// src/lib.rs:47-56 Rust, metrics.py:122-129 NumPy): one tile of INT32 accumulators in TMEM
+// holds the joint counts of (TILE_M/B x TILE_N/B) gene pairs at once.
+//
+// Structure (one CTA per SM, CG CTAs per cluster; CG=2 pairs two SMs on one 256x256 tile):
+//   warp 0      TMA producer  : operand tiles global -> shared, 128-byte K slices, SWIZZLE_128B
+//   warp 1      MMA issuer    : tcgen05.mma.kind::i8 (leader CTA only), accumulators in TMEM
+//   warp 2      TMEM allocator
+//   warps 4..11 epilogue      : tcgen05.ld the accumulators and run the Epi functor; TMEM is
+//                               double buffered so the epilogue of tile t overlaps the MMA of t+1
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue),
+// static tile schedule (tile list in global memory, cluster c takes tiles c, c+nclusters, ...).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "gv_ptx.cuh"
+
+namespace gv {
+
+constexpr int GRAM_BK = 128;           // bytes (= int8 elements) of K per pipeline stage
+constexpr int GRAM_TILE_N = 256;       // accumulator columns per tile
+constexpr int GRAM_EPI_WARPS = 8;      // warps 4..11
+constexpr int GRAM_THREADS = (4 + GRAM_EPI_WARPS) * 32;
+constexpr int GRAM_EPI_BAR = 1;        // named barrier id used by the epilogue warps
+
+template <int CG>
+struct GramCfg {
+  static constexpr int TILE_M = 128 * CG;                 // operand rows on the A side per tile
+  static constexpr int A_ROWS = 128;                      // rows of A each CTA stages
+  static constexpr int B_ROWS = GRAM_TILE_N / CG;         // rows of B each CTA stages
+  static constexpr int A_BYTES = A_ROWS * GRAM_BK;
+  static constexpr int B_BYTES = B_ROWS * GRAM_BK;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (CG == 2) ? 5 : 4;
+  static constexpr int BAR_BYTES = 256;                   // barriers + tmem pointer
+  static constexpr uint32_t IDESC = idesc_i8(TILE_M, GRAM_TILE_N, true, true);
+};
+
+// What the epilogue functor gets for one tile.
+struct EpiTile {
+  uint32_t tmem_acc;   // TMEM address of this tile's accumulator (lane 0, first column)
+  int row0;            // operand row held by TMEM lane 0 of this CTA
+  int col0;            // operand row (of the B side) held by accumulator column 0
+  int quarter;         // lane quarter this warp may read (warp_idx % 4): lanes 32q..32q+31
+  int half;            // which half of the 8 column blocks (of 32 columns) this warp handles
+  int lane;            // lane id
+  int epi_tid;         // 0..255 within the epilogue warps
+};
+
+struct GramArgs {
+  const int2* tiles;   // (row0, col0) per tile, in operand rows; row0 % TILE_M == 0, col0 % 256 == 0
+  int n_tiles;
+  int k_blocks;        // operand K extent / 128
+};
+
+template <int CG, class Epi>
+constexpr size_t gram_smem_bytes() {
+  return 1024 + size_t(GramCfg<CG>::STAGES) * GramCfg<CG>::STAGE_BYTES + GramCfg<CG>::BAR_BYTES +
+         Epi::SMEM_BYTES;
+}
+
+template <int CG, class Epi>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
+                  const typename Epi::Params ep) {
+  using Cfg = GramCfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t bars = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+  uint8_t* epi_smem = smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int n_clusters = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), CG);   // one producer arrive per CTA of the pair (on the leader)
+      mbar_init(empty_bar(s), 1);   // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);                       // one tcgen05.commit
+      mbar_init(tempty_bar(a), CG * GRAM_EPI_WARPS);    // every epilogue warp of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
+      int s = 0; uint32_t ph = 0;
+      for (int t = cluster_id; t < ga.n_tiles; t += n_clusters) {
+        const int2 tc = ga.tiles[t];
+        const int arow = tc.x + int(rank) * Cfg::A_ROWS;
+        const int brow = tc.y + int(rank) * Cfg::B_ROWS;
+        for (int kb = 0; kb < ga.k_blocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t fb = full0 + 8u * s;   // leader's barrier (cluster address if CG==2)
+          if constexpr (CG == 2) {
+            tma_load_2d_pair(&tmap, fb, sa, kb * GRAM_BK, arow);
+            tma_load_2d_pair(&tmap, fb, sb, kb * GRAM_BK, brow);
+            if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES * CG);
+            else        mbar_arrive_cluster(fb);
+          } else {
+            tma_load_2d(&tmap, fb, sa, kb * GRAM_BK, arow);
+            // TMA boxes are at most 256 rows; B_ROWS == 256 here and the box is 128 rows
+            tma_load_2d(&tmap, fb, sb, kb * GRAM_BK, brow);
+            tma_load_2d(&tmap, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
+            mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          }
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (leader && lane == 0) {
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int t = cluster_id; t < ga.n_tiles; t += n_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc) * GRAM_TILE_N;
+        for (int kb = 0; kb < ga.k_blocks; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint64_t adesc = smem_desc_k128(sa);
+          const uint64_t bdesc = smem_desc_k128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GRAM_BK / 32; ++k) {
+            // advance 32 bytes (one K=32 step) inside the 128-byte swizzle row: +2 in the
+            // 16-byte-granular start-address field
+            mma_i8<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
+                       (kb | k) != 0 ? 1u : 0u);
+          }
+          mma_commit<CG>(empty_bar(s));                       // frees the smem slot (both CTAs)
+          if (kb == ga.k_blocks - 1) mma_commit<CG>(tfull_bar(acc));  // accumulator ready
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    EpiTile et;
+    et.quarter = warp & 3;
+    et.half = ew >> 2;
+    et.lane = lane;
+    et.epi_tid = ew * 32 + lane;
+    const uint32_t tempty0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);
+    Epi epi(ep, epi_smem);
+    int it = 0;
+    for (int t = cluster_id; t < ga.n_tiles; t += n_clusters, ++it) {
+      const int2 tc = ga.tiles[t];
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1u;
+      et.row0 = tc.x + int(rank) * 128;
+      et.col0 = tc.y;
+      et.tmem_acc = tmem_base + uint32_t(acc) * GRAM_TILE_N;
+      epi.prepare(et);                       // tile metadata -> smem (overlaps the MMA)
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      epi.run(et);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0 + 8u * acc);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+}  // namespace gv

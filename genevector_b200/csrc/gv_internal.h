@@ -1,0 +1,35 @@
+// gv_internal.h -- declarations shared by the translation units of libgvb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include "../../include/gvb200.h"
+
+namespace gv {
+
+constexpr int MARG_STRIDE_ = 16;   // must equal MARG_STRIDE in gv_epilogues.cuh / GV_MARG_STRIDE
+
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* file, int line);
+int device_sm_count();
+
+struct DiscretizeArgs {
+  const void* values; int value_dtype;
+  const int32_t* col_idx; const int64_t* row_ptr;
+  int64_t n_cells; int n_genes; int64_t nnz; int n_bins;
+  const double* q_table;            // host, [16][16]
+  void* bins_packed; int64_t bins_pitch_bytes;
+  int32_t* n_bins_per_gene; int32_t* marg; double* edges;
+  int64_t* gsum; int64_t* gsq;
+  void* val_rows; int64_t val_pitch; int64_t val_rows_alloc;
+  int val_mode; int val_limbs; int val_limb_bits;
+  uint64_t* data_flags_out;         // host, [2]
+  void* workspace; size_t workspace_bytes;
+};
+
+int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st);
+size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype);
+int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
+                           void* onehot, int64_t kp, int n_blocks, cudaStream_t st);
+
+}  // namespace gv

@@ -1,0 +1,140 @@
+// gv_tiles.cu -- host launchers for the tcgen05 tile kernels (gv_gram.cuh + gv_epilogues.cuh):
+// TMA tensor map of the K-major INT8 operand, cluster launch, template dispatch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include "gv_internal.h"
+#include "gv_epilogues.cuh"
+
+namespace gv {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D map over operand[op_rows][kp] (uint8), box = 128 bytes of K x 128 rows, SWIZZLE_128B.
+static int make_operand_map(CUtensorMap* map, const void* operand, int64_t op_rows, int64_t kp) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(GV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (kp % 128 != 0 || kp <= 0) return set_error(GV_ERR_ARG, "operand K extent must be a positive multiple of 128");
+  if ((reinterpret_cast<uintptr_t>(operand) & 127) != 0)
+    return set_error(GV_ERR_ARG, "operand must be 128-byte aligned");
+  cuuint64_t dims[2] = {cuuint64_t(kp), cuuint64_t(op_rows)};
+  cuuint64_t strides[1] = {cuuint64_t(kp)};
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(operand), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(GV_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return GV_OK;
+}
+
+template <int CG, class Epi>
+static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
+                       int64_t n_tiles, const typename Epi::Params& ep, cudaStream_t st) {
+  if (n_tiles <= 0) return GV_OK;
+  CUtensorMap map;
+  int rc = make_operand_map(&map, operand, op_rows, kp);
+  if (rc != GV_OK) return rc;
+  GramArgs ga;
+  ga.tiles = reinterpret_cast<const int2*>(tiles);
+  ga.n_tiles = int(n_tiles);
+  ga.k_blocks = int(kp / GRAM_BK);
+  auto kern = gram_tiles_kernel<CG, Epi>;
+  const size_t smem = gram_smem_bytes<CG, Epi>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  const int sms = device_sm_count();
+  int64_t clusters = sms / CG;
+  if (clusters > n_tiles) clusters = n_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(unsigned(clusters * CG));
+  cfg.blockDim = dim3(GRAM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, map, ga, ep);
+  if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  return GV_OK;
+}
+
+template <class Epi>
+static int launch_cg(int cta_group, const void* operand, int64_t op_rows, int64_t kp,
+                     const int32_t* tiles, int64_t n_tiles, const typename Epi::Params& ep,
+                     cudaStream_t st) {
+  if (cta_group == 2) return launch_gram<2, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, st);
+  if (cta_group == 1) return launch_gram<1, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, st);
+  return set_error(GV_ERR_ARG, "cta_group must be 1 or 2");
+}
+
+int mi_tiles_dispatch(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
+                      const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
+                      const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out,
+                      int cta_group, cudaStream_t st) {
+  MiParams p;
+  p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out; p.ld_out = ld_out; p.G = n_genes;
+  switch (rows_per_gene) {
+    case 5:  return launch_cg<MiEpi<5>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
+    case 8:  return launch_cg<MiEpi<8>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
+    case 10: return launch_cg<MiEpi<10>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
+    case 16: return launch_cg<MiEpi<16>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
+  }
+  return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10 or 16");
+}
+
+int gram_dump_dispatch(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
+                       int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group,
+                       cudaStream_t st) {
+  DumpParams p;
+  p.out = out; p.ld = ld_out; p.rows = int(op_rows);
+  return launch_cg<DumpEpi>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, st);
+}
+
+int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
+                          const int64_t* gsum, const int64_t* gsq, const int32_t* marg,
+                          int64_t n_cells, int n_genes, const int32_t* tiles, int64_t n_tiles,
+                          int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
+                          cudaStream_t st) {
+  MomentParams p;
+  p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
+  p.ld_out = ld_out; p.G = n_genes; p.n_cells = n_cells;
+  switch (kind) {
+    case GV_MOM_SIGN:
+      if (!sgn || !gsum || !gsq) return set_error(GV_ERR_ARG, "sign needs sgn, gsum, gsq");
+      return launch_cg<MomentEpi<MOM_SIGN>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+    case GV_MOM_PEARSON:
+      if (!out || !gsum || !gsq) return set_error(GV_ERR_ARG, "pearson needs out, gsum, gsq");
+      return launch_cg<MomentEpi<MOM_PEARSON>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+    case GV_MOM_COSINE:
+      if (!out || !gsum || !gsq) return set_error(GV_ERR_ARG, "cosine needs out, gsum, gsq");
+      return launch_cg<MomentEpi<MOM_COSINE>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+    case GV_MOM_JACCARD:
+      if (!out || !marg) return set_error(GV_ERR_ARG, "jaccard needs out, marg");
+      return launch_cg<MomentEpi<MOM_JACCARD>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+  }
+  return set_error(GV_ERR_ARG, "unknown moment kind");
+}
+
+}  // namespace gv

@@ -1,0 +1,139 @@
+/* gvb200.h -- C ABI of libgvb200.so: the B200 (sm_100a) all-pairs gene co-expression engine.
+ *
+ * Drop-in boundary for the hot path of nceglia/genevector (citations are into the reference):
+ *   - the FFI it replaces is genevector._rust.compute_mi_pairs(x_disc, n_bins_per_gene, corr_signs)
+ *     (src/lib.rs:9-15, stub genevector/_rust.pyi:1-5), called from compute_mi_rust
+ *     (genevector/metrics.py:312-339), plus the Python steps around it that the reference runs on
+ *     the CPU for every tier: discretize_genes (metrics.py:25-69) and the Pearson sign
+ *     (metrics.py:106-111);
+ *   - the matrix targets target_pearson / target_cosine / target_jaccard (metrics.py:414-420,
+ *     452-461, 434-449) share the same contraction.
+ *
+ * Conventions
+ *   - every function returns 0 (GV_OK) or a negative gv_status; gv_last_error() gives the text of
+ *     the last failure on the calling thread.  Nothing throws, nothing calls exit().
+ *   - all data pointers are DEVICE pointers on the current CUDA device unless the name ends in
+ *     _host.  The caller owns every buffer (PyTorch tensors are used as plain allocations); the
+ *     library allocates nothing that outlives a call.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it.  gv_discretize_csr
+ *     synchronises the stream once (it reads two data flags back); the tile functions do not.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.0 every compute
+ *     entry point fails with GV_ERR_DEVICE.
+ */
+#ifndef GVB200_H_
+#define GVB200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GV_ABI_VERSION 1
+#define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
+#define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
+#define GV_QTABLE_DIM 16  /* q_table_host is [16][16] float64 */
+
+typedef enum gv_status {
+  GV_OK = 0,
+  GV_ERR_ARG = -1,         /* bad argument (shape, alignment, range) */
+  GV_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
+  GV_ERR_DEVICE = -3,      /* not an sm_100 device */
+  GV_ERR_UNSUPPORTED = -4  /* input outside what the exact integer path covers */
+} gv_status;
+
+typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
+
+/* Score kinds of gv_moment_tiles. */
+typedef enum gv_moment_kind {
+  GV_MOM_SIGN = 0,    /* int8 sign of the Pearson correlation, np.sign(nan_to_num(corrcoef)):
+                         metrics.py:111,134 */
+  GV_MOM_PEARSON = 1, /* metrics.py:414-420 */
+  GV_MOM_COSINE = 2,  /* metrics.py:452-461 */
+  GV_MOM_JACCARD = 3  /* metrics.py:434-449 */
+} gv_moment_kind;
+
+int gv_abi_version(void);
+const char* gv_last_error(void);
+/* GV_OK iff the current device is compute capability 10.0 (B200). */
+int gv_device_check(void);
+
+/* ---------------------------------------------------------------- discretisation
+ * Replaces discretize_genes(X, n_bins) (metrics.py:25-69) for a CSR matrix [n_cells, n_genes].
+ *
+ *   values/col_idx/row_ptr : CSR arrays (canonical: no duplicate entries); value_dtype GV_F32/GV_F64
+ *   q_table_host[k][t-1]   : np.linspace(0,100,k+1)[1:-1][t-1] / 100 for k = 2..n_bins (host memory;
+ *                            numpy's own table so that the quantile fractions match bit for bit)
+ *   bins_packed            : out, uint8 [n_genes][bins_pitch_bytes]; cell c of gene g is nibble
+ *                            (c & 1) of byte c >> 1 (low nibble first); value 0..n_bins.
+ *                            bins_pitch_bytes % 16 == 0 and 2*bins_pitch_bytes >= padded K extent.
+ *   n_bins_per_gene        : out, int32 [n_genes]  (second return value of discretize_genes)
+ *   marg                   : out, int32 [n_genes][16]; [0] = #cells with x > 0, [a] = #cells in bin a
+ *   edges                  : out, float64 [n_genes][16] bin edges (unused slots = DBL_MAX)
+ *   gsum, gsq              : out, int64 [n_genes]  Sum x and Sum x^2 over cells (integer data)
+ *   val_rows (optional)    : out, int8 [val_rows_alloc][val_pitch] K-major rows for
+ *                            gv_moment_tiles: val_mode 0 = n_limbs rows per gene holding base-2^limb_bits
+ *                            digits of the counts; val_mode 1 = one 0/1 detection row per gene.
+ *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen;
+ *                            [1] = max ceil(value)
+ *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype) bytes
+ * n_bins must be in [1, 15] (bins are stored in 4 bits). */
+size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype);
+int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
+                      const int64_t* row_ptr, int64_t n_cells, int n_genes, int64_t nnz, int n_bins,
+                      const double* q_table_host, void* bins_packed, int64_t bins_pitch_bytes,
+                      int32_t* n_bins_per_gene, int32_t* marg, double* edges, int64_t* gsum,
+                      int64_t* gsq, void* val_rows, int64_t val_pitch, int64_t val_rows_alloc,
+                      int val_mode, int val_limbs, int val_limb_bits, uint64_t* data_flags_out_host,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- operand layout
+ * rows_per_gene B for a given n_bins: 5 (n_bins<=5), 8 (<=8), 10 (<=10), 16 (<=15).
+ * The one-hot operand has 32-row blocks of floor(32/B) genes x B non-zero bins (+ zero rows). */
+int gv_rows_per_gene(int n_bins);
+/* number of 32-row blocks / operand rows for n_genes */
+int64_t gv_onehot_rows(int n_genes, int rows_per_gene);
+/* packed 4-bit bins -> INT8 one-hot operand [gv_onehot_rows][kp], kp % 128 == 0 */
+int gv_expand_onehot(const void* bins_packed, int64_t bins_pitch_bytes, int n_genes,
+                     int rows_per_gene, void* onehot, int64_t kp, void* stream);
+
+/* ---------------------------------------------------------------- tile schedule (host)
+ * Upper-triangular tile list over an operand of `op_rows` rows: tiles are tile_m x 256 operand
+ * rows, ordered in bands of `band` tile rows walked column by column so that tiles running at the
+ * same time share operand panels in L2.  Writes (row0, col0) int32 pairs into out_pairs_host
+ * (capacity in pairs) and returns the number of tiles (also when capacity is too small), or a
+ * negative status.  A rank takes a contiguous slice of this list. */
+int64_t gv_tile_schedule(int64_t op_rows, int tile_m, int band, int32_t* out_pairs_host,
+                         int64_t capacity);
+/* rows per tile on the A side for a cta_group (1 -> 128, 2 -> 256) */
+int gv_tile_m(int cta_group);
+
+/* ---------------------------------------------------------------- contraction + MI epilogue
+ * Replaces the per-pair body of compute_mi_pairs (src/lib.rs:40-98) / _compute_all_mi_numba
+ * (metrics.py:147-200) for every gene pair covered by `tiles`: joint counts by tcgen05 INT8 MMA,
+ * MI in a fused fp32 epilogue.  Writes out[i][j] and out[j][i] (i<j), 0 on the diagonal and for
+ * skipped pairs (a gene without positive values: metrics.py:119-120; lib.rs:33).
+ *   sgn: optional int8 [n_genes][ld_sgn] from gv_moment_tiles(GV_MOM_SIGN); score = sign * MI
+ *        (metrics.py:132-135). */
+int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
+                const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
+                const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
+                void* stream);
+
+/* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles. */
+int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
+                 int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, void* stream);
+
+/* ---------------------------------------------------------------- co-moment targets
+ * One INT8 row per gene (val_rows from gv_discretize_csr).  kind GV_MOM_SIGN writes int8 `sgn`
+ * (both triangles, 0 on the diagonal); the other kinds write float32 `out` like gv_mi_tiles.
+ * Exact integer co-moments: requires n_cells * (2^limb_bits - 1)^2 < 2^32. */
+int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
+                    const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
+                    int n_genes, const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
+                    float* out, int64_t ld_out, int cta_group, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVB200_H_ */
