@@ -1,0 +1,87 @@
+"""ctypes binding of libgvb200.so (C ABI declared in include/gvb200.h).
+
+This is the only place the shared library is loaded.  There is no CPU fallback: if the
+library is missing the import fails with a build hint, and every compute entry point of the
+library itself refuses to run on a device that is not sm_100 (GV_ERR_DEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvb200.so")
+
+GV_OK = 0
+GV_F32, GV_F64 = 0, 1
+GV_MOM_SIGN, GV_MOM_PEARSON, GV_MOM_COSINE, GV_MOM_JACCARD = 0, 1, 2, 3
+GV_MARG_STRIDE = 16
+GV_EDGE_STRIDE = 16
+GV_QTABLE_DIM = 16
+GV_ABI_VERSION = 1
+
+
+class GvError(RuntimeError):
+    """A libgvb200 call returned a negative status."""
+
+    def __init__(self, fn: str, status: int, message: str):
+        super().__init__(f"{fn} failed with status {status}: {message}")
+        self.status = status
+
+
+_vp, _i32, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gvb200.h one to one
+SIGNATURES = {
+    "gv_abi_version": (_i32, []),
+    "gv_last_error": (C.c_char_p, []),
+    "gv_device_check": (_i32, []),
+    "gv_discretize_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
+                                 _vp, _sz, _vp]),
+    "gv_rows_per_gene": (_i32, [_i32]),
+    "gv_onehot_rows": (_i64, [_i32, _i32]),
+    "gv_expand_onehot": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "gv_tile_m": (_i32, [_i32]),
+    "gv_tile_schedule": (_i64, [_i64, _i32, _i32, _vp, _i64]),
+    "gv_mi_tiles": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
+                           _i32, _vp]),
+    "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp,
+                               _i64, _vp, _i64, _i32, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libgvb200.so once; raise ImportError with the build command if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built and there is no fallback. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C genevector_b200/csrc`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gv_abi_version() != GV_ABI_VERSION:
+        raise ImportError("libgvb200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(fn_name: str, status: int) -> int:
+    if status < 0:
+        raise GvError(fn_name, int(status), load().gv_last_error().decode("utf-8", "replace"))
+    return status
+
+
+def call(fn_name: str, *args) -> int:
+    """Call an int-returning entry point and raise GvError on a negative status."""
+    return check(fn_name, getattr(load(), fn_name)(*args))
