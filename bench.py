@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- all-pairs signed mutual information throughput (gene-pairs/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C3|C2|GxN] [--impl reference]
+
+One step = one full pass of the hot path over the synthetic count matrix of the workload:
+discretise (rank 0) -> one NCCL broadcast of the bin block (N > 1) -> one-hot expansion ->
+Pearson-sign tiles -> INT8 tcgen05 contraction with the fused MI epilogue over this rank's slice
+of the upper-triangular tile schedule.  `value` times it with the CSR already in HBM; `e2e` times
+the same through host buffers (pinned CSR -> device, result rows -> pinned host) inside the timed
+region.  Prints ONE JSON line (rank 0).  The default workload is BASELINE.json's headline
+configuration, 20,000 genes x 200,000 cells (C4), which fits one B200.
+
+--impl reference times the reference's CPU implementation of the path instead: the C/OpenMP port
+of src/lib.rs + discretize_genes + np.corrcoef (oracle/, the Rust original cannot be built here),
+all host threads, on a bounded gene sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BINS = 10
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_workload(name):
+    from genevector_b200.synth import CONFIGS
+    if name in CONFIGS:
+        g, n = CONFIGS[name]
+        return name, g, n
+    g, n = name.lower().split("x")
+    return name, int(g), int(n)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"],
+                "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        # median under load: the upper half of the samples (idle samples pull the median down)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(n_cells, n_genes_workload, steps, warmup, target_s=8.0, seed=0):
+    """The reference's CPU path (port) on a bounded gene sample of the workload, all host threads.
+    Per step: discretize_genes + np.corrcoef sign + all-pairs MI (lib.rs:30-98) on S genes x all cells."""
+    from oracle import oracle as orc
+    from genevector_b200.synth import synth_counts
+    cores = orc.num_threads()
+
+    def one_step(Xd):
+        t0 = time.perf_counter()
+        xd, nb = orc.discretize_genes_c(Xd, N_BINS)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            corr = np.nan_to_num(np.corrcoef(Xd.T), nan=0.0)
+        _, npairs = orc.mi_pairs_c(xd, nb, corr=corr, sign_mode=1)
+        return time.perf_counter() - t0
+
+    # calibrate on 48 genes, then size the sample for ~target_s per step
+    S0 = min(48, n_genes_workload)
+    X0 = synth_counts(n_cells, S0, seed=seed).toarray()
+    one_step(X0)
+    t_cal = one_step(X0)
+    rate = (S0 * (S0 - 1) / 2) / max(t_cal, 1e-6)
+    S = int(min(n_genes_workload, max(S0, min(1024, np.sqrt(2 * rate * target_s)))))
+    X = synth_counts(n_cells, S, seed=seed).toarray() if S != S0 else X0
+    for _ in range(max(warmup, 0)):
+        one_step(X)
+    times = [one_step(X) for _ in range(max(steps, 1))]
+    pairs = S * (S - 1) / 2
+    t = float(np.mean(times))
+    return {"value": pairs / t, "unit": "gene-pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{S} genes x {n_cells} cells ({int(pairs)} pairs) of the workload's generator, "
+                      f"discretize + corrcoef sign + all-pairs MI per step, mean of {len(times)} steps",
+            "ms_per_step": t * 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl, G, N = parse_workload(args.workload)
+    r = cpu_reference(N, G, args.steps, args.warmup)
+    line = {"metric": "gene-pairs/s", "value": r["value"], "unit": "gene-pairs/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{wl}: all-pairs signed MI, {G} genes x {N} cells, n_bins={N_BINS}",
+                       "note": "CPU path timed on a gene sample; pairs/s is per-pair throughput at this cell count"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "gene-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--unsigned", action="store_true", help="plain MI (no Pearson sign pass)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cta-group", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from genevector_b200.engine import Engine, CsrDevice
+    from genevector_b200.synth import synth_counts_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    signed = not args.unsigned
+    wl, G, N = parse_workload(args.workload)
+    pairs = G * (G - 1) // 2
+    eng = Engine(dev, cta_group=args.cta_group)
+
+    # ---- synthetic input: generated on rank 0's device, staged to pinned host for the e2e leg
+    csr = None
+    host = None
+    if rank == 0:
+        vals, cols, ptr = synth_counts_torch(N, G, seed=0, device=dev)
+        csr = CsrDevice(vals, cols, ptr, N, G)
+        host = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (vals, cols, ptr))
+        torch.cuda.synchronize()
+    nnz = int(csr.nnz) if csr is not None else 0
+
+    # rows of the result this rank owns (gene range spanned by its tile slice) for the D2H leg
+    B = eng.lib.gv_rows_per_gene(N_BINS)
+    op_rows = eng.lib.gv_onehot_rows(G, B)
+    tiles, n_my_tiles, n_all_tiles = eng.schedule(op_rows, rank=rank, world=world)
+    th = tiles.cpu().numpy()
+    gpb = 32 // B
+    g_lo = int(th[:, 0].min()) // 32 * gpb if n_my_tiles else 0
+    g_hi = min(G, (int(th[:, 0].max()) + eng.lib.gv_tile_m(args.cta_group)) // 32 * gpb) if n_my_tiles else 0
+    out = torch.zeros((G, G), dtype=torch.float32, device=dev)
+    res_host = torch.empty((max(g_hi - g_lo, 1), G), dtype=torch.float32, pin_memory=True)
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    operand_bytes = op_rows * ((N + 127) // 128 * 128)
+    flush_needed = operand_bytes <= 2 * L2_BYTES
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.kernel_events = []
+
+    def step_device():
+        if flush_needed:
+            flush.fill_(1)
+        eng.mi_from_csr(csr, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out)
+
+    def step_e2e():
+        if flush_needed:
+            flush.fill_(1)
+        c = None
+        if rank == 0:
+            c = CsrDevice(host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
+                          host[2].to(dev, non_blocking=True), N, G)
+        eng.mi_from_csr(c, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out)
+        if g_hi > g_lo:
+            res_host[:g_hi - g_lo].copy_(out[g_lo:g_hi], non_blocking=True)
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    eng.kernel_events = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    kev = eng.kernel_events
+    eng.kernel_events = None
+    mi_ms = [a.elapsed_time(b) for (name, a, b, _) in kev if name == "gv_mi_tiles"]
+    phase_ms = {}
+    for name, a, b, _ in kev:
+        phase_ms.setdefault(name, []).append(a.elapsed_time(b))
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # correctness guard inside the bench: the result is symmetric, finite, bounded by log2(11)
+    if rank == 0 and world == 1:
+        sub = out[:512, :512]
+        assert torch.isfinite(sub).all() and float(sub.abs().max()) <= 3.46 + 1e-3
+        assert torch.equal(sub, sub.T)
+
+    # ---- roofline of the dominant kernel (contraction + fused MI epilogue), this rank's share
+    peaks = load_peaks()
+    my_pairs_frac = n_my_tiles / max(n_all_tiles, 1)
+    alg_ops = pairs * my_pairs_frac * 2.0 * N_BINS * N_BINS * N        # 2*B^2*N per pair
+    mi_avg_ms = float(np.mean(mi_ms)) if mi_ms else float("nan")
+    achieved_tops = alg_ops / (mi_avg_ms * 1e-3) / 1e12 if mi_ms else None
+    long_step = (ms_dev / args.steps) > 500.0
+    peak_tops = 2.0 * (peaks["bf16_sustained"] if long_step else peaks["bf16_burst"])
+
+    line = {
+        "metric": "gene-pairs/s", "value": pairs / (ms_dev / args.steps * 1e-3), "unit": "gene-pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"{wl}: all-pairs {'signed ' if signed else ''}MI, {G} genes x {N} cells, "
+                               f"n_bins={N_BINS}, nnz={nnz}",
+                   "pairs": pairs, "cta_group": args.cta_group,
+                   "parallelism": f"tile-sharded x{world}, 1 broadcast" if world > 1 else "single GPU",
+                   "l2": "operand larger than L2" if not flush_needed else "L2 flushed between steps"},
+        "e2e": {"value": pairs / (ms_e2e / args.steps * 1e-3), "unit": "gene-pairs/s",
+                "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) if host else 0,
+                "d2h_bytes_per_step": int(max(g_hi - g_lo, 0) * G * 4)},
+        "gpu_launches": int(sum(k for (_, _, _, k) in kev)),
+        "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s",
+                     "frac": (achieved_tops / peak_tops) if achieved_tops else None, "traffic": None,
+                     "kernel": "gram_tiles_kernel<2, MiEpi<10>> (gv_mi_tiles)",
+                     "kernel_ms": mi_avg_ms,
+                     "peak_note": f"2 x {peaks['src']} cuBLAS bf16 ({'sustained' if long_step else 'burst'}): "
+                                  "tcgen05 kind::i8 issues at twice the bf16 rate; nominal dense INT8 is 4500",
+                     "frac_of_nominal_int8": (achieved_tops / 4500.0) if achieved_tops else None},
+        "phases_ms": {k: float(np.mean(v)) for k, v in phase_ms.items()},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(N, G, steps=1, warmup=0, target_s=10.0)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -105,7 +105,7 @@ struct MiEpi {
       const int sj = within / B, b = within - sj * B;
       const int gj = ((et.col0 >> 5) + (c >> 5)) * GPB + sj;
       if (gj < p.G) {
-        m = p.marg[int64_t(gj) * MARG_STRIDE + 1 + b];
+        if (1 + b < MARG_STRIDE) m = p.marg[int64_t(gj) * MARG_STRIDE + 1 + b];  // B=16: bin 16 never occurs
         if (b == 0) meta->cg_nnz[(c >> 5) * GPB + sj] = p.marg[int64_t(gj) * MARG_STRIDE];
       } else if (b == 0) {
         meta->cg_nnz[(c >> 5) * GPB + sj] = 0;
@@ -127,7 +127,7 @@ struct MiEpi {
     int nnz_i = 0, m_ia = 0;
     if (row_ok) {
       nnz_i = p.marg[int64_t(gi) * MARG_STRIDE];
-      m_ia = p.marg[int64_t(gi) * MARG_STRIDE + 1 + pos];
+      if (1 + pos < MARG_STRIDE) m_ia = p.marg[int64_t(gi) * MARG_STRIDE + 1 + pos];
     }
     const float inv_rx = m_ia > 0 ? 1.0f / float(m_ia) : 0.0f;
     int* scr = scr_all + ((et.quarter + 4 * et.half) * SCR_INTS);

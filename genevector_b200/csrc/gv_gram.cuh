@@ -28,7 +28,9 @@ constexpr int GRAM_EPI_WARPS = 8;      // warps 4..11
 constexpr int GRAM_THREADS = (4 + GRAM_EPI_WARPS) * 32;
 constexpr int GRAM_EPI_BAR = 1;        // named barrier id used by the epilogue warps
 
-template <int CG>
+constexpr int GRAM_SMEM_MAX = 227 * 1024;   // dynamic shared memory a CTA may opt in to on sm_100
+
+template <int CG, int EPI_SMEM_BYTES>
 struct GramCfg {
   static constexpr int TILE_M = 128 * CG;                 // operand rows on the A side per tile
   static constexpr int A_ROWS = 128;                      // rows of A each CTA stages
@@ -36,8 +38,12 @@ struct GramCfg {
   static constexpr int A_BYTES = A_ROWS * GRAM_BK;
   static constexpr int B_BYTES = B_ROWS * GRAM_BK;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (CG == 2) ? 5 : 4;
   static constexpr int BAR_BYTES = 256;                   // barriers + tmem pointer
+  // as many pipeline stages as fit next to the epilogue's scratch (1024 = alignment slack)
+  static constexpr int STAGES_FIT = (GRAM_SMEM_MAX - 1024 - BAR_BYTES - EPI_SMEM_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static_assert(STAGES >= 3, "not enough shared memory for a 3-stage operand pipeline");
+  static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier block too small");
   static constexpr uint32_t IDESC = idesc_i8(TILE_M, GRAM_TILE_N, true, true);
 };
 
@@ -60,15 +66,15 @@ struct GramArgs {
 
 template <int CG, class Epi>
 constexpr size_t gram_smem_bytes() {
-  return 1024 + size_t(GramCfg<CG>::STAGES) * GramCfg<CG>::STAGE_BYTES + GramCfg<CG>::BAR_BYTES +
-         Epi::SMEM_BYTES;
+  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES)>;
+  return 1024 + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Epi::SMEM_BYTES;
 }
 
 template <int CG, class Epi>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
                   const typename Epi::Params ep) {
-  using Cfg = GramCfg<CG>;
+  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES)>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));

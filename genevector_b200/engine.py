@@ -1,0 +1,365 @@
+"""Host orchestration of the B200 co-expression engine.
+
+Python stays the host language (as in the reference); PyTorch tensors are used only as device
+buffers and for the NCCL broadcast; every compute step is a call into libgvb200.so
+(include/gvb200.h).  No step has a CPU or PyTorch fallback.
+
+Pipeline for all-pairs (signed) MI on one rank:
+    CSR (host) --H2D--> gv_discretize_csr  -> packed 4-bit bins + marginals (+ INT8 value rows)
+                        gv_moment_tiles    -> int8 Pearson-sign matrix           (signed only)
+                        gv_expand_onehot   -> INT8 one-hot operand (K-major)
+                        gv_mi_tiles        -> float32 score matrix [G][G]
+With several ranks (one process per GPU, torch.distributed/NCCL): rank 0 discretises, one
+broadcast replicates the bin block, every rank expands locally and takes a contiguous slice of
+the upper-triangular tile schedule; no other collective.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GvError  # noqa: F401  (re-export)
+
+_A = 256  # byte alignment of the sections of the broadcast block
+
+
+def _align(n: int, a: int = _A) -> int:
+    return (n + a - 1) // a * a
+
+
+def quantile_table() -> np.ndarray:
+    """numpy's own quantile fractions (metrics.py:64 + np.percentile's division by 100)."""
+    q = np.zeros((_lib.GV_QTABLE_DIM, _lib.GV_QTABLE_DIM), dtype=np.float64)
+    for k in range(2, 16):
+        q[k, :k - 1] = np.linspace(0, 100, k + 1)[1:-1] / 100
+    return q
+
+
+def limb_bits_for(n_cells: int) -> int:
+    """Largest digit width (<= 7) whose squared maximum summed over all cells fits in uint32."""
+    for lb in range(7, 0, -1):
+        if n_cells * ((1 << lb) - 1) ** 2 < (1 << 32):
+            return lb
+    raise GvError("limb_bits_for", _lib.GV_OK - 4, f"n_cells={n_cells} too large for the exact co-moment path")
+
+
+@dataclasses.dataclass
+class CsrDevice:
+    """A cells x genes CSR matrix resident on the device."""
+    values: torch.Tensor     # float32 / float64 [nnz]
+    col_idx: torch.Tensor    # int32 [nnz]
+    row_ptr: torch.Tensor    # int64 [n_cells + 1]
+    n_cells: int
+    n_genes: int
+
+    @property
+    def nnz(self) -> int:
+        return int(self.values.numel())
+
+
+@dataclasses.dataclass
+class BinBlock:
+    """Result of the discretisation: one contiguous device buffer (the broadcast payload) with
+    typed views into it."""
+    buf: torch.Tensor            # uint8, everything below lives in here
+    n_cells: int
+    n_genes: int
+    n_bins: int
+    kp: int                      # K extent padded to 128
+    bins_pitch: int              # bytes per gene row of the packed bins
+    bins: torch.Tensor           # uint8 [G][bins_pitch]
+    marg: torch.Tensor           # int32 [G][16]
+    n_bins_per_gene: torch.Tensor  # int32 [G]
+    edges: torch.Tensor          # float64 [G][16]
+    gsum: torch.Tensor           # int64 [G]
+    gsq: torch.Tensor            # int64 [G]
+    val_rows: Optional[torch.Tensor]   # int8 [G_pad][kp] or None
+    val_mode: int                # -1 none, 0 limbs, 1 detection indicator
+    limb_bits: int
+    data_flags: tuple            # (flag bits, max value)
+
+    def x_disc(self) -> np.ndarray:
+        """Unpack to the reference's layout: int32 [n_cells][n_genes] (tests / small cases)."""
+        b = self.bins.cpu().numpy()
+        lo, hi = b & 0x0F, b >> 4
+        full = np.empty((self.n_genes, b.shape[1] * 2), dtype=np.int32)
+        full[:, 0::2], full[:, 1::2] = lo, hi
+        return np.ascontiguousarray(full[:, :self.n_cells].T)
+
+
+def block_layout(n_cells: int, n_genes: int, val_mode: int):
+    """Byte offsets of the sections of the broadcast block."""
+    kp = _align(max(n_cells, 1), 128)
+    pitch = kp // 2
+    off, lay = 0, {}
+    for name, nbytes in (("bins", n_genes * pitch), ("marg", n_genes * 16 * 4),
+                         ("nbpg", n_genes * 4), ("edges", n_genes * 16 * 8),
+                         ("gsum", n_genes * 8), ("gsq", n_genes * 8),
+                         ("val", (n_genes * kp) if val_mode >= 0 else 0)):
+        lay[name] = (off, nbytes)
+        off += _align(nbytes)
+    return kp, pitch, lay, off
+
+
+def _views(buf, n_cells, n_genes, n_bins, val_mode, limb_bits, flags=(0, 0)) -> BinBlock:
+    kp, pitch, lay, _ = block_layout(n_cells, n_genes, val_mode)
+
+    def v(name, dtype, shape):
+        o, nb = lay[name]
+        return buf[o:o + nb].view(dtype).view(*shape)
+
+    return BinBlock(
+        buf=buf, n_cells=n_cells, n_genes=n_genes, n_bins=n_bins, kp=kp, bins_pitch=pitch,
+        bins=v("bins", torch.uint8, (n_genes, pitch)), marg=v("marg", torch.int32, (n_genes, 16)),
+        n_bins_per_gene=v("nbpg", torch.int32, (n_genes,)),
+        edges=v("edges", torch.float64, (n_genes, 16)), gsum=v("gsum", torch.int64, (n_genes,)),
+        gsq=v("gsq", torch.int64, (n_genes,)),
+        val_rows=v("val", torch.int8, (n_genes, kp)) if val_mode >= 0 else None,
+        val_mode=val_mode, limb_bits=limb_bits, data_flags=flags)
+
+
+def tile_slice(op_rows: int, cta_group: int, band: int, rank: int = 0, world: int = 1):
+    """This rank's contiguous slice of the band-ordered upper-triangular tile schedule
+    (host, int32 [n,2]) and the total tile count.  Tiles cost the same (same K), so equal counts
+    are equal work; the slices are disjoint and cover the schedule."""
+    lib = _lib.load()
+    tile_m = _lib.call("gv_tile_m", cta_group)
+    n = _lib.check("gv_tile_schedule", lib.gv_tile_schedule(op_rows, tile_m, band, None, 0))
+    host = np.zeros((max(n, 1), 2), dtype=np.int32)
+    _lib.check("gv_tile_schedule", lib.gv_tile_schedule(op_rows, tile_m, band, host.ctypes.data, n))
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return np.ascontiguousarray(host[lo:hi]), n
+
+
+def broadcast_block(buf: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """The single collective of the path: replicate rank 0's bin block (NCCL over NVLink on
+    GPUs; any torch.distributed backend works, the CPU tests use gloo)."""
+    import torch.distributed as dist
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(buf[:total], src=src, group=group)
+    return buf
+
+
+class Engine:
+    """One engine per process / device."""
+
+    def __init__(self, device=None, cta_group: int = 2, band: int = 8):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise GvError("Engine", _lib.GV_OK - 3, "no CUDA device: genevector_b200 has no CPU fallback")
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.type != "cuda":
+            raise GvError("Engine", _lib.GV_OK - 3, f"device {device!r} is not a CUDA device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            _lib.call("gv_device_check")
+        self.cta_group = cta_group
+        self.band = band
+        self._sched_cache = {}
+        # bench.py sets this to a list to collect (entry point, start event, end event, kernels)
+        self.kernel_events = None
+
+    # kernels launched by each entry point (memsets / copies not counted)
+    _LAUNCHES = {"gv_discretize_csr": 4, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
+                 "gv_mi_tiles": 1, "gv_gram_dump": 1}
+
+    def _call(self, name, *args):
+        """Call a kernel-launching entry point, optionally bracketed by CUDA events recorded on
+        the launching stream."""
+        if self.kernel_events is None:
+            return _lib.call(name, *args)
+        stream = torch.cuda.current_stream(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc = _lib.call(name, *args)
+        e1.record(stream)
+        self.kernel_events.append((name, e0, e1, self._LAUNCHES.get(name, 1)))
+        return rc
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def upload_csr(self, X, pinned: bool = False) -> CsrDevice:
+        """scipy CSR (host) -> device tensors.  Integer dtypes are converted to the smallest float
+        type that holds them exactly (discretisation arithmetic is identical: see DESIGN.md)."""
+        import scipy.sparse as sp
+        X = sp.csr_matrix(X)
+        if not X.has_canonical_format:
+            X = X.copy()
+            X.sum_duplicates()
+        data = X.data
+        if data.dtype == np.float32 or data.dtype == np.float64:
+            pass
+        elif np.issubdtype(data.dtype, np.integer) or data.dtype == np.bool_:
+            big = data.size and np.abs(data).max() >= (1 << 24)
+            data = data.astype(np.float64 if big else np.float32)
+        else:
+            data = data.astype(np.float64)
+        n_cells, n_genes = X.shape
+        vals = torch.from_numpy(np.ascontiguousarray(data))
+        cols = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32))
+        ptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64))
+        if pinned:
+            vals, cols, ptr = vals.pin_memory(), cols.pin_memory(), ptr.pin_memory()
+        return CsrDevice(vals.to(self.device, non_blocking=pinned), cols.to(self.device, non_blocking=pinned),
+                         ptr.to(self.device, non_blocking=pinned), n_cells, n_genes)
+
+    def schedule(self, op_rows: int, cta_group: Optional[int] = None, rank: int = 0, world: int = 1):
+        """Device tile list (int32 [n,2]) for this rank: a contiguous slice of the band-ordered
+        upper-triangular schedule."""
+        cg = cta_group or self.cta_group
+        key = (op_rows, cg, self.band, rank, world)
+        if key not in self._sched_cache:
+            part, n = tile_slice(op_rows, cg, self.band, rank, world)
+            self._sched_cache[key] = (torch.from_numpy(part).to(self.device), len(part), n)
+        return self._sched_cache[key]
+
+    # ------------------------------------------------------------------ discretisation
+    def discretize(self, csr: CsrDevice, n_bins: int = 10, val_mode: int = -1,
+                   buf: Optional[torch.Tensor] = None) -> BinBlock:
+        """gv_discretize_csr.  val_mode: -1 no value rows, 0 count digits (sign / pearson / cosine),
+        1 detection indicator (jaccard)."""
+        if not 1 <= n_bins <= 15:
+            raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
+        with torch.cuda.device(self.device):
+            kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, val_mode)
+            if buf is None:
+                buf = torch.empty(total, dtype=torch.uint8, device=self.device)
+            assert buf.numel() >= total and buf.device == self.device
+            lb = limb_bits_for(max(csr.n_cells, 1)) if val_mode == 0 else 7
+            blk = _views(buf, csr.n_cells, csr.n_genes, n_bins, val_mode, lb)
+            dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
+            if csr.values.dtype not in (torch.float32, torch.float64):
+                raise GvError("discretize", -1, "values must be float32 or float64")
+            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            q = quantile_table()
+            flags = np.zeros(2, dtype=np.uint64)
+            vr = blk.val_rows
+            self._call("gv_discretize_csr", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(),
+                      csr.row_ptr.data_ptr(), csr.n_cells, csr.n_genes, csr.nnz, n_bins,
+                      q.ctypes.data, blk.bins.data_ptr(), pitch, blk.n_bins_per_gene.data_ptr(),
+                      blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(),
+                      blk.gsq.data_ptr(), vr.data_ptr() if vr is not None else None, kp,
+                      csr.n_genes if vr is not None else 0, max(val_mode, 0), 1, lb,
+                      flags.ctypes.data, ws.data_ptr(), ws_bytes, self._stream())
+            blk.data_flags = (int(flags[0]), int(flags[1]))
+            return blk
+
+    def expand_onehot(self, blk: BinBlock) -> tuple:
+        """gv_expand_onehot: packed bins -> INT8 one-hot operand [rows][kp]."""
+        with torch.cuda.device(self.device):
+            B = _lib.call("gv_rows_per_gene", blk.n_bins)
+            rows = _lib.check("gv_onehot_rows", self.lib.gv_onehot_rows(blk.n_genes, B))
+            onehot = torch.empty((rows, blk.kp), dtype=torch.int8, device=self.device)
+            self._call("gv_expand_onehot", blk.bins.data_ptr(), blk.bins_pitch, blk.n_genes, B,
+                      onehot.data_ptr(), blk.kp, self._stream())
+            return onehot, B
+
+    # ------------------------------------------------------------------ tile kernels
+    def gram_dump(self, operand: torch.Tensor, cta_group: Optional[int] = None) -> torch.Tensor:
+        """Test-only: raw INT32 accumulators of every scheduled tile."""
+        with torch.cuda.device(self.device):
+            cg = cta_group or self.cta_group
+            rows, kp = operand.shape
+            tiles, n, _ = self.schedule(rows, cg)
+            out = torch.zeros((rows, rows), dtype=torch.int32, device=self.device)
+            self._call("gv_gram_dump", operand.data_ptr(), rows, kp, tiles.data_ptr(), n,
+                      out.data_ptr(), rows, cg, self._stream())
+            return out
+
+    def sign_matrix(self, blk: BinBlock, rank: int = 0, world: int = 1) -> torch.Tensor:
+        """int8 [G][ld] Pearson sign from the INT8 value rows (exact integer co-moments)."""
+        assert blk.val_rows is not None and blk.val_mode == 0
+        with torch.cuda.device(self.device):
+            G = blk.n_genes
+            ld = _align(G, 16)
+            sgn = torch.zeros((G, ld), dtype=torch.int8, device=self.device)
+            tiles, n, _ = self.schedule(G, rank=rank, world=world)
+            self._call("gv_moment_tiles", _lib.GV_MOM_SIGN, blk.val_rows.data_ptr(), G, blk.kp,
+                      blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
+                      tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0, self.cta_group,
+                      self._stream())
+            return sgn
+
+    def moment_scores(self, blk: BinBlock, kind: int, out: Optional[torch.Tensor] = None,
+                      rank: int = 0, world: int = 1) -> torch.Tensor:
+        """float32 [G][G] Pearson / cosine / Jaccard matrix (zero diagonal)."""
+        assert blk.val_rows is not None
+        with torch.cuda.device(self.device):
+            G = blk.n_genes
+            if out is None:
+                out = torch.zeros((G, G), dtype=torch.float32, device=self.device)
+            tiles, n, _ = self.schedule(G, rank=rank, world=world)
+            self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), G, blk.kp,
+                      blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
+                      tiles.data_ptr(), n, None, 0, out.data_ptr(), out.stride(0), self.cta_group,
+                      self._stream())
+            return out
+
+    def mi_scores(self, blk: BinBlock, onehot: torch.Tensor, B: int,
+                  sgn: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                  rank: int = 0, world: int = 1) -> torch.Tensor:
+        """float32 [G][G] MI (times the Pearson sign when `sgn` is given)."""
+        with torch.cuda.device(self.device):
+            G = blk.n_genes
+            if out is None:
+                out = torch.zeros((G, G), dtype=torch.float32, device=self.device)
+            rows = onehot.shape[0]
+            tiles, n, _ = self.schedule(rows, rank=rank, world=world)
+            self._call("gv_mi_tiles", onehot.data_ptr(), rows, blk.kp, B, blk.marg.data_ptr(),
+                      sgn.data_ptr() if sgn is not None else None,
+                      sgn.stride(0) if sgn is not None else 0, G, tiles.data_ptr(), n,
+                      out.data_ptr(), out.stride(0), self.cta_group, self._stream())
+            return out
+
+    # ------------------------------------------------------------------ whole paths
+    def _replicate(self, blk_or_none, n_cells, n_genes, n_bins, val_mode, group) -> BinBlock:
+        """The single collective of the path: broadcast the bin block from rank 0."""
+        _, _, _, total = block_layout(n_cells, n_genes, val_mode)
+        if blk_or_none is not None:
+            buf, lb, flags = blk_or_none.buf, blk_or_none.limb_bits, blk_or_none.data_flags
+        else:
+            buf = torch.empty(total, dtype=torch.uint8, device=self.device)
+            lb = limb_bits_for(max(n_cells, 1)) if val_mode == 0 else 7
+            flags = (0, 0)
+        broadcast_block(buf, total, group)
+        return _views(buf, n_cells, n_genes, n_bins, val_mode, lb, flags)
+
+    def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
+                    signed: bool = False, rank: int = 0, world: int = 1, group=None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """All-pairs (signed) MI.  With world > 1 only rank 0 needs `csr`; each rank returns a
+        [G][G] matrix in which the entries of its own tiles are filled."""
+        val_mode = 0 if signed else -1
+        blk = self.discretize(csr, n_bins, val_mode) if rank == 0 else None
+        if world > 1:
+            blk = self._replicate(blk, n_cells, n_genes, n_bins, val_mode, group)
+        sgn = None
+        if signed:
+            # every rank computes the (cheap, 1 % of the work) full sign map: its MI tiles may
+            # need any entry of it and this keeps the path free of a second collective
+            sgn = self.sign_matrix(blk)
+        onehot, B = self.expand_onehot(blk)
+        return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world)
+
+    def target_from_csr(self, csr: CsrDevice, kind: int) -> torch.Tensor:
+        blk = self.discretize(csr, 10, 1 if kind == _lib.GV_MOM_JACCARD else 0)
+        return self.moment_scores(blk, kind)
+
+
+_engines = {}
+
+
+def get_engine(device=None) -> Engine:
+    dev = torch.device(device if device is not None else "cuda")
+    idx = dev.index if dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    key = (dev.type, idx)
+    if key not in _engines:
+        _engines[key] = Engine(device)
+    return _engines[key]

@@ -1,0 +1,132 @@
+"""genevector_b200.metrics -- the reference's operator interface for the co-expression path,
+served by the B200 engine.
+
+Mirrors genevector/metrics.py of nceglia/genevector for the part on the hot path: same names,
+same argument meaning, same error behaviour, so that `GeneVectorDataset(mi_backend="b200")`
+(data.py:320-326 forwards `backend=`) and the reference's own tests read the same:
+
+    discretize_genes(X, n_bins)                         metrics.py:25-69
+    compute_mi_b200(X, gene_names, n_bins, signed)      new tier next to compute_mi_rust (:312-339)
+    target_mi(X, gene_names, signed, backend, device, n_bins)     :381-411
+    target_pearson / target_cosine / target_jaccard     :414-420, :452-461, :434-449
+    TARGETS / register_target / get_target_function     :344-376
+
+There is one backend and no fallback: backend must be "b200" (or "auto", which here can only
+mean "b200"); the reference's CPU tier names raise the same ValueError an unknown name raises
+in the reference (metrics.py:410-411).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .engine import get_engine
+from .scores import ScoreMatrix
+
+TARGETS = {}
+
+
+def register_target(name):
+    """Decorator to register a target function (metrics.py:347-352)."""
+    def wrapper(fn):
+        TARGETS[name] = fn
+        return fn
+    return wrapper
+
+
+def get_target_function(name):
+    """Look up a registered target (metrics.py:355-376); ValueError if unknown."""
+    if name not in TARGETS:
+        available = ", ".join(sorted(TARGETS.keys()))
+        raise ValueError(f"Unknown target '{name}'. Available: {available}")
+    return TARGETS[name]
+
+
+def _device_of(device):
+    if device in (None, "cpu", "auto"):
+        return None            # the engine's current CUDA device; "cpu" cannot be honoured
+    return device
+
+
+def discretize_genes(X, n_bins=10, device=None):
+    """GPU discretisation with the reference's return convention (metrics.py:25-69):
+    (X_disc int32 [n_cells, n_genes], n_bins_per_gene int32 [n_genes])."""
+    eng = get_engine(_device_of(device))
+    csr = eng.upload_csr(X)
+    blk = eng.discretize(csr, n_bins)
+    return blk.x_disc(), blk.n_bins_per_gene.cpu().numpy()
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=True):
+    """All-pairs (signed) mutual information on B200; returns a ScoreMatrix (Mapping view with
+    the reference's dict semantics, see scores.py).
+
+    Under torch.distributed (one process per GPU) the tile space is split over the ranks after a
+    single broadcast of the bin block; with gather=True the disjoint per-rank tiles are then
+    summed onto rank 0 (result assembly, outside the hot path) and the other ranks return their
+    partial matrices."""
+    import torch
+    eng = get_engine(_device_of(device))
+    rank, world = _dist_info()
+    n_cells, n_genes = X.shape
+    if len(gene_names) != n_genes:
+        raise ValueError("gene_names must have one entry per column of X")
+    csr = eng.upload_csr(X) if rank == 0 else None
+    out = eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world)
+    if world > 1 and gather:
+        import torch.distributed as dist
+        dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize(eng.device)
+    return ScoreMatrix(out.cpu().numpy(), gene_names)
+
+
+@register_target("mi")
+def target_mi(X, gene_names, signed=False, backend="b200", device="cuda", n_bins=10, **kwargs):
+    """Mutual information, optionally signed by the Pearson correlation (metrics.py:381-411)."""
+    if backend in ("b200", "auto"):
+        return compute_mi_b200(X, gene_names, n_bins=n_bins, signed=signed, device=device)
+    raise ValueError(f"Unknown MI backend: {backend}")
+
+
+def _moment_target(X, gene_names, kind, device=None):
+    import torch
+    eng = get_engine(_device_of(device))
+    if len(gene_names) != X.shape[1]:
+        raise ValueError("gene_names must have one entry per column of X")
+    csr = eng.upload_csr(X)
+    out = eng.target_from_csr(csr, kind)
+    torch.cuda.synchronize(eng.device)
+    return ScoreMatrix(out.cpu().numpy(), gene_names)
+
+
+@register_target("pearson")
+def target_pearson(X, gene_names, device=None, **kwargs):
+    """Pearson correlation between all gene pairs (metrics.py:414-420)."""
+    return _moment_target(X, gene_names, _lib.GV_MOM_PEARSON, device)
+
+
+@register_target("jaccard")
+def target_jaccard(X, gene_names, device=None, **kwargs):
+    """Jaccard index on detected / not detected (metrics.py:434-449)."""
+    return _moment_target(X, gene_names, _lib.GV_MOM_JACCARD, device)
+
+
+@register_target("cosine")
+def target_cosine(X, gene_names, device=None, **kwargs):
+    """Cosine similarity between gene vectors (metrics.py:452-461)."""
+    return _moment_target(X, gene_names, _lib.GV_MOM_COSINE, device)
+
+
+def install_into_reference(ref_metrics_module):
+    """Plug the B200 tier into an imported `genevector.metrics`: overrides the
+    registry entries through the reference's own register_target hook."""
+    for name in ("mi", "pearson", "cosine", "jaccard"):
+        ref_metrics_module.register_target(name)(TARGETS[name])
+    return ref_metrics_module

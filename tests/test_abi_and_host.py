@@ -1,0 +1,143 @@
+"""CPU tests of the boundary and the host logic: the C-ABI library loads and exports every
+symbol include/gvb200.h declares, fails loudly without a B200, and the host-side pieces (tile
+schedule, broadcast block layout, ScoreMatrix, score-building fast paths) behave."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from genevector_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "gvb200.h")).read()
+    declared = set(re.findall(r"\b(gv_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gv_status", "gv_dtype", "gv_moment_kind"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gv_abi_version() == _lib.GV_ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point refuses; nothing routes to the oracle."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from genevector_b200 import _lib
+    from genevector_b200.engine import Engine, GvError
+    lib = _lib.load()
+    assert lib.gv_device_check() < 0 and lib.gv_last_error()
+    with pytest.raises(GvError):
+        Engine()
+    src = "".join(open(os.path.join(ROOT, "genevector_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "genevector_b200")) if f.endswith(".py"))
+    assert "oracle" not in src.replace("oracle/", "")   # the product never imports the oracle
+
+
+def test_argument_checks_do_not_need_a_gpu():
+    from genevector_b200 import _lib
+    lib = _lib.load()
+    assert lib.gv_rows_per_gene(10) == 10 and lib.gv_rows_per_gene(5) == 5
+    assert lib.gv_rows_per_gene(7) == 8 and lib.gv_rows_per_gene(15) == 16
+    assert lib.gv_rows_per_gene(16) < 0 and b"n_bins" in lib.gv_last_error()
+    assert lib.gv_onehot_rows(20000, 10) == 6667 * 32
+    assert lib.gv_onehot_rows(7, 5) == 64
+    assert lib.gv_tile_m(1) == 128 and lib.gv_tile_m(2) == 256 and lib.gv_tile_m(3) < 0
+
+
+@pytest.mark.parametrize("op_rows,tile_m,band", [(256, 256, 8), (1312, 256, 8), (5000, 256, 3),
+                                                 (1312, 128, 16), (640, 128, 1), (213376, 256, 8)])
+def test_tile_schedule_covers_upper_triangle_once(op_rows, tile_m, band):
+    from genevector_b200 import _lib
+    lib = _lib.load()
+    n = lib.gv_tile_schedule(op_rows, tile_m, band, None, 0)
+    tiles = np.zeros((n, 2), dtype=np.int32)
+    assert lib.gv_tile_schedule(op_rows, tile_m, band, tiles.ctypes.data, n) == n
+    keys = tiles[:, 0].astype(np.int64) * (1 << 32) + tiles[:, 1]
+    assert len(np.unique(keys)) == n                      # no tile twice
+    assert np.all(tiles[:, 0] % tile_m == 0) and np.all(tiles[:, 1] % 256 == 0)
+    tr, tc = -(-op_rows // tile_m), -(-op_rows // 256)
+    r, c = np.meshgrid(np.arange(tr), np.arange(tc), indexing="ij")
+    need = r * tile_m <= c * 256 + 255                    # tile holds some (row <= col)
+    assert n == int(need.sum())
+    got = np.zeros_like(need)
+    got[tiles[:, 0] // tile_m, tiles[:, 1] // 256] = True
+    assert np.array_equal(got, need)
+    if op_rows <= 5000:
+        # every (row <= col) operand pair is inside exactly one scheduled tile
+        cover = np.zeros((op_rows, op_rows), dtype=np.int8)
+        for r0, c0 in tiles:
+            cover[r0:r0 + tile_m, c0:c0 + 256] += 1
+        iu = np.triu_indices(op_rows)
+        assert np.all(cover[iu] == 1)
+    # L2 locality: tiles that run together (148/2 clusters) touch few distinct panels
+    if n >= 74 * 4 and tile_m == 256 and band == 8:
+        w = tiles[74:148]
+        assert len(np.unique(w[:, 0])) + len(np.unique(w[:, 1])) <= 24
+
+
+def test_rank_slices_partition_the_schedule():
+    from genevector_b200 import _lib
+    lib = _lib.load()
+    n = lib.gv_tile_schedule(20000, 256, 8, None, 0)
+    for world in (1, 2, 4, 8):
+        bounds = [((n * r) // world, (n * (r + 1)) // world) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == n
+        assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+        sizes = [b - a for a, b in bounds]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_block_layout_and_limbs():
+    from genevector_b200.engine import block_layout, limb_bits_for, quantile_table
+    kp, pitch, lay, total = block_layout(5000, 2000, 0)
+    assert kp == 5120 and pitch == 2560 and pitch % 16 == 0
+    offs = sorted(lay.values())
+    for (o1, n1), (o2, _) in zip(offs, offs[1:]):
+        assert o1 % 256 == 0 and o1 + n1 <= o2
+    assert total >= offs[-1][0] + offs[-1][1]
+    assert block_layout(5000, 2000, -1)[2]["val"][1] == 0
+    assert limb_bits_for(200000) == 7 and limb_bits_for(266287) == 7 and limb_bits_for(300000) == 6
+    q = quantile_table()
+    assert np.array_equal(q[10, :9], np.linspace(0, 100, 11)[1:-1] / 100)
+
+
+def test_score_matrix_has_the_reference_dict_semantics():
+    from genevector_b200.scores import ScoreMatrix
+    z = load_golden("ref_poisson_500x20_b5")
+    genes = [f"GENE{i}" for i in range(20)]
+    sm = ScoreMatrix(z["mi_raw"].astype(np.float32), genes)
+    ref = z["mi_signed_round5"] * 0 + z["mi_unsigned_round5"]
+    assert len(sm) == 20 and list(sm)[:2] == ["GENE0", "GENE1"]
+    assert "GENE3" in sm and "NOPE" not in sm
+    assert "GENE3" in sm["GENE2"] and "GENE2" not in sm["GENE2"]
+    assert sm["GENE2"]["GENE3"] == ref[2, 3] and sm["GENE2"]["GENE2"] == 0.0
+    assert sm["GENE2"]["NOPE"] == 0.0                          # defaultdict(float) read
+    assert len(sm["GENE0"]) == 19 and len(list(sm["GENE0"].items())) == 19
+    d = sm.to_dict()
+    assert d["GENE5"]["GENE9"] == ref[5, 9] and "GENE5" not in d["GENE5"]
+    assert np.array_equal(sm.rounded(), ref)
+    # the reference's consumer loop (data.py:383-388) over the view
+    n = len(genes)
+    M = np.zeros((n, n), dtype=np.float32)
+    for i, g1 in enumerate(genes):
+        if g1 in sm:
+            for j, g2 in enumerate(genes):
+                if i != j and g2 in sm[g1]:
+                    M[i, j] = sm[g1][g2]
+    assert np.array_equal(M, ref.astype(np.float32))
+
+
+def test_synth_generator_shape_and_density():
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(2000, 300, seed=0)
+    assert X.shape == (2000, 300) and X.dtype == np.float32 and X.indices.dtype == np.int32
+    dens = X.nnz / (2000 * 300)
+    assert 0.05 < dens < 0.2
+    assert X.data.min() >= 1 and np.array_equal(X.data, np.rint(X.data))
+    Y = synth_counts(2000, 300, seed=0)
+    assert (X != Y).nnz == 0

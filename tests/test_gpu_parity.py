@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden
+vectors generated from the reference.  Bars: bins / n_bins_per_gene /
+joint counts bit-exact; raw MI within 1e-6 absolute (fp32 epilogue vs the reference's fp64);
+rounded scores within 1e-5 (+1e-6: a 1e-7 difference can flip the fifth decimal); Pearson sign
+equal wherever the covariance is not exactly zero."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+MI_TOL = 1e-6          # north_star: MI / signed MI within 1e-6 absolute
+ROUND_TOL = 1.1e-5     # 5-dp rounding of two values 1e-6 apart can differ by one unit
+
+
+def onehot_row(g, a, B):
+    gpb = 32 // B
+    return (g // gpb) * 32 + (g % gpb) * B + (a - 1)
+
+
+# ------------------------------------------------------------------ discretisation
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_discretize_bit_exact_vs_reference(engine, case):
+    z = load_golden(case)
+    csr = engine.upload_csr(z["X"])
+    blk = engine.discretize(csr, z["n_bins"])
+    got = blk.x_disc()
+    want = z["x_disc"].astype(np.int32)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"{len(bad)} bins differ, first {bad[:5].tolist()}"
+    assert np.array_equal(blk.n_bins_per_gene.cpu().numpy(), z["n_bins_per_gene"])
+    # edges: float64, identical bits (unused slots differ: oracle uses +inf)
+    e_got, e_want = blk.edges.cpu().numpy(), z["edges"]
+    for g, nb in enumerate(z["n_bins_per_gene"]):
+        ne = max(int(nb) - 2, 0)
+        assert np.array_equal(e_got[g, :ne], e_want[g, :ne]), (g, e_got[g, :ne], e_want[g, :ne])
+    # marginals: bin counts and the non-zero count
+    marg = blk.marg.cpu().numpy()
+    for a in range(1, 16):
+        assert np.array_equal(marg[:, a], (want == a).sum(axis=0)), a
+    assert np.array_equal(marg[:, 0], (want > 0).sum(axis=0))
+
+
+def test_discretize_matches_reference_api(engine):
+    """Same checks as the reference's tests/test_metrics.py:23-31 through the mirrored API."""
+    from genevector_b200.metrics import discretize_genes
+    z = load_golden("ref_poisson_500x50_b10")
+    X_disc, n_bins = discretize_genes(z["X"], n_bins=10)
+    assert X_disc.shape == z["X"].shape and len(n_bins) == z["X"].shape[1]
+    assert X_disc.dtype == np.int32
+    assert np.all(X_disc[np.asarray(z["X"].todense()) == 0] == 0)
+
+
+# ------------------------------------------------------------------ joint counts
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "ref_poisson_500x20_b5",
+                                  "synth_counts_700x96_b10", "synth_counts_400x30_b15"])
+def test_joint_counts_bit_exact(engine, case, cg):
+    """Raw tcgen05 accumulators == the reference's joint histogram (non-zero bins) for every
+    gene pair, and the zero-bin row/column + total follow from the marginals exactly."""
+    from oracle import oracle as orc
+    z = load_golden(case)
+    csr = engine.upload_csr(z["X"])
+    blk = engine.discretize(csr, z["n_bins"])
+    onehot, B = engine.expand_onehot(blk)
+    C = engine.gram_dump(onehot, cta_group=cg).cpu().numpy()
+    x_disc = z["x_disc"].astype(np.int32)
+    nb = z["n_bins_per_gene"]
+    marg = blk.marg.cpu().numpy()
+    G = x_disc.shape[1]
+    rng = np.random.default_rng(0)
+    pairs = [(i, j) for i in range(G) for j in range(i + 1, G)]
+    if len(pairs) > 600:
+        pairs = [pairs[k] for k in rng.choice(len(pairs), 600, replace=False)]
+    for i, j in pairs:
+        if nb[i] <= 1 or nb[j] <= 1:
+            continue
+        J, count = orc.joint_c(x_disc, nb, i, j)
+        rows = [onehot_row(i, a, B) for a in range(1, nb[i])]
+        cols = [onehot_row(j, b, B) for b in range(1, nb[j])]
+        Gij = C[np.ix_(rows, cols)]
+        assert np.array_equal(Gij, J[1:, 1:].astype(np.int64)), (i, j)
+        S = int(Gij.sum())
+        assert np.array_equal(marg[i, 1:nb[i]] - Gij.sum(axis=1), J[1:, 0]), (i, j)
+        assert np.array_equal(marg[j, 1:nb[j]] - Gij.sum(axis=0), J[0, 1:]), (i, j)
+        assert marg[i, 0] + marg[j, 0] - S == count and J[0, 0] == 0, (i, j)
+    for name in z:
+        if name.startswith("joint_"):
+            _, i, j = name.split("_")
+            i, j = int(i), int(j)
+            rows = [onehot_row(i, a, B) for a in range(1, nb[i])]
+            cols = [onehot_row(j, b, B) for b in range(1, nb[j])]
+            assert np.array_equal(C[np.ix_(rows, cols)], z[name][1:, 1:].astype(np.int64))
+
+
+# ------------------------------------------------------------------ MI
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_mi_matches_reference(engine, case, cg):
+    z = load_golden(case)
+    csr = engine.upload_csr(z["X"])
+    blk = engine.discretize(csr, z["n_bins"])
+    onehot, B = engine.expand_onehot(blk)
+    old = engine.cta_group
+    engine.cta_group = cg
+    try:
+        out = engine.mi_scores(blk, onehot, B).cpu().numpy().astype(np.float64)
+    finally:
+        engine.cta_group = old
+    err = np.abs(out - z["mi_raw"])
+    assert err.max() <= MI_TOL, f"max |MI - ref| = {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+    assert np.array_equal(out, out.T) and np.all(np.diag(out) == 0)
+    assert np.abs(np.round(out, 5) - z["mi_unsigned_round5"]).max() <= ROUND_TOL
+
+
+@pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "ref_poisson_500x20_b5",
+                                  "synth_counts_700x96_b10", "synth_counts_400x30_b15"])
+def test_signed_mi_matches_reference(engine, case):
+    from genevector_b200.metrics import compute_mi_b200
+    z = load_golden(case)
+    genes = [f"GENE{i}" for i in range(z["X"].shape[1])]
+    sm = compute_mi_b200(z["X"], genes, n_bins=z["n_bins"], signed=True)
+    got = sm.matrix.astype(np.float64)
+    want = z["mi_raw"] * z["corr_sign"]
+    amb = z["int_sign"] != z["corr_sign"]          # exactly-zero covariance: fp64 sign is noise
+    err = np.abs(got - want)
+    err[amb] = 0.0     # the reference's sign is rounding noise there; ours is exactly 0 by rule
+    assert err.max() <= MI_TOL, f"max err {err.max():.3e}"
+    assert np.abs(sm.rounded() - z["mi_signed_round5"])[~amb].max() <= ROUND_TOL
+    # mapping semantics the reference's consumers rely on (data.py:383-388)
+    assert genes[0] in sm and genes[1] in sm[genes[0]] and genes[0] not in sm[genes[0]]
+    assert abs(sm[genes[0]][genes[1]] - z["mi_signed_round5"][0, 1]) <= ROUND_TOL
+
+
+def test_sign_matrix_exact(engine):
+    z = load_golden("synth_counts_700x96_b10")
+    csr = engine.upload_csr(z["X"])
+    blk = engine.discretize(csr, 10, val_mode=0)
+    sgn = engine.sign_matrix(blk).cpu().numpy()[:, :96]
+    assert np.array_equal(sgn, z["int_sign"])
+
+
+# ------------------------------------------------------------------ matrix targets
+@pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "synth_counts_700x96_b10"])
+def test_matrix_targets_match_reference(engine, case):
+    from genevector_b200.metrics import target_pearson, target_cosine, target_jaccard
+    from oracle import oracle as orc
+    z = load_golden(case)
+    genes = [f"GENE{i}" for i in range(z["X"].shape[1])]
+    p = target_pearson(z["X"], genes)
+    assert np.allclose(p.rounded(), z["pearson"], atol=ROUND_TOL, equal_nan=True)
+    assert np.array_equal(np.isnan(p.rounded()), np.isnan(z["pearson"]))
+    c = target_cosine(z["X"], genes)
+    assert np.abs(c.rounded() - z["cosine"]).max() <= ROUND_TOL
+    j = target_jaccard(z["X"], genes)
+    assert np.abs(j.rounded() - z["jaccard"]).max() <= ROUND_TOL
+    # jaccard is a float32 quotient of exact integers on both sides: bit-exact before rounding
+    jr = orc.jaccard_np(z["X"]).astype(np.float32)
+    assert np.array_equal(j.matrix, jr)
+
+
+# ------------------------------------------------------------------ larger seeded cases vs the C oracle
+@pytest.mark.parametrize("n_cells,n_genes,n_bins,seed", [
+    (1000, 130, 10, 1),      # K not a multiple of 128, several tiles
+    (3000, 333, 10, 2),      # > 1 tile row, ragged last block
+    (2500, 64, 5, 3),        # 6 genes per 32-row block
+    (777, 50, 8, 4),
+    (129, 7, 10, 5),         # tiny
+])
+def test_mi_seeded_vs_oracle(engine, n_cells, n_genes, n_bins, seed):
+    from oracle import oracle as orc
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(n_cells, n_genes, seed=seed)
+    bins_gm, nb, _ = orc.discretize_csr_c(X, n_bins)
+    want, _ = orc.mi_pairs_gm_c(bins_gm, nb, sign=orc.sign_int_c(X))
+    csr = engine.upload_csr(X)
+    out = engine.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=True).cpu().numpy()
+    blk = engine.discretize(csr, n_bins)
+    assert np.array_equal(blk.x_disc(), bins_gm.T.astype(np.int32))
+    assert np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+    err = np.abs(out.astype(np.float64) - want)
+    assert err.max() <= MI_TOL, f"max err {err.max():.3e}"
+
+
+def test_edge_cases(engine):
+    """Empty matrix, one gene, all-zero genes, a constant gene, explicit zeros and negatives."""
+    from oracle import oracle as orc
+    # explicit zero and negative entries are 'not expressed' (metrics.py:53)
+    X = sp.csr_matrix(np.array([[0, 2, -1, 5], [1, 0, 3, 5], [2, 2, 0, 5], [0, 0, 0, 5], [4, 1, -2, 5]],
+                               dtype=np.float32))
+    X.data[0] = 0.0  # stored zero
+    xd, nb = orc.discretize_genes_np(X, 10)
+    csr = engine.upload_csr(X)
+    blk = engine.discretize(csr, 10)
+    assert np.array_equal(blk.x_disc(), xd) and np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+    want = orc.mi_matrix_np(X, 10)
+    out = engine.mi_from_csr(csr, 5, 4, n_bins=10).cpu().numpy()
+    assert np.abs(out - want).max() <= MI_TOL
+    # all-zero matrix: every gene has one bin, every pair is skipped (metrics.py:119-120)
+    Z = sp.csr_matrix((40, 9), dtype=np.float32)
+    csr = engine.upload_csr(Z)
+    blk = engine.discretize(csr, 10)
+    assert np.all(blk.n_bins_per_gene.cpu().numpy() == 1) and not blk.x_disc().any()
+    assert not engine.mi_from_csr(csr, 40, 9).cpu().numpy().any()
+    # a single gene: no pairs
+    one = sp.csr_matrix(np.arange(10, dtype=np.float32).reshape(10, 1))
+    csr = engine.upload_csr(one)
+    assert engine.mi_from_csr(csr, 10, 1).cpu().numpy().shape == (1, 1)
+
+
+def test_backend_dispatch_errors():
+    """Unknown backends raise like the reference (metrics.py:410-411); no CPU tiers exist."""
+    from genevector_b200.metrics import target_mi, get_target_function
+    z = load_golden("ref_poisson_500x20_b5")
+    genes = [f"GENE{i}" for i in range(20)]
+    for bad in ("numpy", "numba", "rust", "gpu", "nope"):
+        with pytest.raises(ValueError, match="Unknown MI backend"):
+            target_mi(z["X"], genes, backend=bad)
+    with pytest.raises(ValueError, match="Unknown target"):
+        get_target_function("spearman_typo")
+    sm = get_target_function("mi")(z["X"], genes, signed=False, backend="b200", device="cuda", n_bins=5)
+    assert np.abs(sm.rounded() - z["mi_unsigned_round5"]).max() <= ROUND_TOL
