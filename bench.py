@@ -76,25 +76,24 @@ class ClockSampler:
         time.sleep(0.25)
         self.proc.terminate()
         self.proc.wait()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         os.unlink(self.path)
-        # median under load: the upper half of the samples (idle samples pull the median down)
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": float(np.median(load)) if load else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+        # the sampler runs only while the timed region does, so every sample is under load
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_median": float(np.median(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------ CPU reference arm

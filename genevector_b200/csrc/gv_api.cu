@@ -47,12 +47,15 @@ static int check_device() {
 
 // implemented in gv_tiles.cu
 int mi_tiles_dispatch(const void*, int64_t, int64_t, int, const int32_t*, const int8_t*, int64_t, int,
-                      const int32_t*, int64_t, float*, int64_t, int, cudaStream_t);
+                      const int32_t*, int64_t, float*, int64_t, int, void*, cudaStream_t);
 int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, int32_t*, int64_t, int,
                        cudaStream_t);
 int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
                           const int32_t*, int64_t, int, const int32_t*, int64_t, int8_t*, int64_t,
-                          float*, int64_t, int, cudaStream_t);
+                          float*, int64_t, int, void*, cudaStream_t);
+
+int build_pairs_dispatch(const float*, int64_t, int, float, int, int, int64_t*, int64_t*, float*,
+                         cudaStream_t);
 
 }  // namespace gv
 
@@ -155,7 +158,7 @@ int64_t gv_tile_schedule(int64_t op_rows, int tile_m, int band, int32_t* out_pai
 int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
                 const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
                 const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
-                void* stream) {
+                void* sync_ws, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!onehot || !marg || !tiles || !out || n_genes <= 0 || ld_out < n_genes)
@@ -164,7 +167,7 @@ int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_ge
   if (op_rows < gv_onehot_rows(n_genes, rows_per_gene))
     return set_error(GV_ERR_ARG, "gv_mi_tiles: operand has too few rows");
   return mi_tiles_dispatch(onehot, op_rows, kp, rows_per_gene, marg, sgn, ld_sgn, n_genes, tiles,
-                           n_tiles, out, ld_out, cta_group, static_cast<cudaStream_t>(stream));
+                           n_tiles, out, ld_out, cta_group, sync_ws, static_cast<cudaStream_t>(stream));
 }
 
 int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
@@ -179,7 +182,7 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
                     int n_genes, const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
-                    float* out, int64_t ld_out, int cta_group, void* stream) {
+                    float* out, int64_t ld_out, int cta_group, void* sync_ws, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!val_rows || !tiles || n_genes <= 0 || op_rows < n_genes)
@@ -187,8 +190,19 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
   if ((sgn && ld_sgn < n_genes) || (out && ld_out < n_genes))
     return set_error(GV_ERR_ARG, "gv_moment_tiles: leading dimension < n_genes");
   return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, tiles,
-                               n_tiles, sgn, ld_sgn, out, ld_out, cta_group,
+                               n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
                                static_cast<cudaStream_t>(stream));
+}
+
+int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_genes, float c,
+                              int clamp_negative, int round5, int64_t* i_idx, int64_t* j_idx,
+                              float* xij, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!scores || !i_idx || !j_idx || !xij || n_genes < 1 || ld_scores < n_genes)
+    return set_error(GV_ERR_ARG, "gv_build_training_tensors: bad argument");
+  return build_pairs_dispatch(scores, ld_scores, n_genes, c * c, clamp_negative, round5, i_idx, j_idx,
+                              xij, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -62,6 +62,11 @@ struct GramArgs {
   const int2* tiles;   // (row0, col0) per tile, in operand rows; row0 % TILE_M == 0, col0 % 256 == 0
   int n_tiles;
   int k_blocks;        // operand K extent / 128
+  // Wave lockstep (optional, zero-initialised device counter): every cluster arrives once per
+  // wave of n_clusters tiles before loading the wave's tile, so tiles in flight walk K together
+  // and share operand panels out of L2 (without it the clusters drift apart and at 20k x 200k
+  // the kernel re-reads the operand from DRAM 380 times: profiles/r01_ncu_mi_c4_v1_nolockstep.txt).
+  unsigned int* wave_sync;
 };
 
 template <int CG, class Epi>
@@ -119,7 +124,20 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
     if (lane == 0) {
       const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
       int s = 0; uint32_t ph = 0;
-      for (int t = cluster_id; t < ga.n_tiles; t += n_clusters) {
+      unsigned int wave = 0;
+      const int n_waves = (ga.n_tiles + n_clusters - 1) / n_clusters;
+      for (int t = cluster_id; int(wave) < n_waves; t += n_clusters, ++wave) {
+        if (ga.wave_sync != nullptr && leader) {
+          // the peer's loads only fill its own stages; MMA cannot start before the leader's arrive
+          atomicAdd(ga.wave_sync, 1u);
+          const unsigned int target = unsigned(n_clusters) * (wave + 1u);
+          const uint64_t t0 = global_timer_ns();
+          while (*reinterpret_cast<volatile unsigned int*>(ga.wave_sync) < target) {
+            __nanosleep(128);
+            if (global_timer_ns() - t0 > 20000000000ull) __trap();
+          }
+        }
+        if (t >= ga.n_tiles) break;
         const int2 tc = ga.tiles[t];
         const int arow = tc.x + int(rank) * Cfg::A_ROWS;
         const int brow = tc.y + int(rank) * Cfg::B_ROWS;

@@ -46,7 +46,8 @@ static int make_operand_map(CUtensorMap* map, const void* operand, int64_t op_ro
 
 template <int CG, class Epi>
 static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
-                       int64_t n_tiles, const typename Epi::Params& ep, cudaStream_t st) {
+                       int64_t n_tiles, const typename Epi::Params& ep, void* sync_ws,
+                       cudaStream_t st) {
   if (n_tiles <= 0) return GV_OK;
   CUtensorMap map;
   int rc = make_operand_map(&map, operand, op_rows, kp);
@@ -55,6 +56,11 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
   ga.tiles = reinterpret_cast<const int2*>(tiles);
   ga.n_tiles = int(n_tiles);
   ga.k_blocks = int(kp / GRAM_BK);
+  ga.wave_sync = static_cast<unsigned int*>(sync_ws);
+  if (sync_ws != nullptr) {
+    cudaError_t e0 = cudaMemsetAsync(sync_ws, 0, 64, st);
+    if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);
+  }
   auto kern = gram_tiles_kernel<CG, Epi>;
   const size_t smem = gram_smem_bytes<CG, Epi>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -83,23 +89,23 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
 template <class Epi>
 static int launch_cg(int cta_group, const void* operand, int64_t op_rows, int64_t kp,
                      const int32_t* tiles, int64_t n_tiles, const typename Epi::Params& ep,
-                     cudaStream_t st) {
-  if (cta_group == 2) return launch_gram<2, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, st);
-  if (cta_group == 1) return launch_gram<1, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, st);
+                     void* sync_ws, cudaStream_t st) {
+  if (cta_group == 2) return launch_gram<2, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, sync_ws, st);
+  if (cta_group == 1) return launch_gram<1, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, sync_ws, st);
   return set_error(GV_ERR_ARG, "cta_group must be 1 or 2");
 }
 
 int mi_tiles_dispatch(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
                       const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
                       const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out,
-                      int cta_group, cudaStream_t st) {
+                      int cta_group, void* sync_ws, cudaStream_t st) {
   MiParams p;
   p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out; p.ld_out = ld_out; p.G = n_genes;
   switch (rows_per_gene) {
-    case 5:  return launch_cg<MiEpi<5>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
-    case 8:  return launch_cg<MiEpi<8>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
-    case 10: return launch_cg<MiEpi<10>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
-    case 16: return launch_cg<MiEpi<16>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, st);
+    case 5:  return launch_cg<MiEpi<5>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    case 8:  return launch_cg<MiEpi<8>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    case 10: return launch_cg<MiEpi<10>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    case 16: return launch_cg<MiEpi<16>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
   }
   return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10 or 16");
 }
@@ -109,30 +115,30 @@ int gram_dump_dispatch(const void* operand, int64_t op_rows, int64_t kp, const i
                        cudaStream_t st) {
   DumpParams p;
   p.out = out; p.ld = ld_out; p.rows = int(op_rows);
-  return launch_cg<DumpEpi>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, st);
+  return launch_cg<DumpEpi>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, nullptr, st);
 }
 
 int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                           const int64_t* gsum, const int64_t* gsq, const int32_t* marg,
                           int64_t n_cells, int n_genes, const int32_t* tiles, int64_t n_tiles,
                           int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
-                          cudaStream_t st) {
+                          void* sync_ws, cudaStream_t st) {
   MomentParams p;
   p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
   p.ld_out = ld_out; p.G = n_genes; p.n_cells = n_cells;
   switch (kind) {
     case GV_MOM_SIGN:
       if (!sgn || !gsum || !gsq) return set_error(GV_ERR_ARG, "sign needs sgn, gsum, gsq");
-      return launch_cg<MomentEpi<MOM_SIGN>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+      return launch_cg<MomentEpi<MOM_SIGN>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case GV_MOM_PEARSON:
       if (!out || !gsum || !gsq) return set_error(GV_ERR_ARG, "pearson needs out, gsum, gsq");
-      return launch_cg<MomentEpi<MOM_PEARSON>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+      return launch_cg<MomentEpi<MOM_PEARSON>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case GV_MOM_COSINE:
       if (!out || !gsum || !gsq) return set_error(GV_ERR_ARG, "cosine needs out, gsum, gsq");
-      return launch_cg<MomentEpi<MOM_COSINE>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+      return launch_cg<MomentEpi<MOM_COSINE>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case GV_MOM_JACCARD:
       if (!out || !marg) return set_error(GV_ERR_ARG, "jaccard needs out, marg");
-      return launch_cg<MomentEpi<MOM_JACCARD>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, st);
+      return launch_cg<MomentEpi<MOM_JACCARD>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
   }
   return set_error(GV_ERR_ARG, "unknown moment kind");
 }

@@ -160,6 +160,9 @@ class Engine:
         self.cta_group = cta_group
         self.band = band
         self._sched_cache = {}
+        # wave lockstep of the persistent tile kernels: "auto" = when the operand exceeds L2
+        self.lockstep = "auto"
+        self._sync_ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
         # bench.py sets this to a list to collect (entry point, start event, end event, kernels)
         self.kernel_events = None
 
@@ -181,6 +184,11 @@ class Engine:
         return rc
 
     # ------------------------------------------------------------------ helpers
+    def _sync_ptr(self, operand_bytes: int):
+        """Device scratch for the wave barrier, or None when the operand fits L2 anyway."""
+        on = self.lockstep is True or (self.lockstep == "auto" and operand_bytes > 96 * 1024 * 1024)
+        return self._sync_ws.data_ptr() if on else None
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -284,7 +292,7 @@ class Engine:
             self._call("gv_moment_tiles", _lib.GV_MOM_SIGN, blk.val_rows.data_ptr(), G, blk.kp,
                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
                       tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0, self.cta_group,
-                      self._stream())
+                      self._sync_ptr(G * blk.kp), self._stream())
             return sgn
 
     def moment_scores(self, blk: BinBlock, kind: int, out: Optional[torch.Tensor] = None,
@@ -299,7 +307,7 @@ class Engine:
             self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), G, blk.kp,
                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
                       tiles.data_ptr(), n, None, 0, out.data_ptr(), out.stride(0), self.cta_group,
-                      self._stream())
+                      self._sync_ptr(G * blk.kp), self._stream())
             return out
 
     def mi_scores(self, blk: BinBlock, onehot: torch.Tensor, B: int,
@@ -315,7 +323,8 @@ class Engine:
             self._call("gv_mi_tiles", onehot.data_ptr(), rows, blk.kp, B, blk.marg.data_ptr(),
                       sgn.data_ptr() if sgn is not None else None,
                       sgn.stride(0) if sgn is not None else 0, G, tiles.data_ptr(), n,
-                      out.data_ptr(), out.stride(0), self.cta_group, self._stream())
+                      out.data_ptr(), out.stride(0), self.cta_group,
+                      self._sync_ptr(rows * blk.kp), self._stream())
             return out
 
     # ------------------------------------------------------------------ whole paths

@@ -114,11 +114,15 @@ int gv_tile_m(int cta_group);
  * MI in a fused fp32 epilogue.  Writes out[i][j] and out[j][i] (i<j), 0 on the diagonal and for
  * skipped pairs (a gene without positive values: metrics.py:119-120; lib.rs:33).
  *   sgn: optional int8 [n_genes][ld_sgn] from gv_moment_tiles(GV_MOM_SIGN); score = sign * MI
- *        (metrics.py:132-135). */
+ *        (metrics.py:132-135).
+ *   sync_ws: optional >= 64 bytes of device scratch.  When given, the persistent CTA pairs run the
+ *        tile schedule in lockstep waves (one arrive per pair per wave) so that the tiles in flight
+ *        share operand panels out of L2; pass it when the operand is larger than L2, NULL otherwise.
+ *        The same buffer must not be used by two launches that can overlap. */
 int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
                 const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
                 const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
-                void* stream);
+                void* sync_ws, void* stream);
 
 /* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles. */
 int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
@@ -131,7 +135,16 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
                     int n_genes, const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
-                    float* out, int64_t ld_out, int cta_group, void* stream);
+                    float* out, int64_t ld_out, int cta_group, void* sync_ws, void* stream);
+
+/* ---------------------------------------------------------------- score-building fast path
+ * Replaces GeneVectorDataset._build_training_tensors (data.py:377-411) for a dense device score
+ * matrix: all n_genes*(n_genes-1) off-diagonal ordered pairs in row-major order,
+ * xij = float32(round5 ? round(score,5) : score) * c^2, negatives clamped to 0 when
+ * clamp_negative (unsigned training, data.py:392-393).  i_idx/j_idx int64, xij float32. */
+int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_genes, float c,
+                              int clamp_negative, int round5, int64_t* i_idx, int64_t* j_idx,
+                              float* xij, void* stream);
 
 #ifdef __cplusplus
 }

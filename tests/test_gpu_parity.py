@@ -222,3 +222,19 @@ def test_backend_dispatch_errors():
         get_target_function("spearman_typo")
     sm = get_target_function("mi")(z["X"], genes, signed=False, backend="b200", device="cuda", n_bins=5)
     assert np.abs(sm.rounded() - z["mi_unsigned_round5"]).max() <= ROUND_TOL
+
+
+def test_wave_lockstep_gives_identical_scores(engine):
+    """The wave barrier only changes when tiles start, never what they compute."""
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(2000, 700, seed=11)        # 234 blocks -> 30 tile rows, 465 tiles > 74 pairs
+    csr = engine.upload_csr(X)
+    old = engine.lockstep
+    try:
+        engine.lockstep = False
+        a = engine.mi_from_csr(csr, 2000, 700, signed=True).cpu().numpy()
+        engine.lockstep = True
+        b = engine.mi_from_csr(csr, 2000, 700, signed=True).cpu().numpy()
+    finally:
+        engine.lockstep = old
+    assert np.array_equal(a, b) and np.abs(a).max() > 0
