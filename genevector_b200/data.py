@@ -1,0 +1,77 @@
+"""genevector_b200.data -- the score-building step of GeneVectorDataset on the matrix path.
+
+Mirrors the two methods of the reference's dataset that sit on the co-expression path:
+
+    compute_target_scores(...)   = GeneVectorDataset._compute_target_scores     data.py:292-334
+    build_training_tensors(...)  = GeneVectorDataset._build_training_tensors    data.py:377-411
+
+The first dispatches to the B200 targets (with the reference's cache protocol); the second turns a
+ScoreMatrix into the (i_idx, j_idx, xij) training tensors with one CUDA kernel
+(gv_build_training_tensors) instead of the reference's double Python loop over the nested dict.
+Everything else of the dataset (Context, entropy, batching) is unchanged reference code and not
+part of this package.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import get_engine
+from .scores import ScoreMatrix
+
+
+def compute_target_scores(X, gene_names, target="mi", target_kwargs=None, signed_mi=True,
+                          mi_backend="b200", device="cuda", use_cache=False):
+    """data.py:292-334: cache probe -> target function -> cache save.  Returns a ScoreMatrix."""
+    from .metrics import get_target_function
+    target_kwargs = target_kwargs or {}
+    cache_key = None
+    if use_cache:
+        from .cache import compute_cache_key, load_scores
+        target_name = target if isinstance(target, str) else "custom"
+        cache_key = compute_cache_key(X, gene_names, target_name, target_kwargs, signed_mi)
+        cached, _ = load_scores(cache_key)
+        if cached is not None:
+            return cached
+    if callable(target):
+        scores = target(X, gene_names, **target_kwargs)
+    elif isinstance(target, str):
+        fn = get_target_function(target)
+        kwargs = {"signed": signed_mi, "backend": mi_backend, "device": device, **target_kwargs}
+        scores = fn(X, gene_names, **kwargs)
+    else:
+        raise TypeError(f"target must be str or callable, got {type(target)}")
+    if use_cache:
+        from .cache import save_scores
+        save_scores(cache_key, scores, gene_names)
+    return scores
+
+
+def build_training_tensors(scores, genes, c=100.0, signed_mi=True, device="cuda"):
+    """data.py:377-411 on the matrix path: (i_idx int64, j_idx int64, xij float32) on `device`,
+    all off-diagonal ordered pairs in row-major order, xij = round(score, 5) * c**2, negatives
+    clamped to 0 when not signed_mi.  `scores` is a ScoreMatrix (or a device/host float32 matrix
+    whose rows follow `genes`)."""
+    genes = list(genes)
+    eng = get_engine(device if device not in (None, "cpu") else None)
+    if isinstance(scores, ScoreMatrix):
+        if scores.genes != genes:
+            order = [scores._index[g] for g in genes]
+            mat = scores.matrix[np.ix_(order, order)]
+        else:
+            mat = scores.matrix
+    else:
+        mat = scores
+    m = torch.as_tensor(mat, dtype=torch.float32).to(eng.device).contiguous()
+    n = len(genes)
+    if m.shape != (n, n):
+        raise ValueError("score matrix does not match the gene list")
+    i_idx = torch.empty(n * (n - 1), dtype=torch.int64, device=eng.device)
+    j_idx = torch.empty_like(i_idx)
+    xij = torch.empty(n * (n - 1), dtype=torch.float32, device=eng.device)
+    with torch.cuda.device(eng.device):
+        _lib.call("gv_build_training_tensors", m.data_ptr(), m.stride(0), n, float(c),
+                  0 if signed_mi else 1, 1, i_idx.data_ptr(), j_idx.data_ptr(), xij.data_ptr(),
+                  torch.cuda.current_stream(eng.device).cuda_stream)
+    return i_idx, j_idx, xij

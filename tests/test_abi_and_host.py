@@ -141,3 +141,41 @@ def test_synth_generator_shape_and_density():
     assert X.data.min() >= 1 and np.array_equal(X.data, np.rint(X.data))
     Y = synth_counts(2000, 300, seed=0)
     assert (X != Y).nnz == 0
+
+
+def test_cache_roundtrip_and_key_compat(tmp_path, monkeypatch):
+    """Same key as the reference (cache.py:29-44) and a round trip through its .npz schema
+    (tests/test_cache.py:7-20 of the reference, tolerance 1e-4 there)."""
+    import hashlib, json
+    from genevector_b200 import cache
+    from genevector_b200.scores import ScoreMatrix
+    monkeypatch.setattr(cache, "CACHE_DIR", str(tmp_path))
+    z = load_golden("ref_poisson_500x20_b5")
+    genes = [f"GENE{i}" for i in range(20)]
+    key = cache.compute_cache_key(z["X"], genes, "mi", {"n_bins": 5}, True)
+    # the reference's recipe, restated
+    X = z["X"]
+    h0 = hashlib.sha256()
+    for a in (X.data, X.indices, X.indptr):
+        h0.update(np.ascontiguousarray(a).tobytes())
+    h0.update(str(X.shape).encode())
+    h = hashlib.sha256()
+    h.update(h0.hexdigest()[:16].encode())
+    h.update(json.dumps(sorted(genes)).encode())
+    h.update(b"mi")
+    h.update(json.dumps({"n_bins": 5}, sort_keys=True, default=str).encode())
+    h.update(b"True")
+    assert key == h.hexdigest()[:32] and len(key) == 32
+    assert key != cache.compute_cache_key(z["X"], genes, "pearson", {"n_bins": 5}, True)
+    sm = ScoreMatrix(z["mi_raw"].astype(np.float32), genes)
+    assert cache.load_scores(key) == (None, None)
+    path = cache.save_scores(key, sm, genes)
+    raw = np.load(path)
+    assert raw["scores"].dtype == np.float32 and raw["scores"].shape == (20, 20)
+    assert [str(g) for g in raw["genes"]] == genes
+    back, g2 = cache.load_scores(key)
+    assert g2 == genes and np.abs(back.rounded() - z["mi_unsigned_round5"]).max() < 1e-6
+    # a nested dict (what the reference passes) is accepted too
+    cache.save_scores(key + "d", sm.to_dict(), genes)
+    back2, _ = cache.load_scores(key + "d")
+    assert np.array_equal(back2.matrix, back.matrix)

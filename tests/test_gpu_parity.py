@@ -238,3 +238,34 @@ def test_wave_lockstep_gives_identical_scores(engine):
     finally:
         engine.lockstep = old
     assert np.array_equal(a, b) and np.abs(a).max() > 0
+
+
+def test_build_training_tensors_matches_reference_loop(engine):
+    """gv_build_training_tensors vs the reference's _build_training_tensors (data.py:377-411)
+    restated with its own dict loop, for signed and unsigned training."""
+    import torch
+    from genevector_b200.data import build_training_tensors, compute_target_scores
+    z = load_golden("ref_poisson_500x50_b10")
+    genes = [f"GENE{i}" for i in range(50)]
+    sm = compute_target_scores(z["X"], genes, target="mi", target_kwargs={"n_bins": 10}, signed_mi=True,
+                               mi_backend="b200", device="cuda", use_cache=False)
+    d = sm.to_dict()
+    for signed in (True, False):
+        n = len(genes)
+        score_matrix = np.zeros((n, n), dtype=np.float32)          # data.py:383-388
+        for i, g1 in enumerate(genes):
+            if g1 in d:
+                for j, g2 in enumerate(genes):
+                    if i != j and g2 in d[g1]:
+                        score_matrix[i, j] = d[g1][g2]
+        score_matrix *= 100.0 ** 2                                  # :390
+        if not signed:
+            score_matrix[score_matrix < 0] = 0.0                    # :392-393
+        idx = np.arange(n)
+        ig, jg = np.meshgrid(idx, idx, indexing="ij")
+        off = ig != jg
+        i_idx, j_idx, xij = build_training_tensors(sm, genes, c=100.0, signed_mi=signed, device="cuda")
+        assert i_idx.dtype == torch.int64 and xij.dtype == torch.float32 and xij.is_cuda
+        assert np.array_equal(i_idx.cpu().numpy(), ig[off].ravel())
+        assert np.array_equal(j_idx.cpu().numpy(), jg[off].ravel())
+        assert np.array_equal(xij.cpu().numpy(), score_matrix[off].ravel())
