@@ -47,7 +47,7 @@ SIGNATURES = {
     "gv_tile_schedule": (_i64, [_i64, _i32, _i32, _vp, _i64]),
     "gv_mi_tiles": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
                            _i32, _vp, _vp]),
-    "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp,
                                _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -49,7 +49,7 @@ static int check_device() {
 int mi_tiles_dispatch(const void*, int64_t, int64_t, int, const int32_t*, const int8_t*, int64_t, int,
                       const int32_t*, int64_t, float*, int64_t, int, void*, cudaStream_t);
 int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, int32_t*, int64_t, int,
-                       cudaStream_t);
+                       int, cudaStream_t);
 int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
                           const int32_t*, int64_t, int, const int32_t*, int64_t, int8_t*, int64_t,
                           float*, int64_t, int, void*, cudaStream_t);
@@ -171,11 +171,12 @@ int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_ge
 }
 
 int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
-                 int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, void* stream) {
+                 int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
+                 void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!operand || !tiles || !out || ld_out < op_rows) return set_error(GV_ERR_ARG, "gv_gram_dump: bad argument");
-  return gram_dump_dispatch(operand, op_rows, kp, tiles, n_tiles, out, ld_out, cta_group,
+  return gram_dump_dispatch(operand, op_rows, kp, tiles, n_tiles, out, ld_out, cta_group, active_rows,
                             static_cast<cudaStream_t>(stream));
 }
 

@@ -25,9 +25,13 @@ struct DumpParams {
   int64_t ld;
   int rows;         // operand rows (bounds)
 };
+// ACT = data rows per 32-row block on the B side (see GramCfg): accumulator column
+// cb*ACT + c holds operand row col0 + cb*32 + c.
+template <int ACT>
 struct DumpEpi {
   using Params = DumpParams;
   static constexpr size_t SMEM_BYTES = 16;
+  static constexpr int ACTIVE_ROWS = ACT;
   const Params& p;
   __device__ DumpEpi(const Params& p_, uint8_t*) : p(p_) {}
   __device__ void prepare(const EpiTile&) {}
@@ -37,11 +41,11 @@ struct DumpEpi {
     for (int cbi = 0; cbi < 4; ++cbi) {
       const int cb = et.half * 4 + cbi;
       uint32_t v[32];
-      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
+      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * ACT), v);
       tmem_ld_wait();
       if (row < p.rows) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < ACT; ++c) {
           const int col = et.col0 + cb * 32 + c;
           if (col < p.rows) p.out[int64_t(row) * p.ld + col] = int32_t(v[c]);
         }
@@ -78,6 +82,8 @@ struct MiEpi {
   using Params = MiParams;
   static constexpr int GPB = 32 / B;          // genes per 32-row block of the operand
   static constexpr int ACTIVE = GPB * B;      // rows of a block that carry data
+  // B side staged densely when a block has exactly 30 data rows (B = 10, 5): N = 240
+  static constexpr int ACTIVE_ROWS = (ACTIVE == 30) ? 30 : 32;
   static constexpr int CG_PER_TILE = 8 * GPB; // column genes per tile
   struct Meta {
     int cm[GRAM_TILE_N];        // marginal count of the (gene,bin) behind each column
@@ -98,17 +104,18 @@ struct MiEpi {
   // Column metadata of the tile: one epilogue thread per accumulator column.
   __device__ void prepare(const EpiTile& et) {
     epi_bar_sync();   // everyone is done with the previous tile's metadata
-    const int c = et.epi_tid;
-    const int within = c & 31;
+    const int c = et.epi_tid;                 // accumulator column
+    const int blk = c / ACTIVE_ROWS;          // 32-row operand block behind it
+    const int within = c - blk * ACTIVE_ROWS;
     int m = 0;
-    if (within < ACTIVE) {
+    if (blk < 8 && within < ACTIVE) {
       const int sj = within / B, b = within - sj * B;
-      const int gj = ((et.col0 >> 5) + (c >> 5)) * GPB + sj;
+      const int gj = ((et.col0 >> 5) + blk) * GPB + sj;
       if (gj < p.G) {
         if (1 + b < MARG_STRIDE) m = p.marg[int64_t(gj) * MARG_STRIDE + 1 + b];  // B=16: bin 16 never occurs
-        if (b == 0) meta->cg_nnz[(c >> 5) * GPB + sj] = p.marg[int64_t(gj) * MARG_STRIDE];
+        if (b == 0) meta->cg_nnz[blk * GPB + sj] = p.marg[int64_t(gj) * MARG_STRIDE];
       } else if (b == 0) {
-        meta->cg_nnz[(c >> 5) * GPB + sj] = 0;
+        meta->cg_nnz[blk * GPB + sj] = 0;
       }
     }
     meta->cm[c] = m;
@@ -136,7 +143,7 @@ struct MiEpi {
     for (int cbi = 0; cbi < 4; ++cbi) {
       const int cb = et.half * 4 + cbi;
       uint32_t v[32];
-      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
+      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * ACTIVE_ROWS), v);
       tmem_ld_wait();
       // stage this warp's 32x32 count block for the column sums (bank = lane + c: no conflicts)
 #pragma unroll
@@ -148,7 +155,7 @@ struct MiEpi {
         const int cgi = cb * GPB + sj;
         const int gj = ((et.col0 >> 5) + cb) * GPB + sj;
         const int nnz_j = meta->cg_nnz[cgi];
-        const int colb = cb * 32 + sj * B;    // first accumulator column of gene j
+        const int colb = cb * ACTIVE_ROWS + sj * B;    // first accumulator column of gene j
 
         // row sum over b (this row's bin a against all non-zero bins of gene j)
         int r = 0;
@@ -233,6 +240,7 @@ struct MomentEpi {
     int64_t csq[GRAM_TILE_N];
   };
   static constexpr size_t SMEM_BYTES = sizeof(Meta) + 16;
+  static constexpr int ACTIVE_ROWS = 32;
   const Params& p;
   Meta* meta;
   __device__ MomentEpi(const Params& p_, uint8_t* smem) : p(p_) {

@@ -30,21 +30,31 @@ constexpr int GRAM_EPI_BAR = 1;        // named barrier id used by the epilogue 
 
 constexpr int GRAM_SMEM_MAX = 227 * 1024;   // dynamic shared memory a CTA may opt in to on sm_100
 
-template <int CG, int EPI_SMEM_BYTES>
+// ACTIVE = operand rows that carry data in every 32-row block (32, or 30 for 3 genes x 10 bins).
+// On the B side the data rows of the 8 blocks of a tile are staged back to back (one TMA box of
+// ACTIVE rows per block), so the MMA runs with N = 8*ACTIVE columns instead of 256 and no
+// accumulator column is spent on padding rows.  The A side keeps whole 32-row blocks: a gene's
+// bins must stay inside one 32-lane TMEM quarter for the epilogue.
+template <int CG, int EPI_SMEM_BYTES, int ACTIVE = 32>
 struct GramCfg {
+  static_assert(ACTIVE == 32 || ACTIVE == 30, "unsupported block occupancy");
   static constexpr int TILE_M = 128 * CG;                 // operand rows on the A side per tile
+  static constexpr int N_COLS = 8 * ACTIVE;               // accumulator columns = MMA N
   static constexpr int A_ROWS = 128;                      // rows of A each CTA stages
-  static constexpr int B_ROWS = GRAM_TILE_N / CG;         // rows of B each CTA stages
+  static constexpr int B_ROWS = N_COLS / CG;              // data rows of B each CTA stages
+  static constexpr int B_BLOCKS = 8 / CG;                 // 32-row operand blocks behind them
   static constexpr int A_BYTES = A_ROWS * GRAM_BK;
   static constexpr int B_BYTES = B_ROWS * GRAM_BK;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_SLOT_BYTES = (GRAM_TILE_N / CG) * GRAM_BK;   // smem reserved for B
+  static constexpr int STAGE_BYTES = A_BYTES + B_SLOT_BYTES;
+  static constexpr int TX_BYTES = A_BYTES + B_BYTES;      // bytes TMA delivers per CTA per stage
   static constexpr int BAR_BYTES = 256;                   // barriers + tmem pointer
   // as many pipeline stages as fit next to the epilogue's scratch (1024 = alignment slack)
   static constexpr int STAGES_FIT = (GRAM_SMEM_MAX - 1024 - BAR_BYTES - EPI_SMEM_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage operand pipeline");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier block too small");
-  static constexpr uint32_t IDESC = idesc_i8(TILE_M, GRAM_TILE_N, true, true);
+  static constexpr uint32_t IDESC = idesc_i8(TILE_M, N_COLS, true, true);
 };
 
 // What the epilogue functor gets for one tile.
@@ -71,15 +81,16 @@ struct GramArgs {
 
 template <int CG, class Epi>
 constexpr size_t gram_smem_bytes() {
-  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES)>;
+  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS>;
   return 1024 + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Epi::SMEM_BYTES;
 }
 
 template <int CG, class Epi>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
-gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
-                  const typename Epi::Params ep) {
-  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES)>;
+gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
+                  const GramArgs ga, const typename Epi::Params ep) {
+  // tmap: 128-row boxes (A side, and B side when ACTIVE == 32); tmap_b: ACTIVE-row boxes
+  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -101,7 +112,7 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
   const int cluster_id = blockIdx.x / CG;
   const int n_clusters = gridDim.x / CG;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap); tma_prefetch_desc(&tmap_b); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), CG);   // one producer arrive per CTA of the pair (on the leader)
@@ -140,7 +151,7 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
         if (t >= ga.n_tiles) break;
         const int2 tc = ga.tiles[t];
         const int arow = tc.x + int(rank) * Cfg::A_ROWS;
-        const int brow = tc.y + int(rank) * Cfg::B_ROWS;
+        const int brow = tc.y + int(rank) * (GRAM_TILE_N / CG);   // first operand row of my B blocks
         for (int kb = 0; kb < ga.k_blocks; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
@@ -148,15 +159,29 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs ga,
           const uint32_t fb = full0 + 8u * s;   // leader's barrier (cluster address if CG==2)
           if constexpr (CG == 2) {
             tma_load_2d_pair(&tmap, fb, sa, kb * GRAM_BK, arow);
-            tma_load_2d_pair(&tmap, fb, sb, kb * GRAM_BK, brow);
-            if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES * CG);
+            if constexpr (Epi::ACTIVE_ROWS == 32) {
+              tma_load_2d_pair(&tmap, fb, sb, kb * GRAM_BK, brow);
+            } else {
+#pragma unroll
+              for (int q = 0; q < Cfg::B_BLOCKS; ++q)
+                tma_load_2d_pair(&tmap_b, fb, sb + q * (Epi::ACTIVE_ROWS * GRAM_BK), kb * GRAM_BK,
+                                 brow + 32 * q);
+            }
+            if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES * CG);
             else        mbar_arrive_cluster(fb);
           } else {
             tma_load_2d(&tmap, fb, sa, kb * GRAM_BK, arow);
-            // TMA boxes are at most 256 rows; B_ROWS == 256 here and the box is 128 rows
-            tma_load_2d(&tmap, fb, sb, kb * GRAM_BK, brow);
-            tma_load_2d(&tmap, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
-            mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+            if constexpr (Epi::ACTIVE_ROWS == 32) {
+              // TMA boxes are at most 256 rows; 256 rows here and the box is 128 rows
+              tma_load_2d(&tmap, fb, sb, kb * GRAM_BK, brow);
+              tma_load_2d(&tmap, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
+            } else {
+#pragma unroll
+              for (int q = 0; q < Cfg::B_BLOCKS; ++q)
+                tma_load_2d(&tmap_b, fb, sb + q * (Epi::ACTIVE_ROWS * GRAM_BK), kb * GRAM_BK,
+                            brow + 32 * q);
+            }
+            mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES);
           }
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }

@@ -26,8 +26,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D map over operand[op_rows][kp] (uint8), box = 128 bytes of K x 128 rows, SWIZZLE_128B.
-static int make_operand_map(CUtensorMap* map, const void* operand, int64_t op_rows, int64_t kp) {
+// 2-D map over operand[op_rows][kp] (uint8), box = 128 bytes of K x box_rows rows, SWIZZLE_128B.
+static int make_operand_map(CUtensorMap* map, const void* operand, int64_t op_rows, int64_t kp,
+                            int box_rows = 128) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(GV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (kp % 128 != 0 || kp <= 0) return set_error(GV_ERR_ARG, "operand K extent must be a positive multiple of 128");
@@ -35,7 +36,7 @@ static int make_operand_map(CUtensorMap* map, const void* operand, int64_t op_ro
     return set_error(GV_ERR_ARG, "operand must be 128-byte aligned");
   cuuint64_t dims[2] = {cuuint64_t(kp), cuuint64_t(op_rows)};
   cuuint64_t strides[1] = {cuuint64_t(kp)};
-  cuuint32_t box[2] = {128, 128};
+  cuuint32_t box[2] = {128, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(operand), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -49,8 +50,10 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
                        int64_t n_tiles, const typename Epi::Params& ep, void* sync_ws,
                        cudaStream_t st) {
   if (n_tiles <= 0) return GV_OK;
-  CUtensorMap map;
+  CUtensorMap map, map_b;
   int rc = make_operand_map(&map, operand, op_rows, kp);
+  if (rc != GV_OK) return rc;
+  rc = make_operand_map(&map_b, operand, op_rows, kp, Epi::ACTIVE_ROWS == 32 ? 128 : Epi::ACTIVE_ROWS);
   if (rc != GV_OK) return rc;
   GramArgs ga;
   ga.tiles = reinterpret_cast<const int2*>(tiles);
@@ -81,7 +84,7 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, map, ga, ep);
+  e = cudaLaunchKernelEx(&cfg, kern, map, map_b, ga, ep);
   if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
   return GV_OK;
 }
@@ -111,11 +114,15 @@ int mi_tiles_dispatch(const void* onehot, int64_t op_rows, int64_t kp, int rows_
 }
 
 int gram_dump_dispatch(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
-                       int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group,
+                       int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
                        cudaStream_t st) {
   DumpParams p;
   p.out = out; p.ld = ld_out; p.rows = int(op_rows);
-  return launch_cg<DumpEpi>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, nullptr, st);
+  if (active_rows == 32)
+    return launch_cg<DumpEpi<32>>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, nullptr, st);
+  if (active_rows == 30)
+    return launch_cg<DumpEpi<30>>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, nullptr, st);
+  return set_error(GV_ERR_ARG, "gram dump: active_rows must be 32 or 30");
 }
 
 int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64_t kp,

@@ -270,7 +270,8 @@ class Engine:
             return onehot, B
 
     # ------------------------------------------------------------------ tile kernels
-    def gram_dump(self, operand: torch.Tensor, cta_group: Optional[int] = None) -> torch.Tensor:
+    def gram_dump(self, operand: torch.Tensor, cta_group: Optional[int] = None,
+                  active_rows: int = 32) -> torch.Tensor:
         """Test-only: raw INT32 accumulators of every scheduled tile."""
         with torch.cuda.device(self.device):
             cg = cta_group or self.cta_group
@@ -278,17 +279,40 @@ class Engine:
             tiles, n, _ = self.schedule(rows, cg)
             out = torch.zeros((rows, rows), dtype=torch.int32, device=self.device)
             self._call("gv_gram_dump", operand.data_ptr(), rows, kp, tiles.data_ptr(), n,
-                      out.data_ptr(), rows, cg, self._stream())
+                      out.data_ptr(), rows, cg, active_rows, self._stream())
             return out
 
-    def sign_matrix(self, blk: BinBlock, rank: int = 0, world: int = 1) -> torch.Tensor:
-        """int8 [G][ld] Pearson sign from the INT8 value rows (exact integer co-moments)."""
+    def sign_tiles_for(self, mi_tiles: np.ndarray, B: int) -> torch.Tensor:
+        """Sign-map tiles (256 x 256 genes) that cover the gene pairs of the given MI tiles
+        (operand-row coordinates), so a rank only computes the part of the sign map it reads."""
+        gpb = 32 // B
+        tm = _lib.call("gv_tile_m", self.cta_group)
+        r_lo = mi_tiles[:, 0].astype(np.int64) // 32 * gpb
+        r_hi = (mi_tiles[:, 0].astype(np.int64) + tm) // 32 * gpb - 1
+        c_lo = mi_tiles[:, 1].astype(np.int64) // 32 * gpb
+        c_hi = (mi_tiles[:, 1].astype(np.int64) + 256) // 32 * gpb - 1
+        keys = set()
+        for rr in (r_lo, r_hi):
+            for cc in (c_lo, c_hi):
+                # an MI tile spans < 256 genes per side, so its corners hit every sign tile it touches
+                keys.update(np.unique((rr // tm) * (1 << 32) + (cc // 256)).tolist())
+        arr = np.array(sorted(keys), dtype=np.int64)
+        st = np.stack([(arr >> 32) * tm, (arr & 0xFFFFFFFF) * 256], axis=1)
+        st = st[st[:, 0] <= st[:, 1] + 255]          # tiles holding some (row <= col)
+        return torch.from_numpy(np.ascontiguousarray(st.astype(np.int32))).to(self.device)
+
+    def sign_matrix(self, blk: BinBlock, tiles: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int8 [G][ld] Pearson sign from the INT8 value rows (exact integer co-moments).
+        `tiles`: optional subset of sign tiles (see sign_tiles_for); default the whole triangle."""
         assert blk.val_rows is not None and blk.val_mode == 0
         with torch.cuda.device(self.device):
             G = blk.n_genes
             ld = _align(G, 16)
             sgn = torch.zeros((G, ld), dtype=torch.int8, device=self.device)
-            tiles, n, _ = self.schedule(G, rank=rank, world=world)
+            if tiles is None:
+                tiles, n, _ = self.schedule(G)
+            else:
+                n = int(tiles.shape[0])
             self._call("gv_moment_tiles", _lib.GV_MOM_SIGN, blk.val_rows.data_ptr(), G, blk.kp,
                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
                       tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0, self.cta_group,
@@ -345,15 +369,28 @@ class Engine:
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All-pairs (signed) MI.  With world > 1 only rank 0 needs `csr`; each rank returns a
         [G][G] matrix in which the entries of its own tiles are filled."""
+        import torch.distributed as dist
         val_mode = 0 if signed else -1
-        blk = self.discretize(csr, n_bins, val_mode) if rank == 0 else None
-        if world > 1:
+        distributed = world > 1 and dist.is_available() and dist.is_initialized()
+        # without an initialised process group the ranks are emulated one after another in this
+        # process (tests): each "rank" then discretises for itself
+        blk = self.discretize(csr, n_bins, val_mode) if (rank == 0 or not distributed) else None
+        if distributed:
             blk = self._replicate(blk, n_cells, n_genes, n_bins, val_mode, group)
         sgn = None
+        B = _lib.call("gv_rows_per_gene", n_bins)
         if signed:
-            # every rank computes the (cheap, 1 % of the work) full sign map: its MI tiles may
-            # need any entry of it and this keeps the path free of a second collective
-            sgn = self.sign_matrix(blk)
+            # each rank computes only the part of the sign map its own MI tiles read (1 % of the
+            # work, sharded like the MI tiles); no second collective
+            st = None
+            if world > 1:
+                rows = _lib.check("gv_onehot_rows", self.lib.gv_onehot_rows(n_genes, B))
+                key = ("sign", rows, self.cta_group, self.band, rank, world)
+                if key not in self._sched_cache:
+                    mine, _ = tile_slice(rows, self.cta_group, self.band, rank, world)
+                    self._sched_cache[key] = self.sign_tiles_for(mine, B)
+                st = self._sched_cache[key]
+            sgn = self.sign_matrix(blk, tiles=st)
         onehot, B = self.expand_onehot(blk)
         return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world)
 

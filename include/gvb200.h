@@ -124,9 +124,13 @@ int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_ge
                 const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
                 void* sync_ws, void* stream);
 
-/* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles. */
+/* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles.
+ * active_rows = 32: every operand row is a column of the tile (N = 256); 30: the B side stages only
+ * the first 30 rows of every 32-row block (N = 240, what gv_mi_tiles does for 10 or 5 rows per
+ * gene) and columns of the other two rows are left untouched. */
 int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
-                 int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, void* stream);
+                 int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
+                 void* stream);
 
 /* ---------------------------------------------------------------- co-moment targets
  * One INT8 row per gene (val_rows from gv_discretize_csr).  kind GV_MOM_SIGN writes int8 `sgn`

@@ -179,3 +179,31 @@ def test_cache_roundtrip_and_key_compat(tmp_path, monkeypatch):
     cache.save_scores(key + "d", sm.to_dict(), genes)
     back2, _ = cache.load_scores(key + "d")
     assert np.array_equal(back2.matrix, back.matrix)
+
+
+def test_sign_tiles_cover_every_pair_of_the_rank(monkeypatch):
+    """Host logic of the sharded sign pass: the sign tiles chosen for a rank's MI tiles contain
+    every gene pair those MI tiles produce."""
+    from genevector_b200 import engine as E
+    from genevector_b200 import _lib
+    lib = _lib.load()
+
+    class Fake:                      # Engine without a device: only the pure host method is used
+        cta_group, band = 2, 8
+        device = "cpu"
+    G, B = 5000, 10
+    gpb = 32 // B
+    rows = lib.gv_onehot_rows(G, B)
+    for world in (2, 8):
+        for rank in (0, world - 1):
+            mine, _ = E.tile_slice(rows, 2, 8, rank, world)
+            st = E.Engine.sign_tiles_for(Fake(), mine, B).numpy()
+            cover = np.zeros((-(-G // 256), -(-G // 256)), dtype=bool)
+            cover[st[:, 0] // 256, st[:, 1] // 256] = True
+            for r0, c0 in mine[:: max(1, len(mine) // 200)]:
+                gi = np.arange(r0 // 32 * gpb, min(G, (r0 + 256) // 32 * gpb))
+                gj = np.arange(c0 // 32 * gpb, min(G, (c0 + 256) // 32 * gpb))
+                ii, jj = np.meshgrid(gi, gj, indexing="ij")
+                m = ii < jj
+                assert cover[ii[m] // 256, jj[m] // 256].all()
+            assert len(st) < 0.75 * len(E.tile_slice(G, 2, 8, 0, 1)[0]) or world == 2
