@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgvb200.so")
 GV_OK = 0
 GV_F32, GV_F64 = 0, 1
 GV_MOM_SIGN, GV_MOM_PEARSON, GV_MOM_COSINE, GV_MOM_JACCARD = 0, 1, 2, 3
+GV_PATH_AUTO, GV_PATH_COUNTS, GV_PATH_GENERAL = 0, 1, 2
 GV_MARG_STRIDE = 16
 GV_EDGE_STRIDE = 16
 GV_QTABLE_DIM = 16
@@ -39,7 +40,7 @@ SIGNATURES = {
     "gv_discretize_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
-                                 _vp, _sz, _vp]),
+                                 _vp, _sz, _i32, _vp, _vp]),
     "gv_rows_per_gene": (_i32, [_i32]),
     "gv_onehot_rows": (_i64, [_i32, _i32]),
     "gv_expand_onehot": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp]),

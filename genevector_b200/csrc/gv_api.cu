@@ -77,7 +77,8 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
                       int32_t* n_bins_per_gene, int32_t* marg, double* edges, int64_t* gsum,
                       int64_t* gsq, void* val_rows, int64_t val_pitch, int64_t val_rows_alloc,
                       int val_mode, int val_limbs, int val_limb_bits, uint64_t* data_flags_out_host,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      void* workspace, size_t workspace_bytes, int path, int* path_used_host,
+                      void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (n_cells < 0 || n_genes <= 0 || nnz < 0) return set_error(GV_ERR_ARG, "bad matrix shape");
@@ -96,6 +97,9 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
   a.val_rows = val_rows; a.val_pitch = val_pitch; a.val_rows_alloc = val_rows_alloc;
   a.val_mode = val_mode; a.val_limbs = val_limbs; a.val_limb_bits = val_limb_bits;
   a.data_flags_out = data_flags_out_host; a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  if (path != GV_PATH_AUTO && path != GV_PATH_COUNTS && path != GV_PATH_GENERAL)
+    return set_error(GV_ERR_ARG, "unknown discretisation path");
+  a.path = path; a.path_used = path_used_host;
   return discretize_dispatch(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -443,6 +443,220 @@ __global__ void k_expand_onehot(const uint32_t* __restrict__ bins_packed, int64_
   }
 }
 
+
+// ================================================================ count-data fast path
+// For non-negative integer data with values <= 255 (scRNA-seq counts, the documented input) the
+// order statistics follow from a per-gene VALUE histogram, so the gene-major regroup is not
+// needed at all:
+//   k_hist2d      one pass over the CSR values: hist[gene][value]++ (20 MB at 20k genes: the
+//                 atomics resolve in L2) + the data flags
+//   k_gene_lut    one warp per gene: n_unique, k, the 2(k-1) order statistics from the cumulative
+//                 histogram, numpy-exact edges, a value -> bin lookup table, marginals, Sum x, Sum x^2
+//   k_assign_csr  second pass over the CSR in cell order: bin = lut[gene][value] -> packed nibble
+//                 (RED.OR; the 64 cells of a 32-byte sector are written while it sits in L2) and the
+//                 optional INT8 value rows
+// Results are bit-identical to the general path (tests compare both with the oracle).
+constexpr int VH = 256;   // histogram slots per gene: integer values 1..255
+
+template <typename T>
+__global__ void k_hist2d(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+                         int64_t nnz, uint32_t* __restrict__ hist,
+                         unsigned long long* __restrict__ flags) {
+  unsigned f = 0;
+  unsigned long long vmax = 0;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const T v = values[e];
+    if (v > T(0)) {
+      const T c = ceil(v);
+      if (c != v) f |= 2u;
+      const unsigned long long ci = c < T(1.8e19) ? (unsigned long long)c : ~0ull;
+      vmax = ci > vmax ? ci : vmax;
+      if (c == v && ci < VH) atomicAdd(&hist[int64_t(col_idx[e]) * VH + int(ci)], 1u);
+    } else if (v < T(0)) {
+      f |= 1u;
+    }
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  for (int d = 16; d >= 1; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, vmax, d);
+    vmax = o > vmax ? o : vmax;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (f) atomicOr(&flags[0], (unsigned long long)f);
+    if (vmax) atomicMax(&flags[1], vmax);
+  }
+}
+
+// One warp per gene.  Lane l owns the 8 histogram slots v = 8l .. 8l+7.
+template <typename T>
+__global__ void k_gene_lut(const uint32_t* __restrict__ hist, int G, int n_bins,
+                           const double* __restrict__ q_table, uint8_t* __restrict__ lut,
+                           int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
+                           double* __restrict__ edges_out, int64_t* __restrict__ gsum,
+                           int64_t* __restrict__ gsq) {
+  using K = ValKey<T>;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
+    uint32_t c[8];
+    const uint4* hp = reinterpret_cast<const uint4*>(hist + int64_t(g) * VH + lane * 8);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    c[0] = h0.x; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w; c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
+    uint32_t tot = 0, nun = 0;
+    long long s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      tot += c[i]; nun += c[i] ? 1u : 0u;
+      const long long v = lane * 8 + i;
+      s1 += v * (long long)c[i]; s2 += v * v * (long long)c[i];
+    }
+    uint32_t inc = tot;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += y;
+    }
+    const uint32_t lane_excl = inc - tot;
+    const int64_t m = __shfl_sync(0xffffffffu, inc, 31);
+    for (int d = 16; d >= 1; d >>= 1) {
+      nun += __shfl_xor_sync(0xffffffffu, nun, d);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) { gsum[g] = s1; gsq[g] = s2; }
+    double edge[14];
+#pragma unroll
+    for (int t = 0; t < 14; ++t) edge[t] = DBL_MAX;
+    int k = 0, n_edges = 0;
+    if (m > 0) {
+      k = int(nun) < n_bins ? int(nun) : n_bins;          // metrics.py:59
+      n_edges = k > 1 ? k - 1 : 0;
+      // value (as the integer it is) holding sorted rank r: the slot whose cumulative range has r
+      auto value_at = [&](int64_t r) -> int {
+        int found = 0;
+        uint32_t run = lane_excl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r >= int64_t(run) && r < int64_t(run) + int64_t(c[i])) found = lane * 8 + i;
+          run += c[i];
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+          const int o = __shfl_xor_sync(0xffffffffu, found, d);
+          found = o > found ? o : found;
+        }
+        return found;
+      };
+#pragma unroll
+      for (int t = 0; t < 14; ++t) {
+        if (t < n_edges) {                                 // warp-uniform
+          const double q = q_table[k * 16 + t];
+          const double vi = __dmul_rn(double(m - 1), q);
+          int64_t ra, rb; double gam;
+          if (vi >= double(m - 1)) { ra = rb = m - 1; gam = __dadd_rn(vi, 1.0); }
+          else { const double fl = floor(vi); ra = int64_t(fl); rb = ra + 1; gam = __dsub_rn(vi, fl); }
+          const T a = T(value_at(ra));
+          const T b = T(value_at(rb));
+          const T d = K::sub(b, a);
+          edge[t] = (gam >= 0.5) ? __dsub_rn(double(b), __dmul_rn(double(d), __dsub_rn(1.0, gam)))
+                                 : __dadd_rn(double(a), __dmul_rn(double(d), gam));
+        }
+      }
+    }
+    // lookup table + marginals
+    uint32_t mg[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) mg[a] = 0;
+    uint32_t packed[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double vd = double(lane * 8 + i);
+      int bin = 1;
+#pragma unroll
+      for (int t = 0; t < 14; ++t) bin += (t < n_edges && edge[t] <= vd) ? 1 : 0;
+      if (lane * 8 + i == 0) bin = 0;
+      packed[i >> 2] |= uint32_t(bin) << ((i & 3) * 8);
+#pragma unroll
+      for (int a = 1; a < 16; ++a) mg[a] += (a == bin) ? c[i] : 0u;
+    }
+    *reinterpret_cast<uint2*>(lut + int64_t(g) * VH + lane * 8) = make_uint2(packed[0], packed[1]);
+#pragma unroll
+    for (int a = 1; a < 16; ++a)
+      for (int d = 16; d >= 1; d >>= 1) mg[a] += __shfl_xor_sync(0xffffffffu, mg[a], d);
+    if (lane == 0) {
+      n_bins_per_gene[g] = m == 0 ? 1 : (k <= 1 ? 2 : k + 1);   // metrics.py:55-57,62,67
+      marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
+#pragma unroll
+      for (int a = 1; a < 16; ++a) marg[int64_t(g) * MARG_STRIDE_ + a] = int32_t(mg[a]);
+#pragma unroll
+      for (int t = 0; t < 14; ++t) edges_out[int64_t(g) * 16 + t] = edge[t];
+      edges_out[int64_t(g) * 16 + 14] = DBL_MAX;
+      edges_out[int64_t(g) * 16 + 15] = DBL_MAX;
+    }
+  }
+}
+
+// The CSR entries are walked in storage order: CTAs draw consecutive chunks of ASSIGN_CHUNK entries
+// from an atomic ticket counter, so at any time the whole grid works on one compact window of a
+// few hundred consecutive cells.  The packed-bin words and value-row sectors of those cells (a few
+// MB over all genes) are then completed while they sit in L2 and reach DRAM once.  (A plain
+// grid-stride loop lets warps drift apart until that window no longer fits L2:
+// profiles/r01_ncu_assign_c4_gridstride.txt, 36 GB of DRAM reads for a 3.2 GB input.)
+// Each warp finds the row of its first entry with one binary search over row_ptr and walks row
+// boundaries from there.
+constexpr int ASSIGN_THREADS = 256;
+constexpr int ASSIGN_PER_THREAD = 4;
+constexpr int ASSIGN_CHUNK = ASSIGN_THREADS * ASSIGN_PER_THREAD;
+
+template <typename T>
+__global__ void __launch_bounds__(ASSIGN_THREADS)
+k_assign_csr(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+             const int64_t* __restrict__ row_ptr, int64_t n_cells, int64_t nnz,
+             const uint8_t* __restrict__ lut, uint32_t* __restrict__ bins_packed,
+             int64_t pitch_words, int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode,
+             int limb_bits, int n_limbs, unsigned long long* __restrict__ ticket) {
+  __shared__ unsigned long long s_chunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_chunks = (nnz + ASSIGN_CHUNK - 1) / ASSIGN_CHUNK;
+  while (true) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const int64_t chunk = int64_t(s_chunk);
+    __syncthreads();
+    if (chunk >= n_chunks) break;
+    // warp w takes ASSIGN_PER_THREAD runs of 32 consecutive entries
+    const int64_t wbase = chunk * ASSIGN_CHUNK + int64_t(warp) * (32 * ASSIGN_PER_THREAD);
+    if (wbase >= nnz) continue;
+    int64_t lo = 0, hi = n_cells - 1;      // largest r with row_ptr[r] <= wbase (warp-uniform)
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (row_ptr[mid] <= wbase) lo = mid; else hi = mid - 1;
+    }
+    int64_t r = lo;
+#pragma unroll
+    for (int u = 0; u < ASSIGN_PER_THREAD; ++u) {
+      const int64_t e = wbase + u * 32 + lane;
+      if (e >= nnz) break;
+      while (e >= row_ptr[r + 1]) ++r;        // also skips empty rows
+      const T v = values[e];
+      if (v > T(0)) {
+        const int g = col_idx[e];
+        const unsigned xi = unsigned(v);
+        const uint32_t bin = lut[int64_t(g) * VH + xi];
+        atomicOr(&bins_packed[int64_t(g) * pitch_words + (r >> 3)], bin << (uint32_t(r & 7) * 4));
+        if (val_rows != nullptr) {
+          if (val_mode == 1) {
+            val_rows[int64_t(g) * val_pitch + r] = 1;
+          } else {
+            for (int l = 0; l < n_limbs; ++l)
+              val_rows[(int64_t(g) * n_limbs + l) * val_pitch + r] =
+                  int8_t((xi >> (l * limb_bits)) & ((1u << limb_bits) - 1u));
+          }
+        }
+      }
+    }
+  }
+}
+
 // ================================================================ host-side launchers
 #define GV_LAUNCH_CHECK()                                     \
   do {                                                        \
@@ -450,32 +664,91 @@ __global__ void k_expand_onehot(const uint32_t* __restrict__ bins_packed, int64_
     if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
   } while (0)
 
+static int check_val_config(const DiscretizeArgs& a, const unsigned long long* hflags) {
+  if (a.val_rows == nullptr || a.val_mode != 0) return GV_OK;
+  if (hflags[0] != 0)
+    return set_error(GV_ERR_UNSUPPORTED,
+                     "co-moment path needs non-negative integer counts (negative or fractional values found)");
+  const int n_limbs = a.val_limbs, limb_bits = a.val_limb_bits;
+  if (n_limbs < 1 || limb_bits < 1 || limb_bits > 7 ||
+      (n_limbs * limb_bits < 64 && (hflags[1] >> (n_limbs * limb_bits)) != 0))
+    return set_error(GV_ERR_UNSUPPORTED, "co-moment path: values exceed the configured limb range");
+  return GV_OK;
+}
+
+#define GV_CUDA_TRY(expr)                                             \
+  do {                                                                \
+    cudaError_t e_ = (expr);                                          \
+    if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
+  } while (0)
+
 template <typename T>
 static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   const int G = a.n_genes;
-  // workspace carve-up (all 256-byte aligned)
+  // workspace carve-up (all 256-byte aligned); the two paths share the front part
   uint8_t* ws = static_cast<uint8_t*>(a.workspace);
   size_t off = 0;
   auto take = [&](size_t bytes) { void* p = ws + off; off += (bytes + 255) & ~size_t(255); return p; };
+  unsigned long long* flags = static_cast<unsigned long long*>(take(64));
+  double* qtab = static_cast<double*>(take(16 * 16 * 8));
+  const size_t front = off;
+  const T* values = static_cast<const T*>(a.values);
+  const int sms = device_sm_count();
+  int8_t* val_rows = static_cast<int8_t*>(a.val_rows);
+  const int n_limbs = a.val_mode == 1 ? 1 : a.val_limbs;
+
+  GV_CUDA_TRY(cudaMemsetAsync(flags, 0, 64, st));
+  GV_CUDA_TRY(cudaMemcpyAsync(qtab, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st));
+  GV_CUDA_TRY(cudaMemsetAsync(a.bins_packed, 0, size_t(G) * a.bins_pitch_bytes, st));
+  if (val_rows != nullptr)
+    GV_CUDA_TRY(cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st));
+  unsigned long long hflags[2] = {0, 0};
+
+  // ---------------- count-data fast path (tried first unless the caller forces the general one)
+  if (a.path != GV_PATH_GENERAL) {
+    uint32_t* hist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
+    uint8_t* lut = static_cast<uint8_t*>(take(size_t(G) * VH));
+    if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
+    GV_CUDA_TRY(cudaMemsetAsync(hist, 0, size_t(G) * VH * 4, st));
+    if (a.nnz > 0) {
+      k_hist2d<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, hist, flags);
+      GV_LAUNCH_CHECK();
+    }
+    GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
+    GV_CUDA_TRY(cudaStreamSynchronize(st));
+    const bool eligible = (hflags[0] & 2ull) == 0 && hflags[1] < (unsigned long long)VH;
+    if (eligible) {
+      if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
+      int rc = check_val_config(a, hflags);
+      if (rc != GV_OK) return rc;
+      k_gene_lut<T><<<(G + 7) / 8, 256, 0, st>>>(hist, G, a.n_bins, qtab, lut, a.n_bins_per_gene, a.marg,
+                                                  a.edges, a.gsum, a.gsq);
+      GV_LAUNCH_CHECK();
+      if (a.nnz > 0) {
+        // flags[4] is the ticket counter (zeroed with the flags block above)
+        k_assign_csr<T><<<sms * 8, ASSIGN_THREADS, 0, st>>>(
+            values, a.col_idx, a.row_ptr, a.n_cells, a.nnz, lut, static_cast<uint32_t*>(a.bins_packed),
+            int64_t(a.bins_pitch_bytes / 4), val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs,
+            flags + 4);
+        GV_LAUNCH_CHECK();
+      }
+      if (a.path_used) *a.path_used = GV_PATH_COUNTS;
+      return GV_OK;
+    }
+    if (a.path == GV_PATH_COUNTS)
+      return set_error(GV_ERR_UNSUPPORTED, "count-data path requested but the values are not integers <= 255");
+    off = front;   // fall through to the general path, reusing the workspace
+  }
+
+  // ---------------- general path: gene-major regroup + radix select (any float data)
   uint32_t* cnt = static_cast<uint32_t*>(take(size_t(G) * 4));
   unsigned long long* cursor = static_cast<unsigned long long*>(take(size_t(G) * 8));
   int64_t* gene_ptr = static_cast<int64_t*>(take(size_t(G + 1) * 8));
-  unsigned long long* flags = static_cast<unsigned long long*>(take(64));
-  double* qtab = static_cast<double*>(take(16 * 16 * 8));
   int32_t* g_cell = static_cast<int32_t*>(take(size_t(a.nnz) * 4));
   T* g_val = static_cast<T*>(take(size_t(a.nnz) * sizeof(T)));
   if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
-
-  cudaError_t e;
-  if ((e = cudaMemsetAsync(cnt, 0, size_t(G) * 4, st)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-  if ((e = cudaMemsetAsync(flags, 0, 64, st)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-  if ((e = cudaMemcpyAsync(qtab, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return set_cuda_error(e, __FILE__, __LINE__);
-  if ((e = cudaMemsetAsync(a.bins_packed, 0, size_t(G) * a.bins_pitch_bytes, st)) != cudaSuccess)
-    return set_cuda_error(e, __FILE__, __LINE__);
-
-  const T* values = static_cast<const T*>(a.values);
-  const int sms = device_sm_count();
+  GV_CUDA_TRY(cudaMemsetAsync(cnt, 0, size_t(G) * 4, st));
+  GV_CUDA_TRY(cudaMemsetAsync(flags, 0, 64, st));
   if (a.nnz > 0) {
     k_count_positive<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, cnt, flags);
     GV_LAUNCH_CHECK();
@@ -487,33 +760,17 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     GV_LAUNCH_CHECK();
   }
   // data flags decide the limb layout of the value rows; read them back (one small sync)
-  unsigned long long hflags[2] = {0, 0};
-  if ((e = cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-    return set_cuda_error(e, __FILE__, __LINE__);
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
+  GV_CUDA_TRY(cudaStreamSynchronize(st));
   if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
-
-  int8_t* val_rows = static_cast<int8_t*>(a.val_rows);
-  int n_limbs = a.val_limbs, limb_bits = a.val_limb_bits;
-  if (val_rows != nullptr) {
-    if (a.val_mode == 0) {
-      if (hflags[0] != 0)
-        return set_error(GV_ERR_UNSUPPORTED,
-                         "co-moment path needs non-negative integer counts (negative or fractional values found)");
-      if (n_limbs < 1 || limb_bits < 1 || limb_bits > 7 ||
-          (n_limbs * limb_bits < 64 && (hflags[1] >> (n_limbs * limb_bits)) != 0))
-        return set_error(GV_ERR_UNSUPPORTED, "co-moment path: values exceed the configured limb range");
-    }
-    const size_t rows = size_t(G) * (a.val_mode == 1 ? 1 : n_limbs);
-    if ((e = cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st)) != cudaSuccess)
-      return set_cuda_error(e, __FILE__, __LINE__);
-    (void)rows;
-  }
+  int rc = check_val_config(a, hflags);
+  if (rc != GV_OK) return rc;
   k_gene_bins<T><<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, 0, st>>>(
       gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
       int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
-      a.val_pitch, a.val_mode, limb_bits, a.val_mode == 1 ? 1 : n_limbs);
+      a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs);
   GV_LAUNCH_CHECK();
+  if (a.path_used) *a.path_used = GV_PATH_GENERAL;
   return GV_OK;
 }
 
@@ -529,8 +786,11 @@ int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
 size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype) {
   auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
   const size_t vs = value_dtype == GV_F64 ? 8 : 4;
-  return al(size_t(G) * 4) + al(size_t(G) * 8) + al(size_t(G + 1) * 8) + al(64) + al(16 * 16 * 8) +
-         al(size_t(nnz) * 4) + al(size_t(nnz) * vs) + 256;
+  const size_t front = al(64) + al(16 * 16 * 8);
+  const size_t counts = al(size_t(G) * VH * 4) + al(size_t(G) * VH);
+  const size_t general = al(size_t(G) * 4) + al(size_t(G) * 8) + al(size_t(G + 1) * 8) +
+                         al(size_t(nnz) * 4) + al(size_t(nnz) * vs);
+  return front + (counts > general ? counts : general) + 256;
 }
 
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,

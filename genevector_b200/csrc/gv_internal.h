@@ -25,6 +25,8 @@ struct DiscretizeArgs {
   int val_mode; int val_limbs; int val_limb_bits;
   uint64_t* data_flags_out;         // host, [2]
   void* workspace; size_t workspace_bytes;
+  int path;                         // GV_PATH_AUTO / GV_PATH_COUNTS / GV_PATH_GENERAL
+  int* path_used;                   // host, optional
 };
 
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st);

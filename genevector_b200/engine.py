@@ -81,6 +81,7 @@ class BinBlock:
     val_mode: int                # -1 none, 0 limbs, 1 detection indicator
     limb_bits: int
     data_flags: tuple            # (flag bits, max value)
+    path_used: int = 0           # gv_disc_path the discretisation took (1 counts, 2 general)
 
     def x_disc(self) -> np.ndarray:
         """Unpack to the reference's layout: int32 [n_cells][n_genes] (tests / small cases)."""
@@ -167,7 +168,7 @@ class Engine:
         self.kernel_events = None
 
     # kernels launched by each entry point (memsets / copies not counted)
-    _LAUNCHES = {"gv_discretize_csr": 4, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
+    _LAUNCHES = {"gv_discretize_csr": 3, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
                  "gv_mi_tiles": 1, "gv_gram_dump": 1}
 
     def _call(self, name, *args):
@@ -229,7 +230,7 @@ class Engine:
 
     # ------------------------------------------------------------------ discretisation
     def discretize(self, csr: CsrDevice, n_bins: int = 10, val_mode: int = -1,
-                   buf: Optional[torch.Tensor] = None) -> BinBlock:
+                   buf: Optional[torch.Tensor] = None, path: int = _lib.GV_PATH_AUTO) -> BinBlock:
         """gv_discretize_csr.  val_mode: -1 no value rows, 0 count digits (sign / pearson / cosine),
         1 detection indicator (jaccard)."""
         if not 1 <= n_bins <= 15:
@@ -248,6 +249,7 @@ class Engine:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             q = quantile_table()
             flags = np.zeros(2, dtype=np.uint64)
+            used = np.zeros(1, dtype=np.int32)
             vr = blk.val_rows
             self._call("gv_discretize_csr", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(),
                       csr.row_ptr.data_ptr(), csr.n_cells, csr.n_genes, csr.nnz, n_bins,
@@ -255,8 +257,10 @@ class Engine:
                       blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(),
                       blk.gsq.data_ptr(), vr.data_ptr() if vr is not None else None, kp,
                       csr.n_genes if vr is not None else 0, max(val_mode, 0), 1, lb,
-                      flags.ctypes.data, ws.data_ptr(), ws_bytes, self._stream())
+                      flags.ctypes.data, ws.data_ptr(), ws_bytes, path, used.ctypes.data,
+                      self._stream())
             blk.data_flags = (int(flags[0]), int(flags[1]))
+            blk.path_used = int(used[0])
             return blk
 
     def expand_onehot(self, blk: BinBlock) -> tuple:

@@ -44,6 +44,12 @@ typedef enum gv_status {
 
 typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
 
+/* Discretisation strategies (same results, bit for bit):
+ *   GV_PATH_COUNTS  per-gene value histogram + lookup table; needs integer values in 1..255
+ *   GV_PATH_GENERAL gene-major regroup + multi-target radix select; any float32/float64 data
+ *   GV_PATH_AUTO    try COUNTS, fall back to GENERAL when the data do not qualify */
+typedef enum gv_disc_path { GV_PATH_AUTO = 0, GV_PATH_COUNTS = 1, GV_PATH_GENERAL = 2 } gv_disc_path;
+
 /* Score kinds of gv_moment_tiles. */
 typedef enum gv_moment_kind {
   GV_MOM_SIGN = 0,    /* int8 sign of the Pearson correlation, np.sign(nan_to_num(corrcoef)):
@@ -77,6 +83,7 @@ int gv_device_check(void);
  *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen;
  *                            [1] = max ceil(value)
  *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype) bytes
+ *   path / path_used_host  : gv_disc_path to use; the one taken is written to *path_used_host (optional)
  * n_bins must be in [1, 15] (bins are stored in 4 bits). */
 size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype);
 int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
@@ -85,7 +92,8 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
                       int32_t* n_bins_per_gene, int32_t* marg, double* edges, int64_t* gsum,
                       int64_t* gsq, void* val_rows, int64_t val_pitch, int64_t val_rows_alloc,
                       int val_mode, int val_limbs, int val_limb_bits, uint64_t* data_flags_out_host,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      void* workspace, size_t workspace_bytes, int path, int* path_used_host,
+                      void* stream);
 
 /* ---------------------------------------------------------------- operand layout
  * rows_per_gene B for a given n_bins: 5 (n_bins<=5), 8 (<=8), 10 (<=10), 16 (<=15).

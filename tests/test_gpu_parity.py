@@ -21,11 +21,18 @@ def onehot_row(g, a, B):
 
 
 # ------------------------------------------------------------------ discretisation
+@pytest.mark.parametrize("path", ["auto", "general"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_discretize_bit_exact_vs_reference(engine, case):
+def test_discretize_bit_exact_vs_reference(engine, case, path):
+    """Both discretisation strategies (count-data histogram/LUT, general radix select) give the
+    reference's bins, n_bins_per_gene, edges and marginals bit for bit."""
+    from genevector_b200 import _lib
     z = load_golden(case)
     csr = engine.upload_csr(z["X"])
-    blk = engine.discretize(csr, z["n_bins"])
+    blk = engine.discretize(csr, z["n_bins"], path=_lib.GV_PATH_AUTO if path == "auto" else _lib.GV_PATH_GENERAL)
+    is_counts = bool(np.array_equal(z["X"].data, np.rint(z["X"].data)) and z["X"].data.max() < 256)
+    want_path = _lib.GV_PATH_COUNTS if (path == "auto" and is_counts) else _lib.GV_PATH_GENERAL
+    assert blk.path_used == want_path
     got = blk.x_disc()
     want = z["x_disc"].astype(np.int32)
     bad = np.argwhere(got != want)
@@ -185,9 +192,16 @@ def test_mi_seeded_vs_oracle(engine, n_cells, n_genes, n_bins, seed):
     want, _ = orc.mi_pairs_gm_c(bins_gm, nb, sign=orc.sign_int_c(X))
     csr = engine.upload_csr(X)
     out = engine.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=True).cpu().numpy()
-    blk = engine.discretize(csr, n_bins)
-    assert np.array_equal(blk.x_disc(), bins_gm.T.astype(np.int32))
-    assert np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+    from genevector_b200 import _lib
+    for path in (_lib.GV_PATH_COUNTS, _lib.GV_PATH_GENERAL):
+        blk = engine.discretize(csr, n_bins, val_mode=0, path=path)
+        assert blk.path_used == path
+        assert np.array_equal(blk.x_disc(), bins_gm.T.astype(np.int32))
+        assert np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+        Xd = np.asarray(X.todense())
+        assert np.array_equal(blk.gsum.cpu().numpy(), Xd.sum(axis=0).astype(np.int64))
+        assert np.array_equal(blk.gsq.cpu().numpy(), (Xd.astype(np.int64) ** 2).sum(axis=0))
+        assert np.array_equal(blk.val_rows.cpu().numpy()[:, :n_cells], Xd.T.astype(np.int8))
     err = np.abs(out.astype(np.float64) - want)
     assert err.max() <= MI_TOL, f"max err {err.max():.3e}"
 
@@ -296,3 +310,24 @@ def test_rank_slices_assemble_to_the_single_rank_result(engine, world):
         nz_owner += (part != 0).int()
     assert torch.equal(acc, full)
     assert int(nz_owner.max()) == 1
+
+
+def test_count_path_falls_back_and_refuses(engine):
+    """Values >= 256 or fractional values are outside the histogram path: AUTO falls back to the
+    general path (same result), COUNTS refuses loudly."""
+    from genevector_b200 import _lib
+    from genevector_b200.engine import GvError
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    X = sp.csr_matrix((rng.integers(0, 4, size=(300, 20)) * rng.integers(1, 400, size=(300, 20))).astype(np.float32))
+    assert X.data.max() >= 256
+    xd, nb = orc.discretize_genes_np(X, 10)
+    csr = engine.upload_csr(X)
+    blk = engine.discretize(csr, 10)
+    assert blk.path_used == _lib.GV_PATH_GENERAL
+    assert np.array_equal(blk.x_disc(), xd) and np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+    with pytest.raises(GvError, match="count-data path"):
+        engine.discretize(csr, 10, path=_lib.GV_PATH_COUNTS)
+    # signed MI on such data is refused (one 7-bit limb): fail loudly, no silent fallback
+    with pytest.raises(GvError, match="limb range"):
+        engine.mi_from_csr(csr, 300, 20, signed=True)
