@@ -51,8 +51,8 @@ int mi_tiles_dispatch(const void*, int64_t, int64_t, int, const int32_t*, const 
 int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, int32_t*, int64_t, int,
                        int, cudaStream_t);
 int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
-                          const int32_t*, int64_t, int, const int32_t*, int64_t, int8_t*, int64_t,
-                          float*, int64_t, int, void*, cudaStream_t);
+                          const int32_t*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
+                          int64_t, float*, int64_t, int, void*, cudaStream_t);
 
 int build_pairs_dispatch(const float*, int64_t, int, float, int, int, int64_t*, int64_t*, float*,
                          cudaStream_t);
@@ -186,16 +186,17 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t
 
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
-                    int n_genes, const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
-                    float* out, int64_t ld_out, int cta_group, void* sync_ws, void* stream) {
+                    int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
+                    int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
+                    void* sync_ws, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
-  if (!val_rows || !tiles || n_genes <= 0 || op_rows < n_genes)
+  if (!val_rows || !tiles || n_genes <= 0 || n_limbs < 1 || op_rows < int64_t(n_genes) * n_limbs)
     return set_error(GV_ERR_ARG, "gv_moment_tiles: bad argument");
   if ((sgn && ld_sgn < n_genes) || (out && ld_out < n_genes))
     return set_error(GV_ERR_ARG, "gv_moment_tiles: leading dimension < n_genes");
-  return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, tiles,
-                               n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
+  return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, n_limbs,
+                               limb_bits, tiles, n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
                                static_cast<cudaStream_t>(stream));
 }
 

@@ -230,14 +230,20 @@ struct MomentParams {
   int64_t ld_out;
   int G;
   int64_t n_cells;
+  int limb_bits;         // digit width of the value rows (two-digit operands)
 };
 
-template <int KIND>
+// L = operand rows per gene: base-2^limb_bits digits of the count, least significant first
+// (row = gene*L + digit).  Sum_c x_i x_j = Sum_{p,q} 2^{limb_bits (p+q)} acc[(i,p),(j,q)]: the q sum
+// is taken in registers (adjacent columns), the p sum across adjacent lanes.
+template <int KIND, int L>
 struct MomentEpi {
+  static_assert(L == 1 || L == 2, "one or two digits per gene");
   using Params = MomentParams;
+  static constexpr int GENES_PER_TILE = GRAM_TILE_N / L;
   struct Meta {
-    int64_t csum[GRAM_TILE_N];
-    int64_t csq[GRAM_TILE_N];
+    int64_t csum[GENES_PER_TILE];
+    int64_t csq[GENES_PER_TILE];
   };
   static constexpr size_t SMEM_BYTES = sizeof(Meta) + 16;
   static constexpr int ACTIVE_ROWS = 32;
@@ -249,18 +255,22 @@ struct MomentEpi {
   __device__ void prepare(const EpiTile& et) {
     epi_bar_sync();
     const int c = et.epi_tid;
-    const int gj = et.col0 + c;
-    if constexpr (KIND == MOM_JACCARD) {
-      meta->csum[c] = gj < p.G ? int64_t(p.marg[int64_t(gj) * MARG_STRIDE]) : 0;
-      meta->csq[c] = 0;
-    } else {
-      meta->csum[c] = gj < p.G ? p.gsum[gj] : 0;
-      meta->csq[c] = gj < p.G ? p.gsq[gj] : 0;
+    if (c < GENES_PER_TILE) {
+      const int gj = et.col0 / L + c;
+      if constexpr (KIND == MOM_JACCARD) {
+        meta->csum[c] = gj < p.G ? int64_t(p.marg[int64_t(gj) * MARG_STRIDE]) : 0;
+        meta->csq[c] = 0;
+      } else {
+        meta->csum[c] = gj < p.G ? p.gsum[gj] : 0;
+        meta->csq[c] = gj < p.G ? p.gsq[gj] : 0;
+      }
     }
     epi_bar_sync();
   }
   __device__ void run(const EpiTile& et) {
-    const int gi = et.row0 + et.quarter * 32 + et.lane;
+    const int row = et.row0 + et.quarter * 32 + et.lane;
+    const int gi = row / L;
+    const int digit = row - gi * L;
     const bool row_ok = gi < p.G;
     int64_t sx = 0, sxx = 0;
     if (row_ok) {
@@ -273,6 +283,7 @@ struct MomentEpi {
     }
     const int64_t n = p.n_cells;
     const int64_t var_i = n * sxx - sx * sx;
+    const int lb = p.limb_bits;
 #pragma unroll 1
     for (int cbi = 0; cbi < 4; ++cbi) {
       const int cb = et.half * 4 + cbi;
@@ -280,16 +291,22 @@ struct MomentEpi {
       tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int cc = cb * 32 + c;
-        const int gj = et.col0 + cc;
-        if (!row_ok || gj >= p.G || gi > gj) continue;
-        const int64_t sxy = int64_t(v[c]);   // accumulators are read as unsigned 32-bit
-        const int64_t sy = meta->csum[cc];
+      for (int c = 0; c < 32 / L; ++c) {
+        const int cg = (cb * 32) / L + c;       // column gene within the tile
+        const int gj = et.col0 / L + cg;
+        // accumulators are read as unsigned 32-bit (sums of digit products < 2^32)
+        int64_t sxy = int64_t(v[c * L]);
+        if constexpr (L == 2) {
+          sxy += int64_t(v[c * L + 1]) << lb;
+          sxy <<= (digit * lb);
+          sxy += __shfl_xor_sync(0xffffffffu, sxy, 1);   // add the other digit row of gene i
+        }
+        if (digit != 0 || !row_ok || gj >= p.G || gi > gj) continue;
+        const int64_t sy = meta->csum[cg];
         if constexpr (KIND == MOM_SIGN) {
           int8_t s = 0;
           if (gi != gj) {
-            const int64_t syy = meta->csq[cc];
+            const int64_t syy = meta->csq[cg];
             const int64_t var_j = n * syy - sy * sy;
             const int64_t cov = n * sxy - sx * sy;
             s = (var_i == 0 || var_j == 0) ? 0 : (cov > 0 ? 1 : (cov < 0 ? -1 : 0));
@@ -300,14 +317,14 @@ struct MomentEpi {
           float r = 0.0f;
           if (gi != gj) {
             if constexpr (KIND == MOM_PEARSON) {
-              const int64_t syy = meta->csq[cc];
+              const int64_t syy = meta->csq[cg];
               const int64_t var_j = n * syy - sy * sy;
               const int64_t cov = n * sxy - sx * sy;
               double q = double(cov) / sqrt(double(var_i) * double(var_j));  // 0/0 -> NaN as np.corrcoef
               q = q > 1.0 ? 1.0 : (q < -1.0 ? -1.0 : q);
               r = float(q);
             } else if constexpr (KIND == MOM_COSINE) {
-              const int64_t syy = meta->csq[cc];
+              const int64_t syy = meta->csq[cg];
               r = (sxx == 0 || syy == 0) ? 0.0f
                                          : float(double(sxy) / sqrt(double(sxx) * double(syy)));
             } else {  // JACCARD: float32 division of exact integers, as metrics.py:443-447

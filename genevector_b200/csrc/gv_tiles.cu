@@ -125,29 +125,44 @@ int gram_dump_dispatch(const void* operand, int64_t op_rows, int64_t kp, const i
   return set_error(GV_ERR_ARG, "gram dump: active_rows must be 32 or 30");
 }
 
-int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
-                          const int64_t* gsum, const int64_t* gsq, const int32_t* marg,
-                          int64_t n_cells, int n_genes, const int32_t* tiles, int64_t n_tiles,
-                          int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
-                          void* sync_ws, cudaStream_t st) {
-  MomentParams p;
-  p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
-  p.ld_out = ld_out; p.G = n_genes; p.n_cells = n_cells;
+template <int L>
+static int moment_dispatch_l(int kind, int cta_group, const void* val_rows, int64_t op_rows, int64_t kp,
+                             const int32_t* tiles, int64_t n_tiles, const MomentParams& p,
+                             void* sync_ws, cudaStream_t st) {
   switch (kind) {
     case GV_MOM_SIGN:
-      if (!sgn || !gsum || !gsq) return set_error(GV_ERR_ARG, "sign needs sgn, gsum, gsq");
-      return launch_cg<MomentEpi<MOM_SIGN>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+      return launch_cg<MomentEpi<MOM_SIGN, L>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case GV_MOM_PEARSON:
-      if (!out || !gsum || !gsq) return set_error(GV_ERR_ARG, "pearson needs out, gsum, gsq");
-      return launch_cg<MomentEpi<MOM_PEARSON>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+      return launch_cg<MomentEpi<MOM_PEARSON, L>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case GV_MOM_COSINE:
-      if (!out || !gsum || !gsq) return set_error(GV_ERR_ARG, "cosine needs out, gsum, gsq");
-      return launch_cg<MomentEpi<MOM_COSINE>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+      return launch_cg<MomentEpi<MOM_COSINE, L>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case GV_MOM_JACCARD:
-      if (!out || !marg) return set_error(GV_ERR_ARG, "jaccard needs out, marg");
-      return launch_cg<MomentEpi<MOM_JACCARD>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+      return launch_cg<MomentEpi<MOM_JACCARD, L>>(cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
   }
   return set_error(GV_ERR_ARG, "unknown moment kind");
+}
+
+int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
+                          const int64_t* gsum, const int64_t* gsq, const int32_t* marg,
+                          int64_t n_cells, int n_genes, int n_limbs, int limb_bits,
+                          const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
+                          float* out, int64_t ld_out, int cta_group, void* sync_ws, cudaStream_t st) {
+  MomentParams p;
+  p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
+  p.ld_out = ld_out; p.G = n_genes; p.n_cells = n_cells; p.limb_bits = limb_bits;
+  if (kind == GV_MOM_SIGN && (!sgn || !gsum || !gsq)) return set_error(GV_ERR_ARG, "sign needs sgn, gsum, gsq");
+  if ((kind == GV_MOM_PEARSON || kind == GV_MOM_COSINE) && (!out || !gsum || !gsq))
+    return set_error(GV_ERR_ARG, "pearson / cosine need out, gsum, gsq");
+  if (kind == GV_MOM_JACCARD && (!out || !marg || n_limbs != 1))
+    return set_error(GV_ERR_ARG, "jaccard needs out, marg and one detection row per gene");
+  if (limb_bits < 1 || limb_bits > 7) return set_error(GV_ERR_ARG, "limb_bits must be in [1,7]");
+  // exactness: every digit product summed over all cells must fit the (unsigned) 32-bit accumulator
+  const uint64_t dmax = (1ull << limb_bits) - 1ull;
+  if (uint64_t(n_cells) * dmax * dmax >= (1ull << 32))
+    return set_error(GV_ERR_UNSUPPORTED, "co-moment accumulators would overflow: lower limb_bits");
+  if (n_limbs == 1) return moment_dispatch_l<1>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+  if (n_limbs == 2) return moment_dispatch_l<2>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+  return set_error(GV_ERR_UNSUPPORTED, "co-moment path supports one or two digits per gene");
 }
 
 }  // namespace gv

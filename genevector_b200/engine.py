@@ -77,8 +77,9 @@ class BinBlock:
     edges: torch.Tensor          # float64 [G][16]
     gsum: torch.Tensor           # int64 [G]
     gsq: torch.Tensor            # int64 [G]
-    val_rows: Optional[torch.Tensor]   # int8 [G_pad][kp] or None
-    val_mode: int                # -1 none, 0 limbs, 1 detection indicator
+    val_rows: Optional[torch.Tensor]   # int8 [G * n_limbs][kp] or None
+    val_mode: int                # -1 none, 0 count digits, 1 detection indicator
+    n_limbs: int                 # INT8 rows per gene in val_rows (1 or 2)
     limb_bits: int
     data_flags: tuple            # (flag bits, max value)
     path_used: int = 0           # gv_disc_path the discretisation took (1 counts, 2 general)
@@ -92,22 +93,26 @@ class BinBlock:
         return np.ascontiguousarray(full[:, :self.n_cells].T)
 
 
-def block_layout(n_cells: int, n_genes: int, val_mode: int):
-    """Byte offsets of the sections of the broadcast block."""
+HEADER_BYTES = 256   # int64[0] = n_limbs, [1] = limb_bits, [2] = data flag bits, [3] = max value
+
+
+def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1):
+    """Byte offsets of the sections of the broadcast block.  The value rows come last, so a
+    two-digit block is the one-digit block plus a tail."""
     kp = _align(max(n_cells, 1), 128)
     pitch = kp // 2
     off, lay = 0, {}
-    for name, nbytes in (("bins", n_genes * pitch), ("marg", n_genes * 16 * 4),
-                         ("nbpg", n_genes * 4), ("edges", n_genes * 16 * 8),
-                         ("gsum", n_genes * 8), ("gsq", n_genes * 8),
-                         ("val", (n_genes * kp) if val_mode >= 0 else 0)):
+    for name, nbytes in (("header", HEADER_BYTES), ("bins", n_genes * pitch),
+                         ("marg", n_genes * 16 * 4), ("nbpg", n_genes * 4),
+                         ("edges", n_genes * 16 * 8), ("gsum", n_genes * 8), ("gsq", n_genes * 8),
+                         ("val", (n_genes * n_limbs * kp) if val_mode >= 0 else 0)):
         lay[name] = (off, nbytes)
         off += _align(nbytes)
     return kp, pitch, lay, off
 
 
-def _views(buf, n_cells, n_genes, n_bins, val_mode, limb_bits, flags=(0, 0)) -> BinBlock:
-    kp, pitch, lay, _ = block_layout(n_cells, n_genes, val_mode)
+def _views(buf, n_cells, n_genes, n_bins, val_mode, n_limbs, limb_bits, flags=(0, 0)) -> BinBlock:
+    kp, pitch, lay, _ = block_layout(n_cells, n_genes, val_mode, n_limbs)
 
     def v(name, dtype, shape):
         o, nb = lay[name]
@@ -119,8 +124,8 @@ def _views(buf, n_cells, n_genes, n_bins, val_mode, limb_bits, flags=(0, 0)) -> 
         n_bins_per_gene=v("nbpg", torch.int32, (n_genes,)),
         edges=v("edges", torch.float64, (n_genes, 16)), gsum=v("gsum", torch.int64, (n_genes,)),
         gsq=v("gsq", torch.int64, (n_genes,)),
-        val_rows=v("val", torch.int8, (n_genes, kp)) if val_mode >= 0 else None,
-        val_mode=val_mode, limb_bits=limb_bits, data_flags=flags)
+        val_rows=v("val", torch.int8, (n_genes * n_limbs, kp)) if val_mode >= 0 else None,
+        val_mode=val_mode, n_limbs=n_limbs, limb_bits=limb_bits, data_flags=flags)
 
 
 def tile_slice(op_rows: int, cta_group: int, band: int, rank: int = 0, world: int = 1):
@@ -230,37 +235,53 @@ class Engine:
 
     # ------------------------------------------------------------------ discretisation
     def discretize(self, csr: CsrDevice, n_bins: int = 10, val_mode: int = -1,
-                   buf: Optional[torch.Tensor] = None, path: int = _lib.GV_PATH_AUTO) -> BinBlock:
+                   buf: Optional[torch.Tensor] = None, path: int = _lib.GV_PATH_AUTO,
+                   n_limbs: Optional[int] = None) -> BinBlock:
         """gv_discretize_csr.  val_mode: -1 no value rows, 0 count digits (sign / pearson / cosine),
-        1 detection indicator (jaccard)."""
+        1 detection indicator (jaccard).  n_limbs None = one digit per gene, retried with two when
+        the counts do not fit one (values up to 2^(2*limb_bits) - 1)."""
         if not 1 <= n_bins <= 15:
             raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
+        if csr.values.dtype not in (torch.float32, torch.float64):
+            raise GvError("discretize", -1, "values must be float32 or float64")
+        auto_limbs = n_limbs is None and val_mode == 0
+        L = 1 if (n_limbs is None or val_mode != 0) else n_limbs
         with torch.cuda.device(self.device):
-            kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, val_mode)
-            if buf is None:
-                buf = torch.empty(total, dtype=torch.uint8, device=self.device)
-            assert buf.numel() >= total and buf.device == self.device
             lb = limb_bits_for(max(csr.n_cells, 1)) if val_mode == 0 else 7
-            blk = _views(buf, csr.n_cells, csr.n_genes, n_bins, val_mode, lb)
             dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
-            if csr.values.dtype not in (torch.float32, torch.float64):
-                raise GvError("discretize", -1, "values must be float32 or float64")
             ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             q = quantile_table()
-            flags = np.zeros(2, dtype=np.uint64)
-            used = np.zeros(1, dtype=np.int32)
-            vr = blk.val_rows
-            self._call("gv_discretize_csr", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(),
-                      csr.row_ptr.data_ptr(), csr.n_cells, csr.n_genes, csr.nnz, n_bins,
-                      q.ctypes.data, blk.bins.data_ptr(), pitch, blk.n_bins_per_gene.data_ptr(),
-                      blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(),
-                      blk.gsq.data_ptr(), vr.data_ptr() if vr is not None else None, kp,
-                      csr.n_genes if vr is not None else 0, max(val_mode, 0), 1, lb,
-                      flags.ctypes.data, ws.data_ptr(), ws_bytes, path, used.ctypes.data,
-                      self._stream())
+            while True:
+                kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, val_mode, L)
+                b = buf if (buf is not None and buf.numel() >= total) else \
+                    torch.empty(total, dtype=torch.uint8, device=self.device)
+                assert b.device == self.device
+                blk = _views(b, csr.n_cells, csr.n_genes, n_bins, val_mode, L, lb)
+                flags = np.zeros(2, dtype=np.uint64)
+                used = np.zeros(1, dtype=np.int32)
+                vr = blk.val_rows
+                try:
+                    self._call("gv_discretize_csr", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(),
+                               csr.row_ptr.data_ptr(), csr.n_cells, csr.n_genes, csr.nnz, n_bins,
+                               q.ctypes.data, blk.bins.data_ptr(), pitch, blk.n_bins_per_gene.data_ptr(),
+                               blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(),
+                               blk.gsq.data_ptr(), vr.data_ptr() if vr is not None else None, kp,
+                               csr.n_genes * L if vr is not None else 0, max(val_mode, 0), L, lb,
+                               flags.ctypes.data, ws.data_ptr(), ws_bytes, path, used.ctypes.data,
+                               self._stream())
+                except GvError as e:
+                    fits_two = int(flags[0]) == 0 and int(flags[1]) < (1 << (2 * lb))
+                    if auto_limbs and L == 1 and e.status == -4 and "limb range" in str(e) and fits_two:
+                        L = 2          # counts above one digit: redo with two INT8 rows per gene
+                        continue
+                    raise
+                break
             blk.data_flags = (int(flags[0]), int(flags[1]))
             blk.path_used = int(used[0])
+            hdr = torch.tensor([L, lb, int(flags[0]), int(flags[1]) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64)
+            o, _ = lay["header"]
+            b[o:o + 32].view(torch.int64).copy_(hdr)
             return blk
 
     def expand_onehot(self, blk: BinBlock) -> tuple:
@@ -286,11 +307,13 @@ class Engine:
                       out.data_ptr(), rows, cg, active_rows, self._stream())
             return out
 
-    def sign_tiles_for(self, mi_tiles: np.ndarray, B: int) -> torch.Tensor:
-        """Sign-map tiles (256 x 256 genes) that cover the gene pairs of the given MI tiles
-        (operand-row coordinates), so a rank only computes the part of the sign map it reads."""
+    def sign_tiles_for(self, mi_tiles: np.ndarray, B: int, n_limbs: int = 1) -> torch.Tensor:
+        """Sign-map tiles (operand rows of the value matrix: n_limbs rows per gene) that cover the
+        gene pairs of the given MI tiles (one-hot operand rows), so a rank only computes the part
+        of the sign map it reads."""
         gpb = 32 // B
         tm = _lib.call("gv_tile_m", self.cta_group)
+        gr, gc = tm // n_limbs, 256 // n_limbs          # genes per sign tile side
         r_lo = mi_tiles[:, 0].astype(np.int64) // 32 * gpb
         r_hi = (mi_tiles[:, 0].astype(np.int64) + tm) // 32 * gpb - 1
         c_lo = mi_tiles[:, 1].astype(np.int64) // 32 * gpb
@@ -298,8 +321,9 @@ class Engine:
         keys = set()
         for rr in (r_lo, r_hi):
             for cc in (c_lo, c_hi):
-                # an MI tile spans < 256 genes per side, so its corners hit every sign tile it touches
-                keys.update(np.unique((rr // tm) * (1 << 32) + (cc // 256)).tolist())
+                # an MI tile spans fewer genes per side than a sign tile, so its corners hit every
+                # sign tile it touches
+                keys.update(np.unique((rr // gr) * (1 << 32) + (cc // gc)).tolist())
         arr = np.array(sorted(keys), dtype=np.int64)
         st = np.stack([(arr >> 32) * tm, (arr & 0xFFFFFFFF) * 256], axis=1)
         st = st[st[:, 0] <= st[:, 1] + 255]          # tiles holding some (row <= col)
@@ -313,14 +337,15 @@ class Engine:
             G = blk.n_genes
             ld = _align(G, 16)
             sgn = torch.zeros((G, ld), dtype=torch.int8, device=self.device)
+            rows = G * blk.n_limbs
             if tiles is None:
-                tiles, n, _ = self.schedule(G)
+                tiles, n, _ = self.schedule(rows)
             else:
                 n = int(tiles.shape[0])
-            self._call("gv_moment_tiles", _lib.GV_MOM_SIGN, blk.val_rows.data_ptr(), G, blk.kp,
-                      blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
-                      tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0, self.cta_group,
-                      self._sync_ptr(G * blk.kp), self._stream())
+            self._call("gv_moment_tiles", _lib.GV_MOM_SIGN, blk.val_rows.data_ptr(), rows, blk.kp,
+                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
+                       blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0,
+                       self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
             return sgn
 
     def moment_scores(self, blk: BinBlock, kind: int, out: Optional[torch.Tensor] = None,
@@ -331,11 +356,12 @@ class Engine:
             G = blk.n_genes
             if out is None:
                 out = torch.zeros((G, G), dtype=torch.float32, device=self.device)
-            tiles, n, _ = self.schedule(G, rank=rank, world=world)
-            self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), G, blk.kp,
-                      blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
-                      tiles.data_ptr(), n, None, 0, out.data_ptr(), out.stride(0), self.cta_group,
-                      self._sync_ptr(G * blk.kp), self._stream())
+            rows = G * blk.n_limbs
+            tiles, n, _ = self.schedule(rows, rank=rank, world=world)
+            self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), rows, blk.kp,
+                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
+                       blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, None, 0, out.data_ptr(),
+                       out.stride(0), self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
             return out
 
     def mi_scores(self, blk: BinBlock, onehot: torch.Tensor, B: int,
@@ -357,16 +383,28 @@ class Engine:
 
     # ------------------------------------------------------------------ whole paths
     def _replicate(self, blk_or_none, n_cells, n_genes, n_bins, val_mode, group) -> BinBlock:
-        """The single collective of the path: broadcast the bin block from rank 0."""
-        _, _, _, total = block_layout(n_cells, n_genes, val_mode)
+        """The single collective of the path: broadcast the bin block from rank 0.  The header at
+        the front of the block says whether the value rows have one or two digits per gene; only in
+        the two-digit case (counts > 2^limb_bits - 1) is the extra tail sent by a second broadcast."""
+        _, _, lay, total1 = block_layout(n_cells, n_genes, val_mode, 1)
+        _, _, _, total2 = block_layout(n_cells, n_genes, val_mode, 2)
         if blk_or_none is not None:
-            buf, lb, flags = blk_or_none.buf, blk_or_none.limb_bits, blk_or_none.data_flags
+            buf = blk_or_none.buf
         else:
-            buf = torch.empty(total, dtype=torch.uint8, device=self.device)
-            lb = limb_bits_for(max(n_cells, 1)) if val_mode == 0 else 7
-            flags = (0, 0)
-        broadcast_block(buf, total, group)
-        return _views(buf, n_cells, n_genes, n_bins, val_mode, lb, flags)
+            buf = torch.empty(total1, dtype=torch.uint8, device=self.device)
+        broadcast_block(buf, total1, group)
+        o, _ = lay["header"]
+        hdr = buf[o:o + 32].view(torch.int64).cpu()
+        L, lb, flags = int(hdr[0]), int(hdr[1]), (int(hdr[2]), int(hdr[3]))
+        if L == 2:
+            if blk_or_none is None:
+                big = torch.empty(total2, dtype=torch.uint8, device=self.device)
+                big[:total1].copy_(buf)
+                buf = big
+            import torch.distributed as dist
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast(buf[total1:total2], src=src, group=group)
+        return _views(buf, n_cells, n_genes, n_bins, val_mode, L, lb, flags)
 
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
                     signed: bool = False, rank: int = 0, world: int = 1, group=None,
@@ -389,10 +427,10 @@ class Engine:
             st = None
             if world > 1:
                 rows = _lib.check("gv_onehot_rows", self.lib.gv_onehot_rows(n_genes, B))
-                key = ("sign", rows, self.cta_group, self.band, rank, world)
+                key = ("sign", rows, self.cta_group, self.band, rank, world, blk.n_limbs)
                 if key not in self._sched_cache:
                     mine, _ = tile_slice(rows, self.cta_group, self.band, rank, world)
-                    self._sched_cache[key] = self.sign_tiles_for(mine, B)
+                    self._sched_cache[key] = self.sign_tiles_for(mine, B, blk.n_limbs)
                 st = self._sched_cache[key]
             sgn = self.sign_matrix(blk, tiles=st)
         onehot, B = self.expand_onehot(blk)

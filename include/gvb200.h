@@ -141,13 +141,16 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t
                  void* stream);
 
 /* ---------------------------------------------------------------- co-moment targets
- * One INT8 row per gene (val_rows from gv_discretize_csr).  kind GV_MOM_SIGN writes int8 `sgn`
- * (both triangles, 0 on the diagonal); the other kinds write float32 `out` like gv_mi_tiles.
- * Exact integer co-moments: requires n_cells * (2^limb_bits - 1)^2 < 2^32. */
+ * val_rows from gv_discretize_csr: n_limbs INT8 rows per gene (row = gene*n_limbs + digit, base
+ * 2^limb_bits digits of the count; one 0/1 row for GV_MOM_JACCARD), op_rows >= n_genes*n_limbs;
+ * tiles are in operand rows.  kind GV_MOM_SIGN writes int8 `sgn` (both triangles, 0 on the
+ * diagonal); the other kinds write float32 `out` like gv_mi_tiles.  The co-moments are exact
+ * integers: requires n_cells * (2^limb_bits - 1)^2 < 2^32 and n_limbs in {1, 2}. */
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
-                    int n_genes, const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
-                    float* out, int64_t ld_out, int cta_group, void* sync_ws, void* stream);
+                    int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
+                    int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
+                    void* sync_ws, void* stream);
 
 /* ---------------------------------------------------------------- score-building fast path
  * Replaces GeneVectorDataset._build_training_tensors (data.py:377-411) for a dense device score

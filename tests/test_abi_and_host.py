@@ -101,6 +101,10 @@ def test_block_layout_and_limbs():
         assert o1 % 256 == 0 and o1 + n1 <= o2
     assert total >= offs[-1][0] + offs[-1][1]
     assert block_layout(5000, 2000, -1)[2]["val"][1] == 0
+    # a two-digit block is the one-digit block plus a tail (what the second broadcast sends)
+    _, _, lay2, total2 = block_layout(5000, 2000, 0, 2)
+    assert all(lay2[k] == lay[k] for k in lay if k != "val")
+    assert lay2["val"][0] == lay["val"][0] and lay2["val"][1] == 2 * lay["val"][1] and total2 > total
     assert limb_bits_for(200000) == 7 and limb_bits_for(266287) == 7 and limb_bits_for(300000) == 6
     q = quantile_table()
     assert np.array_equal(q[10, :9], np.linspace(0, 100, 11)[1:-1] / 100)

@@ -38,7 +38,7 @@ def _worker(rank, world, port, tmp):
     buf = torch.zeros(total, dtype=torch.uint8)
     if rank == 0:
         # rank 0 "discretises": fill the block exactly as gv_discretize_csr lays it out
-        blk = E._views(buf, n_cells, n_genes, n_bins, val_mode, 7)
+        blk = E._views(buf, n_cells, n_genes, n_bins, val_mode, 1, 7)
         bins_gm, nb, _ = orc.discretize_csr_c(z["X"], n_bins)
         packed = np.zeros((n_genes, pitch), dtype=np.uint8)
         padded = np.zeros((n_genes, pitch * 2), dtype=np.uint8)
@@ -52,7 +52,7 @@ def _worker(rank, world, port, tmp):
         marg[:, 0] = (bins_gm > 0).sum(axis=1)
         blk.marg.copy_(torch.from_numpy(marg))
     E.broadcast_block(buf, total)                       # the one collective
-    blk = E._views(buf, n_cells, n_genes, n_bins, val_mode, 7)
+    blk = E._views(buf, n_cells, n_genes, n_bins, val_mode, 1, 7)
     x_disc = blk.x_disc()
     assert np.array_equal(x_disc, z["x_disc"].astype(np.int32)), "block did not survive the broadcast"
     assert np.array_equal(blk.n_bins_per_gene.numpy(), z["n_bins_per_gene"])

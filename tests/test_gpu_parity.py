@@ -328,6 +328,41 @@ def test_count_path_falls_back_and_refuses(engine):
     assert np.array_equal(blk.x_disc(), xd) and np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
     with pytest.raises(GvError, match="count-data path"):
         engine.discretize(csr, 10, path=_lib.GV_PATH_COUNTS)
-    # signed MI on such data is refused (one 7-bit limb): fail loudly, no silent fallback
+    # signed MI on such data takes two 7-bit digits per gene (counts up to 16383)
+    blk2 = engine.discretize(csr, 10, val_mode=0)
+    assert blk2.n_limbs == 2 and blk2.val_rows.shape[0] == 40
+    Xd = np.asarray(X.todense()).astype(np.int64)
+    vr = blk2.val_rows.cpu().numpy()[:, :300].astype(np.int64)
+    assert np.array_equal(vr[0::2] + (vr[1::2] << blk2.limb_bits), Xd.T)
+    want, _ = orc.mi_pairs_c(xd, nb, corr=orc.sign_int_c(X).astype(np.float64), sign_mode=1)
+    out = engine.mi_from_csr(csr, 300, 20, signed=True).cpu().numpy()
+    assert np.abs(out - want).max() <= MI_TOL
+    # counts beyond two digits are refused loudly
+    Xbig = X.copy(); Xbig.data[0] = 20000.0
     with pytest.raises(GvError, match="limb range"):
-        engine.mi_from_csr(csr, 300, 20, signed=True)
+        engine.mi_from_csr(engine.upload_csr(Xbig), 300, 20, signed=True)
+    with pytest.raises(GvError, match="non-negative integer"):
+        Xf = X.copy(); Xf.data[0] = 2.5
+        engine.mi_from_csr(engine.upload_csr(Xf), 300, 20, signed=True)
+
+
+@pytest.mark.parametrize("n_cells,n_genes,seed", [(900, 300, 31), (1300, 150, 32)])
+def test_two_digit_counts_matrix_targets_and_sign(engine, n_cells, n_genes, seed):
+    """Counts up to a few thousand (two INT8 digits per gene): sign map exact, Pearson / cosine
+    against np.corrcoef / sklearn, on a case with several 128-gene tiles."""
+    from genevector_b200 import _lib
+    from genevector_b200.synth import synth_counts
+    from oracle import oracle as orc
+    X = synth_counts(n_cells, n_genes, seed=seed)
+    rng = np.random.default_rng(seed)
+    X.data = (X.data * rng.integers(1, 300, size=X.data.shape)).astype(np.float32)
+    assert 127 < X.data.max() < 16384
+    csr = engine.upload_csr(X)
+    blk = engine.discretize(csr, 10, val_mode=0)
+    assert blk.n_limbs == 2
+    assert np.array_equal(engine.sign_matrix(blk).cpu().numpy()[:, :n_genes], orc.sign_int_c(X))
+    p = engine.moment_scores(blk, _lib.GV_MOM_PEARSON).cpu().numpy().astype(np.float64)
+    want = orc.pearson_np(X); np.fill_diagonal(want, 0.0)
+    assert np.abs(p - want).max() <= 2e-6
+    c = engine.moment_scores(blk, _lib.GV_MOM_COSINE).cpu().numpy().astype(np.float64)
+    assert np.abs(c - orc.cosine_np(X)).max() <= 2e-6
