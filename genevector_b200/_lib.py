@@ -41,6 +41,7 @@ SIGNATURES = {
     "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _i32, _vp, _vp]),
+    "gv_gene_entropy": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "gv_rows_per_gene": (_i32, [_i32]),
     "gv_onehot_rows": (_i64, [_i32, _i32]),
     "gv_expand_onehot": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp]),

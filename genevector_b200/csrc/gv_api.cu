@@ -103,6 +103,17 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
   return discretize_dispatch(a, static_cast<cudaStream_t>(stream));
 }
 
+int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
+                    int64_t n_cells, int n_genes, double* entropy_out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (n_genes <= 0 || n_cells < 0 || nnz < 0 || !entropy_out || !workspace || (nnz > 0 && (!values || !col_idx)))
+    return set_error(GV_ERR_ARG, "gv_gene_entropy: bad argument");
+  return gene_entropy_dispatch(values, value_dtype, col_idx, nnz, n_cells, n_genes, entropy_out, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int gv_rows_per_gene(int n_bins) {
   if (n_bins < 1 || n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
   if (n_bins <= 5) return 5;

@@ -657,6 +657,54 @@ k_assign_csr(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
   }
 }
 
+// ---------------------------------------------------------------- k_gene_entropy
+// GeneVectorDataset.get_gene_entropy (data.py:186-203): per gene, np.unique(column,
+// return_counts=True), drop the first count (the smallest value's: the zeros when the gene has any,
+// data.py:201-202) and scipy.stats.entropy (natural log) of the rest.  One warp per gene over the
+// value histogram of the count-data path; the zero count is n_cells minus the positive entries.
+__global__ void k_gene_entropy(const uint32_t* __restrict__ hist, int G, int64_t n_cells,
+                               double* __restrict__ ent) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
+    uint32_t c[8];
+    const uint4* hp = reinterpret_cast<const uint4*>(hist + int64_t(g) * VH + lane * 8);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    c[0] = h0.x; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w; c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
+    long long pos = 0;
+    int first = VH;                       // smallest value present
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pos += c[i];
+      if (c[i] && lane * 8 + i < first) first = lane * 8 + i;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+      pos += __shfl_xor_sync(0xffffffffu, pos, d);
+      const int o = __shfl_xor_sync(0xffffffffu, first, d);
+      first = o < first ? o : first;
+    }
+    const long long zeros = n_cells - pos;
+    // counts kept = all positive-value counts, minus the smallest one when there are no zeros
+    const int drop = zeros > 0 ? -1 : first;
+    long long kept = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kept += (lane * 8 + i == drop) ? 0 : c[i];
+    for (int d = 16; d >= 1; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
+    double h = 0.0;
+    if (kept > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (c[i] && lane * 8 + i != drop) {
+          const double pk = double(c[i]) / double(kept);
+          h -= pk * log(pk);
+        }
+      }
+    }
+    for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    if (lane == 0) ent[g] = h;
+  }
+}
+
 // ================================================================ host-side launchers
 #define GV_LAUNCH_CHECK()                                     \
   do {                                                        \
@@ -772,6 +820,40 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   GV_LAUNCH_CHECK();
   if (a.path_used) *a.path_used = GV_PATH_GENERAL;
   return GV_OK;
+}
+
+template <typename T>
+static int gene_entropy_impl(const void* values, const int32_t* col_idx, int64_t nnz, int64_t n_cells,
+                             int G, double* ent, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t need = 256 + ((size_t(G) * VH * 4 + 255) & ~size_t(255));
+  if (ws_bytes < need) return set_error(GV_ERR_ARG, "gene entropy: workspace too small");
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(ws);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + 256);
+  GV_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
+  const int sms = device_sm_count();
+  if (nnz > 0) {
+    k_hist2d<T><<<sms * 8, 256, 0, st>>>(static_cast<const T*>(values), col_idx, nnz, hist, flags);
+    GV_LAUNCH_CHECK();
+  }
+  unsigned long long hflags[2] = {0, 0};
+  GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
+  GV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (hflags[0] != 0 || hflags[1] >= (unsigned long long)VH)
+    return set_error(GV_ERR_UNSUPPORTED, "gene entropy needs non-negative integer counts <= 255");
+  k_gene_entropy<<<(G + 7) / 8, 256, 0, st>>>(hist, G, n_cells, ent);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
+int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
+                          int64_t n_cells, int G, double* ent, void* workspace, size_t ws_bytes,
+                          cudaStream_t st) {
+  if (value_dtype == GV_F32)
+    return gene_entropy_impl<float>(values, col_idx, nnz, n_cells, G, ent, workspace, ws_bytes, st);
+  if (value_dtype == GV_F64)
+    return gene_entropy_impl<double>(values, col_idx, nnz, n_cells, G, ent, workspace, ws_bytes, st);
+  return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {

@@ -95,6 +95,15 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
                       void* workspace, size_t workspace_bytes, int path, int* path_used_host,
                       void* stream);
 
+/* ---------------------------------------------------------------- gene entropy
+ * Replaces GeneVectorDataset.get_gene_entropy (data.py:186-203), which runs before every score
+ * computation (data.py:349): per gene the entropy (nats) of the counts of its unique values after
+ * dropping the first.  Count data only (non-negative integers <= 255).  entropy_out float64 [n_genes];
+ * workspace >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype) bytes. */
+int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
+                    int64_t n_cells, int n_genes, double* entropy_out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- operand layout
  * rows_per_gene B for a given n_bins: 5 (n_bins<=5), 8 (<=8), 10 (<=10), 16 (<=15).
  * The one-hot operand has 32-row blocks of floor(32/B) genes x B non-zero bins (+ zero rows). */

@@ -279,3 +279,16 @@ def round5_dict_matrix(M):
     R = np.round(np.asarray(M, dtype=np.float64), 5)
     np.fill_diagonal(R, 0.0)
     return R
+
+
+# --------------------------------------------------------------------------- gene entropy
+def gene_entropy_np(X):
+    """GeneVectorDataset.get_gene_entropy (data.py:186-203): per gene, scipy entropy of the counts
+    of the unique values with the first count dropped."""
+    from scipy.stats import entropy
+    Xd = _dense(X).T
+    out = np.zeros(Xd.shape[0])
+    for g, exp in enumerate(Xd):
+        counts = np.unique(exp, return_counts=True)
+        out[g] = entropy(counts[1][1:])
+    return out

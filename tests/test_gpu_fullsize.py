@@ -160,3 +160,37 @@ def test_c5_matrix_targets_sampled(engine):
         else:
             assert np.abs(got - want).max() <= tol + 1e-6, np.abs(got - want).max()
         del out
+
+
+def test_c1_pbmc_like_full_vs_oracle_and_training_handoff(engine):
+    """configs[0] stand-in (example/PBMC.h5ad is a missing blob): 1,000 genes x 13,000 cells,
+    seed 42; every pair against the oracle, then the hand-off to the trainer: the (i_idx, j_idx,
+    xij) tensors drive two steps of the reference's training objective (model.py:82-85,149-150,
+    172-199: two embedding tables, row-wise dot product, MSE, Adadelta) restated here."""
+    from oracle import oracle as orc
+    from genevector_b200.data import build_training_tensors, compute_target_scores, get_gene_entropy
+    from genevector_b200.synth import synth_counts, gene_names
+    G, N = 1000, 13000
+    X = synth_counts(N, G, seed=42)
+    genes = gene_names(G)
+    bins_gm, nb, _ = orc.discretize_csr_c(X, 10)
+    want, _ = orc.mi_pairs_gm_c(bins_gm, nb, sign=orc.sign_int_c(X))
+    sm = compute_target_scores(X, genes, target="mi", signed_mi=True, mi_backend="b200", device="cuda")
+    assert np.abs(sm.matrix.astype(np.float64) - want).max() <= MI_TOL
+    ent = get_gene_entropy(X, genes)
+    assert np.abs(np.array([ent[g] for g in genes]) - orc.gene_entropy_np(X)).max() < 1e-12
+    i_idx, j_idx, xij = build_training_tensors(sm, genes, c=100.0, signed_mi=True, device="cuda")
+    assert i_idx.numel() == G * (G - 1) and xij.is_cuda
+    torch.manual_seed(0)
+    wi = torch.nn.Embedding(G, 100).cuda()
+    wj = torch.nn.Embedding(G, 100).cuda()
+    opt = torch.optim.Adadelta(list(wi.parameters()) + list(wj.parameters()))
+    losses = []
+    for _ in range(2):
+        opt.zero_grad()
+        pred = (wi(i_idx) * wj(j_idx)).sum(dim=1)
+        loss = torch.nn.functional.mse_loss(pred, xij)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert np.isfinite(losses).all() and losses[1] < losses[0]

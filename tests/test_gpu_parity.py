@@ -366,3 +366,19 @@ def test_two_digit_counts_matrix_targets_and_sign(engine, n_cells, n_genes, seed
     assert np.abs(p - want).max() <= 2e-6
     c = engine.moment_scores(blk, _lib.GV_MOM_COSINE).cpu().numpy().astype(np.float64)
     assert np.abs(c - orc.cosine_np(X)).max() <= 2e-6
+
+
+def test_gene_entropy_matches_reference(engine):
+    """data.py:186-203 incl. its quirk of dropping the first unique value even when it is not 0."""
+    from genevector_b200.data import get_gene_entropy
+    from genevector_b200.engine import GvError
+    from oracle import oracle as orc
+    z = load_golden("synth_counts_700x96_b10")      # has an all-zero gene, constants, a dense gene
+    genes = [f"GENE{i}" for i in range(96)]
+    got = get_gene_entropy(z["X"], genes)
+    want = orc.gene_entropy_np(z["X"])
+    assert list(got) == genes
+    assert np.abs(np.array([got[g] for g in genes]) - want).max() < 1e-12
+    zl = load_golden("lognorm_f32_300x40_b7")
+    with pytest.raises(GvError, match="integer counts"):
+        get_gene_entropy(zl["X"], [f"G{i}" for i in range(40)])
