@@ -29,6 +29,18 @@ def import_reference_metrics():
     return importlib.import_module("genevector.metrics")
 
 
+def import_reference_data():
+    return importlib.import_module("genevector.data")
+
+
+class _FakeAnnData:
+    """The two attributes GeneVectorDataset.get_gene_entropy touches (data.py:196-198)."""
+    def __init__(self, X, genes):
+        import pandas
+        self.X = X
+        self.var = pandas.DataFrame(index=genes)
+
+
 def dict_to_matrix(scores, genes):
     idx = {g: i for i, g in enumerate(genes)}
     M = np.zeros((len(genes), len(genes)), dtype=np.float64)
@@ -126,6 +138,11 @@ def make_case(refm, name, X, n_bins, with_targets=True, with_numba=True):
         x_disc=X_disc.astype(np.int8), n_bins_per_gene=nb, edges=edges_c,
         mi_raw=raw, mi_unsigned_round5=mi_u, mi_signed_round5=mi_s, corr_sign=fsign,
         int_sign=isign, n_sign_ambiguous=np.int64(n_amb), **joints)
+    # gene entropy straight from the reference's GeneVectorDataset.get_gene_entropy (data.py:186-203)
+    refd = import_reference_data()
+    ent = refd.GeneVectorDataset.get_gene_entropy(_FakeAnnData(X, genes))
+    out["gene_entropy"] = np.array([ent[g] for g in genes])
+    assert np.array_equal(out["gene_entropy"], orc.gene_entropy_np(X), equal_nan=True), name
     if with_targets:
         out["pearson"] = dict_to_matrix(refm.target_pearson(X, genes), genes)
         out["cosine"] = dict_to_matrix(refm.target_cosine(X, genes), genes)

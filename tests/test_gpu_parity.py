@@ -377,6 +377,7 @@ def test_gene_entropy_matches_reference(engine):
     genes = [f"GENE{i}" for i in range(96)]
     got = get_gene_entropy(z["X"], genes)
     want = orc.gene_entropy_np(z["X"])
+    assert np.array_equal(want, z["gene_entropy"])          # the reference's own output
     assert list(got) == genes
     assert np.abs(np.array([got[g] for g in genes]) - want).max() < 1e-12
     zl = load_golden("lognorm_f32_300x40_b7")

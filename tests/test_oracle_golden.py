@@ -88,3 +88,9 @@ def test_matrix_target_oracles():
     assert np.allclose(orc.round5_dict_matrix(orc.pearson_np(z["X"])), z["pearson"], atol=1e-12)
     assert np.allclose(orc.round5_dict_matrix(orc.cosine_np(z["X"])), z["cosine"], atol=1e-12)
     assert np.allclose(orc.round5_dict_matrix(orc.jaccard_np(z["X"])), z["jaccard"], atol=1e-12)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_gene_entropy_oracle_matches_reference(case):
+    z = load_golden(case)
+    assert np.array_equal(orc.gene_entropy_np(z["X"]), z["gene_entropy"], equal_nan=True)
