@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--unsigned", action="store_true", help="plain MI (no Pearson sign pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=2)
+    ap.add_argument("--operand", default="int8", choices=["int8", "fp4"],
+                    help="storage of the one-hot operand (fp4: tcgen05 kind::mxf4, exact counts)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -181,6 +183,7 @@ def main():
     wl, G, N = parse_workload(args.workload)
     pairs = G * (G - 1) // 2
     eng = Engine(dev, cta_group=args.cta_group)
+    eng.operand = args.operand
 
     # ---- synthetic input: generated on rank 0's device, staged to pinned host for the e2e leg
     csr = None
@@ -203,7 +206,7 @@ def main():
     out = torch.zeros((G, G), dtype=torch.float32, device=dev)
     res_host = torch.empty((max(g_hi - g_lo, 1), G), dtype=torch.float32, pin_memory=True)
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
-    operand_bytes = op_rows * ((N + 127) // 128 * 128)
+    operand_bytes = op_rows * ((N + 255) // 256 * 256) // (2 if args.operand == "fp4" else 1)
     flush_needed = operand_bytes <= 2 * L2_BYTES
 
     def barrier():
@@ -282,7 +285,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         ent = json.load(open(tpath)).get(f"{wl}:{world}")
-        if ent and signed and args.cta_group == 2:
+        if ent and signed and args.cta_group == 2 and args.operand == "int8":
             traffic = ent["traffic_bytes"]
 
     line = {
@@ -292,7 +295,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"{wl}: all-pairs {'signed ' if signed else ''}MI, {G} genes x {N} cells, "
                                f"n_bins={N_BINS}, nnz={nnz}",
-                   "pairs": pairs, "cta_group": args.cta_group,
+                   "pairs": pairs, "cta_group": args.cta_group, "operand": args.operand,
                    "parallelism": f"tile-sharded x{world}, 1 broadcast" if world > 1 else "single GPU",
                    "l2": "operand larger than L2" if not flush_needed else "L2 flushed between steps"},
         "e2e": {"value": pairs / (ms_e2e / args.steps * 1e-3), "unit": "gene-pairs/s",
@@ -303,7 +306,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s",
                      "frac": (achieved_tops / peak_tops) if achieved_tops else None, "traffic": traffic,
                      "algorithmic_operand_bytes": int(operand_bytes),
-                     "kernel": "gram_tiles_kernel<2, MiEpi<10>> (gv_mi_tiles)",
+                     "kernel": f"gram_tiles_kernel<{args.cta_group}, MiEpi<10{', fp4' if args.operand == 'fp4' else ''}>> (gv_mi_tiles)",
                      "kernel_ms": mi_avg_ms,
                      "peak_note": f"2 x {peaks['src']} cuBLAS bf16 ({'sustained' if long_step else 'burst'}): "
                                   "tcgen05 kind::i8 issues at twice the bf16 rate; nominal dense INT8 is 4500. "

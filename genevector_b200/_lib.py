@@ -19,7 +19,8 @@ GV_PATH_AUTO, GV_PATH_COUNTS, GV_PATH_GENERAL = 0, 1, 2
 GV_MARG_STRIDE = 16
 GV_EDGE_STRIDE = 16
 GV_QTABLE_DIM = 16
-GV_ABI_VERSION = 1
+GV_ABI_VERSION = 2
+GV_OPERAND_INT8, GV_OPERAND_FP4 = 0, 1
 
 
 class GvError(RuntimeError):
@@ -44,12 +45,12 @@ SIGNATURES = {
     "gv_gene_entropy": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "gv_rows_per_gene": (_i32, [_i32]),
     "gv_onehot_rows": (_i64, [_i32, _i32]),
-    "gv_expand_onehot": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "gv_expand_onehot": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp]),
     "gv_tile_m": (_i32, [_i32]),
     "gv_tile_schedule": (_i64, [_i64, _i32, _i32, _vp, _i64]),
     "gv_mi_tiles": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
-                           _i32, _vp, _vp]),
-    "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+                           _i32, _i32, _vp, _vp]),
+    "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -47,9 +47,9 @@ static int check_device() {
 
 // implemented in gv_tiles.cu
 int mi_tiles_dispatch(const void*, int64_t, int64_t, int, const int32_t*, const int8_t*, int64_t, int,
-                      const int32_t*, int64_t, float*, int64_t, int, void*, cudaStream_t);
+                      const int32_t*, int64_t, float*, int64_t, int, int, void*, cudaStream_t);
 int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, int32_t*, int64_t, int,
-                       int, cudaStream_t);
+                       int, int, cudaStream_t);
 int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
                           const int32_t*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
                           int64_t, float*, int64_t, int, void*, cudaStream_t);
@@ -130,14 +130,14 @@ int64_t gv_onehot_rows(int n_genes, int rows_per_gene) {
 }
 
 int gv_expand_onehot(const void* bins_packed, int64_t bins_pitch_bytes, int n_genes,
-                     int rows_per_gene, void* onehot, int64_t kp, void* stream) {
+                     int rows_per_gene, void* onehot, int64_t kp, int operand_format, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!bins_packed || !onehot || n_genes <= 0) return set_error(GV_ERR_ARG, "bad argument");
   const int64_t rows = gv_onehot_rows(n_genes, rows_per_gene);
   if (rows < 0) return int(rows);
   return expand_onehot_dispatch(bins_packed, bins_pitch_bytes, n_genes, rows_per_gene, onehot, kp,
-                                int(rows / 32), static_cast<cudaStream_t>(stream));
+                                int(rows / 32), operand_format, static_cast<cudaStream_t>(stream));
 }
 
 int gv_tile_m(int cta_group) {
@@ -173,7 +173,7 @@ int64_t gv_tile_schedule(int64_t op_rows, int tile_m, int band, int32_t* out_pai
 int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
                 const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
                 const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
-                void* sync_ws, void* stream) {
+                int operand_format, void* sync_ws, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!onehot || !marg || !tiles || !out || n_genes <= 0 || ld_out < n_genes)
@@ -182,17 +182,18 @@ int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_ge
   if (op_rows < gv_onehot_rows(n_genes, rows_per_gene))
     return set_error(GV_ERR_ARG, "gv_mi_tiles: operand has too few rows");
   return mi_tiles_dispatch(onehot, op_rows, kp, rows_per_gene, marg, sgn, ld_sgn, n_genes, tiles,
-                           n_tiles, out, ld_out, cta_group, sync_ws, static_cast<cudaStream_t>(stream));
+                           n_tiles, out, ld_out, cta_group, operand_format, sync_ws,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
                  int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
-                 void* stream) {
+                 int operand_format, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!operand || !tiles || !out || ld_out < op_rows) return set_error(GV_ERR_ARG, "gv_gram_dump: bad argument");
   return gram_dump_dispatch(operand, op_rows, kp, tiles, n_tiles, out, ld_out, cta_group, active_rows,
-                            static_cast<cudaStream_t>(stream));
+                            operand_format, static_cast<cudaStream_t>(stream));
 }
 
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,

@@ -444,6 +444,51 @@ __global__ void k_expand_onehot(const uint32_t* __restrict__ bins_packed, int64_
 }
 
 
+// FP4 variant: the same rows as 4-bit E2M1 one-hot values (0x2 = 1.0), two cells per byte in the
+// packing of bins_packed itself (low nibble = even cell), so an operand row is exactly as long
+// as a packed-bin row.  Every lane turns 16 packed bytes (32 cells) into 16 bytes per bin row.
+template <int B>
+__global__ void k_expand_onehot_fp4(const uint32_t* __restrict__ bins_packed, int64_t pitch_words,
+                                    int G, uint8_t* __restrict__ onehot, int64_t row_bytes,
+                                    int n_blocks) {
+  constexpr int GPB = 32 / B;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int64_t chunks = (row_bytes + 511) / 512;       // 512 bytes = 1024 cells per warp step
+  for (int blk = blockIdx.y; blk < n_blocks; blk += gridDim.y) {
+    for (int64_t ch = int64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); ch < chunks;
+         ch += int64_t(gridDim.x) * warps_per_cta) {
+      const int64_t byte0 = ch * 512 + lane * 16;
+      if (byte0 >= row_bytes) continue;
+      uint8_t* obase = onehot + int64_t(blk) * 32 * row_bytes + byte0;
+#pragma unroll
+      for (int sj = 0; sj < GPB; ++sj) {
+        const int g = blk * GPB + sj;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (g < G && (byte0 >> 2) + 3 < pitch_words)
+          w = *reinterpret_cast<const uint4*>(bins_packed + int64_t(g) * pitch_words + (byte0 >> 2));
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const uint32_t pat = uint32_t(b + 1) * 0x11111111u;
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t x = ws[i] ^ pat;                       // nibble == 0 where bin == b+1
+            x = (x | (x >> 2)) & 0x33333333u;
+            x = (x | (x >> 1)) & 0x11111111u;               // 1 where the nibble was non-zero
+            o[i] = (x ^ 0x11111111u) << 1;                  // 0x2 (E2M1 1.0) where bin == b+1
+          }
+          *reinterpret_cast<uint4*>(obase + int64_t(sj * B + b) * row_bytes) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+#pragma unroll
+      for (int r = GPB * B; r < 32; ++r)
+        *reinterpret_cast<uint4*>(obase + int64_t(r) * row_bytes) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 // ================================================================ count-data fast path
 // For non-negative integer data with values <= 255 (scRNA-seq counts, the documented input) the
 // order statistics follow from a per-gene VALUE histogram, so the gene-major regroup is not
@@ -876,13 +921,31 @@ size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype) {
 }
 
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
-                           void* onehot, int64_t kp, int n_blocks, cudaStream_t st) {
+                           void* onehot, int64_t kp, int n_blocks, int operand_format,
+                           cudaStream_t st) {
+  const uint32_t* bp = static_cast<const uint32_t*>(bins_packed);
+  if (operand_format == GV_OPERAND_FP4) {
+    if (kp % 256 != 0) return set_error(GV_ERR_ARG, "expand (fp4): K extent must be a multiple of 256 cells");
+    if (pitch_bytes % 16 != 0 || pitch_bytes * 2 < kp)
+      return set_error(GV_ERR_ARG, "expand: bins pitch must cover the padded K extent");
+    const int64_t row_bytes = kp / 2;
+    const int64_t chunks = (row_bytes + 511) / 512;
+    dim3 grid((unsigned)((chunks + 7) / 8), (unsigned)(n_blocks < 65535 ? n_blocks : 65535));
+    uint8_t* oh = static_cast<uint8_t*>(onehot);
+    switch (rows_per_gene) {
+      case 5:  k_expand_onehot_fp4<5><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, row_bytes, n_blocks); break;
+      case 10: k_expand_onehot_fp4<10><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, row_bytes, n_blocks); break;
+      default: return set_error(GV_ERR_ARG, "expand (fp4): rows_per_gene must be 5 or 10");
+    }
+    GV_LAUNCH_CHECK();
+    return GV_OK;
+  }
+  if (operand_format != GV_OPERAND_INT8) return set_error(GV_ERR_ARG, "unknown operand format");
   if (kp % 128 != 0) return set_error(GV_ERR_ARG, "expand: K extent must be a multiple of 128");
   if (pitch_bytes % 16 != 0 || pitch_bytes * 2 < kp)
     return set_error(GV_ERR_ARG, "expand: bins pitch must cover the padded K extent");
   const int64_t chunks = (kp + 1023) / 1024;
   dim3 grid((unsigned)((chunks + 7) / 8), (unsigned)(n_blocks < 65535 ? n_blocks : 65535));
-  const uint32_t* bp = static_cast<const uint32_t*>(bins_packed);
   int8_t* oh = static_cast<int8_t*>(onehot);
   switch (rows_per_gene) {
     case 5:  k_expand_onehot<5><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;

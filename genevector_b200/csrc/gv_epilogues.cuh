@@ -27,11 +27,21 @@ struct DumpParams {
 };
 // ACT = data rows per 32-row block on the B side (see GramCfg): accumulator column
 // cb*ACT + c holds operand row col0 + cb*32 + c.
-template <int ACT>
+// FP32 accumulators of the FP4 operand path hold exact integers: back to INT32.
+template <bool FP4>
+__device__ __forceinline__ void acc_to_int(uint32_t (&v)[32]) {
+  if constexpr (FP4) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = uint32_t(__float2int_rn(__uint_as_float(v[c])));
+  }
+}
+
+template <int ACT, bool FP4 = false>
 struct DumpEpi {
   using Params = DumpParams;
   static constexpr size_t SMEM_BYTES = 16;
   static constexpr int ACTIVE_ROWS = ACT;
+  static constexpr bool OPERAND_FP4 = FP4;
   const Params& p;
   __device__ DumpEpi(const Params& p_, uint8_t*) : p(p_) {}
   __device__ void prepare(const EpiTile&) {}
@@ -43,6 +53,7 @@ struct DumpEpi {
       uint32_t v[32];
       tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * ACT), v);
       tmem_ld_wait();
+      acc_to_int<FP4>(v);
       if (row < p.rows) {
 #pragma unroll
         for (int c = 0; c < ACT; ++c) {
@@ -77,9 +88,10 @@ __device__ __forceinline__ T seg_reduce(T x, int pos) {
   return x;
 }
 
-template <int B>
+template <int B, bool FP4 = false>
 struct MiEpi {
   using Params = MiParams;
+  static constexpr bool OPERAND_FP4 = FP4;
   static constexpr int GPB = 32 / B;          // genes per 32-row block of the operand
   static constexpr int ACTIVE = GPB * B;      // rows of a block that carry data
   // B side staged densely when a block has exactly 30 data rows (B = 10, 5): N = 240
@@ -145,6 +157,7 @@ struct MiEpi {
       uint32_t v[32];
       tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * ACTIVE_ROWS), v);
       tmem_ld_wait();
+      acc_to_int<FP4>(v);
       // stage this warp's 32x32 count block for the column sums (bank = lane + c: no conflicts)
 #pragma unroll
       for (int c = 0; c < ACTIVE; ++c) scr[lane * 33 + c] = int(v[c]);
@@ -247,6 +260,7 @@ struct MomentEpi {
   };
   static constexpr size_t SMEM_BYTES = sizeof(Meta) + 16;
   static constexpr int ACTIVE_ROWS = 32;
+  static constexpr bool OPERAND_FP4 = false;
   const Params& p;
   Meta* meta;
   __device__ MomentEpi(const Params& p_, uint8_t* smem) : p(p_) {

@@ -35,9 +35,17 @@ constexpr int GRAM_SMEM_MAX = 227 * 1024;   // dynamic shared memory a CTA may o
 // ACTIVE rows per block), so the MMA runs with N = 8*ACTIVE columns instead of 256 and no
 // accumulator column is spent on padding rows.  The A side keeps whole 32-row blocks: a gene's
 // bins must stay inside one 32-lane TMEM quarter for the epilogue.
-template <int CG, int EPI_SMEM_BYTES, int ACTIVE = 32>
+//
+// FP4 = true: the operand holds 4-bit E2M1 one-hot values (two cells per byte) and the MMA is
+// kind::mxf4.block_scale with unit UE8M0 scales: a 128-byte K slice then covers 256 cells and every
+// MMA 64 of them, at the same bytes per instruction as INT8, i.e. twice the cells per second.
+// The scale factors live in the 16 + 16 TMEM columns the N = 240 layout leaves free
+// (columns 240..255 and 496..511), so FP4 needs ACTIVE == 30.
+template <int CG, int EPI_SMEM_BYTES, int ACTIVE = 32, bool FP4 = false>
 struct GramCfg {
   static_assert(ACTIVE == 32 || ACTIVE == 30, "unsupported block occupancy");
+  static_assert(!FP4 || ACTIVE == 30, "the FP4 operand needs the 240-column accumulator layout");
+  static constexpr uint32_t SFA_COL = 240, SFB_COL = 496;
   static constexpr int TILE_M = 128 * CG;                 // operand rows on the A side per tile
   static constexpr int N_COLS = 8 * ACTIVE;               // accumulator columns = MMA N
   static constexpr int A_ROWS = 128;                      // rows of A each CTA stages
@@ -54,7 +62,7 @@ struct GramCfg {
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage operand pipeline");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier block too small");
-  static constexpr uint32_t IDESC = idesc_i8(TILE_M, N_COLS, true, true);
+  static constexpr uint32_t IDESC = FP4 ? idesc_mxf4(TILE_M, N_COLS) : idesc_i8(TILE_M, N_COLS, true, true);
 };
 
 // What the epilogue functor gets for one tile.
@@ -81,7 +89,7 @@ struct GramArgs {
 
 template <int CG, class Epi>
 constexpr size_t gram_smem_bytes() {
-  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS>;
+  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS, Epi::OPERAND_FP4>;
   return 1024 + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Epi::SMEM_BYTES;
 }
 
@@ -90,7 +98,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
                   const GramArgs ga, const typename Epi::Params ep) {
   // tmap: 128-row boxes (A side, and B side when ACTIVE == 32); tmap_b: ACTIVE-row boxes
-  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS>;
+  using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS, Epi::OPERAND_FP4>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -129,6 +137,17 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if constexpr (Epi::OPERAND_FP4) {
+    // unit scale factors (UE8M0 0x7F = 2^0) for every row of A and B, in every lane quarter
+    if (warp >= 4 && warp < 8) {
+      const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+      tmem_fill_32x16(tmem_base + lane_base + Cfg::SFA_COL, 0x7F7F7F7Fu);
+      tmem_fill_32x16(tmem_base + lane_base + Cfg::SFB_COL, 0x7F7F7F7Fu);
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -207,8 +226,12 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           for (int k = 0; k < GRAM_BK / 32; ++k) {
             // advance 32 bytes (one K=32 step) inside the 128-byte swizzle row: +2 in the
             // 16-byte-granular start-address field
-            mma_i8<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
-                       (kb | k) != 0 ? 1u : 0u);
+            if constexpr (Epi::OPERAND_FP4)
+              mma_mxf4<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
+                           tmem_base + Cfg::SFA_COL, tmem_base + Cfg::SFB_COL, (kb | k) != 0 ? 1u : 0u);
+            else
+              mma_i8<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
+                         (kb | k) != 0 ? 1u : 0u);
           }
           mma_commit<CG>(empty_bar(s));                       // frees the smem slot (both CTAs)
           if (kb == ga.k_blocks - 1) mma_commit<CG>(tfull_bar(acc));  // accumulator ready

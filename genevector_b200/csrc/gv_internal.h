@@ -35,6 +35,7 @@ int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* co
                           int64_t n_cells, int G, double* ent, void* workspace, size_t ws_bytes,
                           cudaStream_t st);
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
-                           void* onehot, int64_t kp, int n_blocks, cudaStream_t st);
+                           void* onehot, int64_t kp, int n_blocks, int operand_format,
+                           cudaStream_t st);
 
 }  // namespace gv

@@ -148,6 +148,36 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T with 4-bit E2M1 operands (two per byte, K = 64 per instruction),
+// block-scaled by UE8M0 factors held in TMEM (one per 32 elements), FP32 accumulators.  Used with
+// unit scales and one-hot {0, 1.0} operands: the products are exact and so are the sums up to 2^24.
+template <int CG>
+__device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t sfa_tmem, uint32_t sfb_tmem,
+                                         uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(sfa_tmem), "r"(sfb_tmem), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(sfa_tmem), "r"(sfb_tmem), "r"(accumulate)
+        : "memory");
+}
+
+// Fill 16 consecutive TMEM columns of this warp's 32 lanes with one 32-bit value.
+__device__ __forceinline__ void tmem_fill_32x16(uint32_t taddr, uint32_t x) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(x)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread completed.
 // CG==2: the arrive is multicast to the same barrier offset in both CTAs of the pair.
 template <int CG>
@@ -202,6 +232,16 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N, bool a_signed, boo
          | ((a_signed ? 1u : 0u) << 7)        // a_format: 0 = u8, 1 = s8
          | ((b_signed ? 1u : 0u) << 10)       // b_format
          | (static_cast<uint32_t>(N >> 3) << 17)
+         | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::mxf4.block_scale: E2M1 operands, UE8M0 scales, both K-major,
+// FP32 accumulate.  Field layout: cute/arch/mma_sm100_desc.hpp (InstrDescriptorBlockScaled).
+__host__ __device__ constexpr uint32_t idesc_mxf4(int M, int N) {
+  return (1u << 7)                             // a_format: E2M1
+         | (1u << 10)                          // b_format: E2M1
+         | (static_cast<uint32_t>(N >> 3) << 17)
+         | (1u << 23)                          // scale format: UE8M0
          | (static_cast<uint32_t>(M >> 4) << 24);
 }
 

@@ -101,9 +101,17 @@ static int launch_cg(int cta_group, const void* operand, int64_t op_rows, int64_
 int mi_tiles_dispatch(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
                       const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
                       const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out,
-                      int cta_group, void* sync_ws, cudaStream_t st) {
+                      int cta_group, int operand_format, void* sync_ws, cudaStream_t st) {
   MiParams p;
   p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out; p.ld_out = ld_out; p.G = n_genes;
+  if (operand_format == GV_OPERAND_FP4) {
+    switch (rows_per_gene) {
+      case 5:  return launch_cg<MiEpi<5, true>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+      case 10: return launch_cg<MiEpi<10, true>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    }
+    return set_error(GV_ERR_ARG, "the FP4 operand needs rows_per_gene 5 or 10 (n_bins <= 5 or 9..10)");
+  }
+  if (operand_format != GV_OPERAND_INT8) return set_error(GV_ERR_ARG, "unknown operand format");
   switch (rows_per_gene) {
     case 5:  return launch_cg<MiEpi<5>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case 8:  return launch_cg<MiEpi<8>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
@@ -115,9 +123,13 @@ int mi_tiles_dispatch(const void* onehot, int64_t op_rows, int64_t kp, int rows_
 
 int gram_dump_dispatch(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
                        int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
-                       cudaStream_t st) {
+                       int operand_format, cudaStream_t st) {
   DumpParams p;
   p.out = out; p.ld = ld_out; p.rows = int(op_rows);
+  if (operand_format == GV_OPERAND_FP4) {
+    if (active_rows != 30) return set_error(GV_ERR_ARG, "gram dump (fp4): active_rows must be 30");
+    return launch_cg<DumpEpi<30, true>>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, nullptr, st);
+  }
   if (active_rows == 32)
     return launch_cg<DumpEpi<32>>(cta_group, operand, op_rows, kp, tiles, n_tiles, p, nullptr, st);
   if (active_rows == 30)

@@ -99,7 +99,7 @@ HEADER_BYTES = 256   # int64[0] = n_limbs, [1] = limb_bits, [2] = data flag bits
 def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1):
     """Byte offsets of the sections of the broadcast block.  The value rows come last, so a
     two-digit block is the one-digit block plus a tail."""
-    kp = _align(max(n_cells, 1), 128)
+    kp = _align(max(n_cells, 1), 256)      # a 128-byte K slice of the FP4 operand is 256 cells
     pitch = kp // 2
     off, lay = 0, {}
     for name, nbytes in (("header", HEADER_BYTES), ("bins", n_genes * pitch),
@@ -166,6 +166,9 @@ class Engine:
         self.cta_group = cta_group
         self.band = band
         self._sched_cache = {}
+        # storage of the MI operand: "int8" (tcgen05 kind::i8, the default) or "fp4" (kind::mxf4 with
+        # unit scales: half the bytes, twice the cells per MMA, same exact counts)
+        self.operand = "int8"
         # wave lockstep of the persistent tile kernels: "auto" = when the operand exceeds L2
         self.lockstep = "auto"
         self._sync_ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
@@ -284,19 +287,31 @@ class Engine:
             b[o:o + 32].view(torch.int64).copy_(hdr)
             return blk
 
-    def expand_onehot(self, blk: BinBlock) -> tuple:
-        """gv_expand_onehot: packed bins -> INT8 one-hot operand [rows][kp]."""
+    def _fmt(self, operand: Optional[str]) -> int:
+        op = operand or self.operand
+        if op == "int8":
+            return _lib.GV_OPERAND_INT8
+        if op == "fp4":
+            return _lib.GV_OPERAND_FP4
+        raise GvError("operand", -1, f"unknown operand format {op!r} (int8 or fp4)")
+
+    def expand_onehot(self, blk: BinBlock, operand: Optional[str] = None) -> tuple:
+        """gv_expand_onehot: packed bins -> one-hot operand [rows][row_bytes] (int8: one byte per
+        cell; fp4: two cells per byte).  Returns (operand tensor, rows per gene)."""
         with torch.cuda.device(self.device):
+            fmt = self._fmt(operand)
             B = _lib.call("gv_rows_per_gene", blk.n_bins)
             rows = _lib.check("gv_onehot_rows", self.lib.gv_onehot_rows(blk.n_genes, B))
-            onehot = torch.empty((rows, blk.kp), dtype=torch.int8, device=self.device)
+            row_bytes = blk.kp if fmt == _lib.GV_OPERAND_INT8 else blk.kp // 2
+            onehot = torch.empty((rows, row_bytes), dtype=torch.int8 if fmt == 0 else torch.uint8,
+                                 device=self.device)
             self._call("gv_expand_onehot", blk.bins.data_ptr(), blk.bins_pitch, blk.n_genes, B,
-                      onehot.data_ptr(), blk.kp, self._stream())
+                       onehot.data_ptr(), blk.kp, fmt, self._stream())
             return onehot, B
 
     # ------------------------------------------------------------------ tile kernels
     def gram_dump(self, operand: torch.Tensor, cta_group: Optional[int] = None,
-                  active_rows: int = 32) -> torch.Tensor:
+                  active_rows: int = 32, fmt: int = 0) -> torch.Tensor:
         """Test-only: raw INT32 accumulators of every scheduled tile."""
         with torch.cuda.device(self.device):
             cg = cta_group or self.cta_group
@@ -304,7 +319,7 @@ class Engine:
             tiles, n, _ = self.schedule(rows, cg)
             out = torch.zeros((rows, rows), dtype=torch.int32, device=self.device)
             self._call("gv_gram_dump", operand.data_ptr(), rows, kp, tiles.data_ptr(), n,
-                      out.data_ptr(), rows, cg, active_rows, self._stream())
+                      out.data_ptr(), rows, cg, active_rows, fmt, self._stream())
             return out
 
     def sign_tiles_for(self, mi_tiles: np.ndarray, B: int, n_limbs: int = 1) -> torch.Tensor:
@@ -372,13 +387,14 @@ class Engine:
             G = blk.n_genes
             if out is None:
                 out = torch.zeros((G, G), dtype=torch.float32, device=self.device)
-            rows = onehot.shape[0]
+            rows, row_bytes = onehot.shape
+            fmt = _lib.GV_OPERAND_FP4 if onehot.dtype == torch.uint8 else _lib.GV_OPERAND_INT8
             tiles, n, _ = self.schedule(rows, rank=rank, world=world)
-            self._call("gv_mi_tiles", onehot.data_ptr(), rows, blk.kp, B, blk.marg.data_ptr(),
+            self._call("gv_mi_tiles", onehot.data_ptr(), rows, row_bytes, B, blk.marg.data_ptr(),
                       sgn.data_ptr() if sgn is not None else None,
                       sgn.stride(0) if sgn is not None else 0, G, tiles.data_ptr(), n,
-                      out.data_ptr(), out.stride(0), self.cta_group,
-                      self._sync_ptr(rows * blk.kp), self._stream())
+                      out.data_ptr(), out.stride(0), self.cta_group, fmt,
+                      self._sync_ptr(rows * row_bytes), self._stream())
             return out
 
     # ------------------------------------------------------------------ whole paths

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GV_ABI_VERSION 1
+#define GV_ABI_VERSION 2
 #define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
 #define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
 #define GV_QTABLE_DIM 16  /* q_table_host is [16][16] float64 */
@@ -49,6 +49,13 @@ typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
  *   GV_PATH_GENERAL gene-major regroup + multi-target radix select; any float32/float64 data
  *   GV_PATH_AUTO    try COUNTS, fall back to GENERAL when the data do not qualify */
 typedef enum gv_disc_path { GV_PATH_AUTO = 0, GV_PATH_COUNTS = 1, GV_PATH_GENERAL = 2 } gv_disc_path;
+
+/* Storage of the one-hot operand of the MI contraction (both give bit-exact joint counts):
+ *   GV_OPERAND_INT8  one byte per (row, cell); tcgen05 kind::i8, INT32 accumulators (the default)
+ *   GV_OPERAND_FP4   4-bit E2M1 (two cells per byte); tcgen05 kind::mxf4.block_scale with unit scales,
+ *                    FP32 accumulators (exact below 2^24 cells), half the operand bytes and twice the
+ *                    cells per MMA; needs 10 or 5 rows per gene */
+typedef enum gv_operand_format { GV_OPERAND_INT8 = 0, GV_OPERAND_FP4 = 1 } gv_operand_format;
 
 /* Score kinds of gv_moment_tiles. */
 typedef enum gv_moment_kind {
@@ -110,9 +117,11 @@ int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
 int gv_rows_per_gene(int n_bins);
 /* number of 32-row blocks / operand rows for n_genes */
 int64_t gv_onehot_rows(int n_genes, int rows_per_gene);
-/* packed 4-bit bins -> INT8 one-hot operand [gv_onehot_rows][kp], kp % 128 == 0 */
+/* packed 4-bit bins -> one-hot operand rows.  kp = K extent in cells.
+ *   GV_OPERAND_INT8: int8 [gv_onehot_rows][kp], kp % 128 == 0
+ *   GV_OPERAND_FP4 : uint8 [gv_onehot_rows][kp / 2], kp % 256 == 0 */
 int gv_expand_onehot(const void* bins_packed, int64_t bins_pitch_bytes, int n_genes,
-                     int rows_per_gene, void* onehot, int64_t kp, void* stream);
+                     int rows_per_gene, void* onehot, int64_t kp, int operand_format, void* stream);
 
 /* ---------------------------------------------------------------- tile schedule (host)
  * Upper-triangular tile list over an operand of `op_rows` rows: tiles are tile_m x 256 operand
@@ -132,22 +141,23 @@ int gv_tile_m(int cta_group);
  * skipped pairs (a gene without positive values: metrics.py:119-120; lib.rs:33).
  *   sgn: optional int8 [n_genes][ld_sgn] from gv_moment_tiles(GV_MOM_SIGN); score = sign * MI
  *        (metrics.py:132-135).
+ *   row_bytes: bytes per operand row (= padded cells for INT8, half of them for FP4), % 128 == 0.
  *   sync_ws: optional >= 64 bytes of device scratch.  When given, the persistent CTA pairs run the
  *        tile schedule in lockstep waves (one arrive per pair per wave) so that the tiles in flight
  *        share operand panels out of L2; pass it when the operand is larger than L2, NULL otherwise.
  *        The same buffer must not be used by two launches that can overlap. */
-int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t kp, int rows_per_gene,
+int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t row_bytes, int rows_per_gene,
                 const int32_t* marg, const int8_t* sgn, int64_t ld_sgn, int n_genes,
                 const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
-                void* sync_ws, void* stream);
+                int operand_format, void* sync_ws, void* stream);
 
 /* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles.
  * active_rows = 32: every operand row is a column of the tile (N = 256); 30: the B side stages only
  * the first 30 rows of every 32-row block (N = 240, what gv_mi_tiles does for 10 or 5 rows per
  * gene) and columns of the other two rows are left untouched. */
-int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
+int gv_gram_dump(const void* operand, int64_t op_rows, int64_t row_bytes, const int32_t* tiles,
                  int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
-                 void* stream);
+                 int operand_format, void* stream);
 
 /* ---------------------------------------------------------------- co-moment targets
  * val_rows from gv_discretize_csr: n_limbs INT8 rows per gene (row = gene*n_limbs + digit, base

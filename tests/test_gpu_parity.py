@@ -383,3 +383,49 @@ def test_gene_entropy_matches_reference(engine):
     zl = load_golden("lognorm_f32_300x40_b7")
     with pytest.raises(GvError, match="integer counts"):
         get_gene_entropy(zl["X"], [f"G{i}" for i in range(40)])
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "ref_poisson_500x20_b5", "synth_counts_700x96_b10"])
+def test_fp4_operand_counts_and_scores_identical_to_int8(engine, case, cg):
+    """The FP4 (E2M1, unit-scale mxf4) operand gives the same joint counts bit for bit, hence the
+    same scores, as the INT8 operand."""
+    from genevector_b200 import _lib
+    z = load_golden(case)
+    csr = engine.upload_csr(z["X"])
+    blk = engine.discretize(csr, z["n_bins"])
+    oh8, B = engine.expand_onehot(blk, "int8")
+    oh4, _ = engine.expand_onehot(blk, "fp4")
+    assert oh4.shape == (oh8.shape[0], oh8.shape[1] // 2)
+    # operand bytes: nibble c&1 of byte c>>1 is 0x2 exactly where the INT8 operand is 1
+    a8 = oh8.cpu().numpy()
+    a4 = oh4.cpu().numpy()
+    assert np.array_equal(a4 & 0x0F, a8[:, 0::2] * 2) and np.array_equal(a4 >> 4, a8[:, 1::2] * 2)
+    c8 = engine.gram_dump(oh8, cta_group=cg, active_rows=30).cpu().numpy()
+    c4 = engine.gram_dump(oh4, cta_group=cg, active_rows=30, fmt=_lib.GV_OPERAND_FP4).cpu().numpy()
+    assert np.array_equal(c4, c8)
+    old = engine.cta_group
+    engine.cta_group = cg
+    try:
+        m8 = engine.mi_scores(blk, oh8, B).cpu().numpy()
+        m4 = engine.mi_scores(blk, oh4, B).cpu().numpy()
+    finally:
+        engine.cta_group = old
+    assert np.array_equal(m4, m8)
+    assert np.abs(m4.astype(np.float64) - z["mi_raw"]).max() <= MI_TOL
+
+
+def test_fp4_operand_seeded_vs_oracle(engine):
+    from oracle import oracle as orc
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(3000, 333, seed=2)
+    bins_gm, nb, _ = orc.discretize_csr_c(X, 10)
+    want, _ = orc.mi_pairs_gm_c(bins_gm, nb, sign=orc.sign_int_c(X))
+    csr = engine.upload_csr(X)
+    old = engine.operand
+    engine.operand = "fp4"
+    try:
+        out = engine.mi_from_csr(csr, 3000, 333, signed=True).cpu().numpy()
+    finally:
+        engine.operand = old
+    assert np.abs(out.astype(np.float64) - want).max() <= MI_TOL

@@ -39,7 +39,7 @@ def probe(cg, rows, kp, density=0.3, seed=0, vmax=1):
     torch.cuda.synchronize()
     t0 = time.time()
     st = lib.gv_gram_dump(a_d.data_ptr(), rows, kp, tiles_d.data_ptr(), len(tiles), out.data_ptr(),
-                          rows, cg, 32, torch.cuda.current_stream().cuda_stream)
+                          rows, cg, 32, 0, torch.cuda.current_stream().cuda_stream)
     if st != 0:
         print(f"[cg={cg}] launch status {st}: {lib.gv_last_error().decode()}")
         return False
