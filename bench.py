@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--unsigned", action="store_true", help="plain MI (no Pearson sign pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=2)
-    ap.add_argument("--operand", default="int8", choices=["int8", "fp4"],
+    ap.add_argument("--operand", default="fp4", choices=["int8", "fp4"],
                     help="storage of the one-hot operand (fp4: tcgen05 kind::mxf4, exact counts)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -274,18 +274,22 @@ def main():
 
     # ---- roofline of the dominant kernel (contraction + fused MI epilogue), this rank's share
     peaks = load_peaks()
+    fp4 = args.operand == "fp4"
     my_pairs_frac = n_my_tiles / max(n_all_tiles, 1)
     alg_ops = pairs * my_pairs_frac * 2.0 * N_BINS * N_BINS * N        # 2*B^2*N per pair
     mi_avg_ms = float(np.mean(mi_ms)) if mi_ms else float("nan")
     achieved_tops = alg_ops / (mi_avg_ms * 1e-3) / 1e12 if mi_ms else None
     long_step = (ms_dev / args.steps) > 500.0
-    peak_tops = 2.0 * (peaks["bf16_sustained"] if long_step else peaks["bf16_burst"])
+    # tcgen05 issue rates relative to bf16: kind::i8 2x, kind::mxf4 4x
+    rate = 4.0 if fp4 else 2.0
+    nominal = 9000.0 if fp4 else 4500.0
+    peak_tops = rate * (peaks["bf16_sustained"] if long_step else peaks["bf16_burst"])
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        ent = json.load(open(tpath)).get(f"{wl}:{world}")
-        if ent and signed and args.cta_group == 2 and args.operand == "int8":
+        ent = json.load(open(tpath)).get(f"{wl}:{world}:{args.operand}")
+        if ent and signed and args.cta_group == 2:
             traffic = ent["traffic_bytes"]
 
     line = {
@@ -308,11 +312,12 @@ def main():
                      "algorithmic_operand_bytes": int(operand_bytes),
                      "kernel": f"gram_tiles_kernel<{args.cta_group}, MiEpi<10{', fp4' if args.operand == 'fp4' else ''}>> (gv_mi_tiles)",
                      "kernel_ms": mi_avg_ms,
-                     "peak_note": f"2 x {peaks['src']} cuBLAS bf16 ({'sustained' if long_step else 'burst'}): "
-                                  "tcgen05 kind::i8 issues at twice the bf16 rate; nominal dense INT8 is 4500. "
-                                  "frac > 1 is expected: one-hot operands draw less power than the dense "
-                                  "random data of the cuBLAS measurement, so this kernel holds ~1.9 GHz where "
-                                  "that one was power-capped",
+                     "peak_note": f"{rate:.0f} x {peaks['src']} cuBLAS bf16 ({'sustained' if long_step else 'burst'}): "
+                                  f"tcgen05 {'kind::mxf4' if fp4 else 'kind::i8'} issues at {rate:.0f}x the bf16 rate "
+                                  f"(nominal dense {'FP4 9000' if fp4 else 'INT8 4500'} TOP/s). frac > 1 is expected: "
+                                  "one-hot operands draw less power than the dense random data of the cuBLAS "
+                                  "measurement, so this kernel holds ~1.9 GHz where that one was power-capped",
+                     "frac_of_nominal": (achieved_tops / nominal) if achieved_tops else None,
                      "frac_of_nominal_int8": (achieved_tops / 4500.0) if achieved_tops else None},
         "phases_ms": {k: float(np.mean(v)) for k, v in phase_ms.items()},
         "clocks": clocks,

@@ -166,9 +166,10 @@ class Engine:
         self.cta_group = cta_group
         self.band = band
         self._sched_cache = {}
-        # storage of the MI operand: "int8" (tcgen05 kind::i8, the default) or "fp4" (kind::mxf4 with
-        # unit scales: half the bytes, twice the cells per MMA, same exact counts)
-        self.operand = "int8"
+        # storage of the MI operand: "int8" (tcgen05 kind::i8, INT32 accumulators), "fp4" (kind::mxf4
+        # with unit scales, FP32 accumulators: half the bytes, twice the cells per MMA, the same exact
+        # counts below 2^24 cells) or "auto" (fp4 where it applies: 10 or 5 rows per gene)
+        self.operand = "auto"
         # wave lockstep of the persistent tile kernels: "auto" = when the operand exceeds L2
         self.lockstep = "auto"
         self._sync_ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
@@ -287,8 +288,12 @@ class Engine:
             b[o:o + 32].view(torch.int64).copy_(hdr)
             return blk
 
-    def _fmt(self, operand: Optional[str]) -> int:
+    def _fmt(self, operand: Optional[str], blk: Optional[BinBlock] = None) -> int:
         op = operand or self.operand
+        if op == "auto":
+            ok = blk is not None and _lib.call("gv_rows_per_gene", blk.n_bins) in (5, 10) \
+                and blk.n_cells < (1 << 24)
+            op = "fp4" if ok else "int8"
         if op == "int8":
             return _lib.GV_OPERAND_INT8
         if op == "fp4":
@@ -299,7 +304,9 @@ class Engine:
         """gv_expand_onehot: packed bins -> one-hot operand [rows][row_bytes] (int8: one byte per
         cell; fp4: two cells per byte).  Returns (operand tensor, rows per gene)."""
         with torch.cuda.device(self.device):
-            fmt = self._fmt(operand)
+            fmt = self._fmt(operand, blk)
+            if fmt == _lib.GV_OPERAND_FP4 and blk.n_cells >= (1 << 24):
+                raise GvError("expand_onehot", -4, "fp4 operand: counts are exact only below 2^24 cells")
             B = _lib.call("gv_rows_per_gene", blk.n_bins)
             rows = _lib.check("gv_onehot_rows", self.lib.gv_onehot_rows(blk.n_genes, B))
             row_bytes = blk.kp if fmt == _lib.GV_OPERAND_INT8 else blk.kp // 2

@@ -71,7 +71,7 @@ def test_joint_counts_bit_exact(engine, case, cg):
     z = load_golden(case)
     csr = engine.upload_csr(z["X"])
     blk = engine.discretize(csr, z["n_bins"])
-    onehot, B = engine.expand_onehot(blk)
+    onehot, B = engine.expand_onehot(blk, "int8")
     C = engine.gram_dump(onehot, cta_group=cg).cpu().numpy()
     if (32 // B) * B == 30:
         # the production MI kernel stages only the 30 data rows of each block on the B side

@@ -12,5 +12,5 @@ for path in sys.argv[1:]:
     print(f"{path}: n_gpus={d.get('n_gpus')} ms/step={d['ms_per_step']:.2f} value={d['value']:.4g} "
           f"e2e_ms={d['e2e'].get('ms_per_step', float('nan')):.2f} e2e={d['e2e']['value']:.4g} "
           f"kernel_ms={r.get('kernel_ms')} TOPS={r.get('achieved')} frac={r.get('frac')} "
-          f"nominal_frac={r.get('frac_of_nominal_int8')}")
+          f"nominal_frac={r.get('frac_of_nominal')} of_int8_nominal={r.get('frac_of_nominal_int8')} operand={d['config'].get('operand')}")
     print("   clocks:", d.get("clocks"), "phases:", d.get("phases_ms"), "cpu:", d.get("cpu_baseline"))
