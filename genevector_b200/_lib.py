@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgvb200.so")
+# GVB200_LIB selects another build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("GVB200_LIB") or os.path.join(_HERE, "libgvb200.so")
 
 GV_OK = 0
 GV_F32, GV_F64 = 0, 1

@@ -102,7 +102,9 @@ struct MiEpi {
     float cinv[GRAM_TILE_N];    // 1 / cm (0 where cm == 0)
     int cg_nnz[CG_PER_TILE];    // #cells with x>0 per column gene (0 => skip pair)
   };
-  static constexpr size_t SCR_INTS = 32 * 33;
+  // warp-private transpose scratch: 32 rows x ACTIVE columns, odd row stride (no bank conflicts)
+  static constexpr int SCR_STRIDE = (ACTIVE % 2 == 0) ? ACTIVE + 1 : ACTIVE;
+  static constexpr size_t SCR_INTS = 32 * SCR_STRIDE;
   static constexpr size_t SMEM_BYTES = sizeof(Meta) + GRAM_EPI_WARPS * SCR_INTS * 4 + 16;
 
   const Params& p;
@@ -160,7 +162,7 @@ struct MiEpi {
       acc_to_int<FP4>(v);
       // stage this warp's 32x32 count block for the column sums (bank = lane + c: no conflicts)
 #pragma unroll
-      for (int c = 0; c < ACTIVE; ++c) scr[lane * 33 + c] = int(v[c]);
+      for (int c = 0; c < ACTIVE; ++c) scr[lane * SCR_STRIDE + c] = int(v[c]);
       __syncwarp();
 
 #pragma unroll
@@ -178,7 +180,7 @@ struct MiEpi {
         int csum = 0;
         if (active) {
 #pragma unroll
-          for (int a2 = 0; a2 < B; ++a2) csum += scr[(seg0 + a2) * 33 + sj * B + pos];
+          for (int a2 = 0; a2 < B; ++a2) csum += scr[(seg0 + a2) * SCR_STRIDE + sj * B + pos];
         }
         // S = #cells where both genes are non-zero; T = #cells where either is (metrics.py:124)
         int S = seg_reduce<B>(r, pos);

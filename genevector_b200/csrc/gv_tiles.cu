@@ -45,6 +45,24 @@ static int make_operand_map(CUtensorMap* map, const void* operand, int64_t op_ro
   return GV_OK;
 }
 
+// 3-D map over the same operand seen as [op_rows/32 blocks][32 rows][kp bytes]; one box fetches
+// the first `active` rows of `blocks` consecutive 32-row blocks (they land contiguously in smem).
+static int make_block_map(CUtensorMap* map, const void* operand, int64_t op_rows, int64_t kp,
+                          int active, int blocks) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(GV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (op_rows % 32 != 0) return set_error(GV_ERR_ARG, "operand rows must be a multiple of 32");
+  cuuint64_t dims[3] = {cuuint64_t(kp), 32, cuuint64_t(op_rows / 32)};
+  cuuint64_t strides[2] = {cuuint64_t(kp), cuuint64_t(kp) * 32};
+  cuuint32_t box[3] = {128, cuuint32_t(active), cuuint32_t(blocks)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(operand), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(GV_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed");
+  return GV_OK;
+}
+
 template <int CG, class Epi>
 static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
                        int64_t n_tiles, const typename Epi::Params& ep, void* sync_ws,
@@ -53,7 +71,8 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
   CUtensorMap map, map_b;
   int rc = make_operand_map(&map, operand, op_rows, kp);
   if (rc != GV_OK) return rc;
-  rc = make_operand_map(&map_b, operand, op_rows, kp, Epi::ACTIVE_ROWS == 32 ? 128 : Epi::ACTIVE_ROWS);
+  if (Epi::ACTIVE_ROWS == 32) rc = make_operand_map(&map_b, operand, op_rows, kp, 128);
+  else rc = make_block_map(&map_b, operand, op_rows, kp, Epi::ACTIVE_ROWS, 8 / CG);
   if (rc != GV_OK) return rc;
   GramArgs ga;
   ga.tiles = reinterpret_cast<const int2*>(tiles);
