@@ -17,10 +17,11 @@ GV_OK = 0
 GV_F32, GV_F64 = 0, 1
 GV_MOM_SIGN, GV_MOM_PEARSON, GV_MOM_COSINE, GV_MOM_JACCARD = 0, 1, 2, 3
 GV_PATH_AUTO, GV_PATH_COUNTS, GV_PATH_GENERAL = 0, 1, 2
+GV_VAL_COUNTS, GV_VAL_DETECTED, GV_VAL_FIXED_POINT, GV_VAL_RANKS = 0, 1, 2, 3
 GV_MARG_STRIDE = 16
 GV_EDGE_STRIDE = 16
 GV_QTABLE_DIM = 16
-GV_ABI_VERSION = 2
+GV_ABI_VERSION = 3
 GV_OPERAND_INT8, GV_OPERAND_FP4 = 0, 1
 
 
@@ -39,13 +40,14 @@ SIGNATURES = {
     "gv_abi_version": (_i32, []),
     "gv_last_error": (C.c_char_p, []),
     "gv_device_check": (_i32, []),
-    "gv_discretize_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "gv_discretize_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _i32, _vp, _vp]),
-    "gv_gene_entropy": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "gv_gene_entropy": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "gv_rows_per_gene": (_i32, [_i32]),
     "gv_onehot_rows": (_i64, [_i32, _i32]),
+    "gv_value_rows": (_i64, [_i32, _i32]),
     "gv_expand_onehot": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp]),
     "gv_tile_m": (_i32, [_i32]),
     "gv_tile_schedule": (_i64, [_i64, _i32, _i32, _vp, _i64]),

@@ -67,8 +67,8 @@ int gv_abi_version(void) { return GV_ABI_VERSION; }
 const char* gv_last_error(void) { return g_last_error.c_str(); }
 int gv_device_check(void) { return check_device(); }
 
-size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype) {
-  return discretize_workspace_bytes(nnz < 0 ? 0 : nnz, n_genes < 0 ? 0 : n_genes, value_dtype);
+size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype, int sorted) {
+  return discretize_workspace_bytes(nnz < 0 ? 0 : nnz, n_genes < 0 ? 0 : n_genes, value_dtype, sorted);
 }
 
 int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
@@ -89,6 +89,11 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
   if (nnz > 0 && (!values || !col_idx)) return set_error(GV_ERR_ARG, "null CSR arrays");
   if (val_rows && (val_pitch < n_cells || val_pitch % 128 != 0))
     return set_error(GV_ERR_ARG, "val_pitch must be a multiple of 128 covering n_cells");
+  if (val_rows && (val_mode < 0 || val_mode > 3)) return set_error(GV_ERR_ARG, "unknown val_mode");
+  if (val_rows && val_mode != 1 && (val_limbs < 1 || val_limbs > 4))
+    return set_error(GV_ERR_ARG, "val_limbs must be in [1,4]");
+  if (val_rows && val_rows_alloc < gv_value_rows(n_genes, val_mode == 1 ? 1 : val_limbs))
+    return set_error(GV_ERR_ARG, "val_rows_alloc < gv_value_rows(n_genes, val_limbs)");
   DiscretizeArgs a;
   a.values = values; a.value_dtype = value_dtype; a.col_idx = col_idx; a.row_ptr = row_ptr;
   a.n_cells = n_cells; a.n_genes = n_genes; a.nnz = nnz; a.n_bins = n_bins; a.q_table = q_table_host;
@@ -103,15 +108,15 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
   return discretize_dispatch(a, static_cast<cudaStream_t>(stream));
 }
 
-int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
-                    int64_t n_cells, int n_genes, double* entropy_out, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
+                    const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int n_genes,
+                    double* entropy_out, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (n_genes <= 0 || n_cells < 0 || nnz < 0 || !entropy_out || !workspace || (nnz > 0 && (!values || !col_idx)))
     return set_error(GV_ERR_ARG, "gv_gene_entropy: bad argument");
-  return gene_entropy_dispatch(values, value_dtype, col_idx, nnz, n_cells, n_genes, entropy_out, workspace,
-                               workspace_bytes, static_cast<cudaStream_t>(stream));
+  return gene_entropy_dispatch(values, value_dtype, col_idx, row_ptr, nnz, n_cells, n_genes, entropy_out,
+                               workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int gv_rows_per_gene(int n_bins) {
@@ -126,6 +131,12 @@ int64_t gv_onehot_rows(int n_genes, int rows_per_gene) {
   if (rows_per_gene != 5 && rows_per_gene != 8 && rows_per_gene != 10 && rows_per_gene != 16)
     return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10 or 16");
   const int gpb = 32 / rows_per_gene;
+  return int64_t((n_genes + gpb - 1) / gpb) * 32;
+}
+
+int64_t gv_value_rows(int n_genes, int n_limbs) {
+  if (n_limbs < 1 || n_limbs > 4 || n_genes < 0) return set_error(GV_ERR_ARG, "n_limbs must be in [1,4]");
+  const int gpb = 32 / n_limbs;
   return int64_t((n_genes + gpb - 1) / gpb) * 32;
 }
 
@@ -203,7 +214,8 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     void* sync_ws, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
-  if (!val_rows || !tiles || n_genes <= 0 || n_limbs < 1 || op_rows < int64_t(n_genes) * n_limbs)
+  if (!val_rows || !tiles || n_genes <= 0 || n_limbs < 1 || n_limbs > 4 ||
+      op_rows < gv_value_rows(n_genes, n_limbs))
     return set_error(GV_ERR_ARG, "gv_moment_tiles: bad argument");
   if ((sgn && ld_sgn < n_genes) || (out && ld_out < n_genes))
     return set_error(GV_ERR_ARG, "gv_moment_tiles: leading dimension < n_genes");

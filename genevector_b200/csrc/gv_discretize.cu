@@ -39,6 +39,29 @@ template <> struct ValKey<double> {
   __device__ static double sub(double b, double a) { return __dsub_rn(b, a); }
 };
 
+// ---------------------------------------------------------------- value rows
+// Operand of the co-moment contraction (gv_moment_tiles): n_limbs INT8 rows per gene holding the
+// base-2^limb_bits digits of a non-negative integer per cell, in 32-row blocks of 32/n_limbs genes
+// (row = block*32 + slot*n_limbs + digit; see MomentEpi in gv_epilogues.cuh).  What the integer is:
+//   val_mode 0  the count itself (exact co-moments)
+//   val_mode 1  1 where the gene is detected (one row per gene; Jaccard)
+//   val_mode 2  fixed point: rint(x * 2^e_g) with a per-gene power-of-two scale that puts the gene's
+//               largest value just below 2^(n_limbs*limb_bits) (Pearson / cosine are invariant to it)
+//   val_mode 3  doubled average rank minus (n_zero + 1): 0 for the gene's zero cells,
+//               n_zero + #{values < x} + #{values <= x} for the others (Spearman = Pearson of ranks)
+__device__ __forceinline__ int64_t val_row0(int g, int n_limbs) {
+  const int gpb = 32 / n_limbs;
+  const int blk = g / gpb;
+  return int64_t(blk) * 32 + (g - blk * gpb) * n_limbs;
+}
+__device__ __forceinline__ void write_digits(int8_t* __restrict__ val_rows, int64_t val_pitch, int g,
+                                             int64_t cell, unsigned long long xi, int n_limbs,
+                                             int limb_bits) {
+  int8_t* p = val_rows + val_row0(g, n_limbs) * val_pitch + cell;
+  const unsigned long long mask = (1ull << limb_bits) - 1ull;
+  for (int l = 0; l < n_limbs; ++l) p[int64_t(l) * val_pitch] = int8_t((xi >> (l * limb_bits)) & mask);
+}
+
 // ---------------------------------------------------------------- k_count_positive
 // flags[0] |= 1 if a value is negative, |= 2 if a positive value is not an integer;
 // flags[1] = max over ceil(values) (as uint64).
@@ -155,6 +178,7 @@ struct GeneSmem {
   uint32_t marg[16];
   uint32_t scan_tmp[GB_THREADS];
   unsigned long long red[GB_THREADS / 32][2];
+  unsigned long long kmax[GB_THREADS / 32];
   int n_distinct;
   int n_slots;
   int n_undone;
@@ -168,7 +192,7 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
             int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
             double* __restrict__ edges_out, int64_t* __restrict__ gsum, int64_t* __restrict__ gsq,
             int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode, int limb_bits,
-            int n_limbs) {
+            int n_limbs, int64_t n_cells) {
   using K = ValKey<T>;
   __shared__ GeneSmem sm;
   const int tid = threadIdx.x;
@@ -193,13 +217,12 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
     if (tid < 16) sm.marg[tid] = 0;
     if (tid == 0) sm.n_distinct = 0;
     __syncthreads();
-    long long s1 = 0, s2 = 0;
+    unsigned long long kmax = 0;
     for (int64_t e = e0 + tid; e < e1; e += GB_THREADS) {
       const T v = g_val[e];
       const uint64_t key = K::key(v);
       atomicAdd(&sm.h0[uint32_t(key >> (K::W - H0_BITS))], 1u);
-      const long long xi = (long long)v;   // exact when the data are counts (flagged otherwise)
-      s1 += xi; s2 += xi * xi;
+      kmax = key > kmax ? key : kmax;
       if (*(volatile int*)&sm.n_distinct <= n_bins) {
         // open-addressing insert; stops mattering once more than n_bins values are known
         uint32_t h = uint32_t((key * 0x9E3779B97F4A7C15ull) >> 58);   // 6 bits
@@ -215,18 +238,13 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
         }
       }
     }
-    // block-reduce the sums
+    // largest value of the gene (positive floats order like their bit patterns)
     for (int d = 16; d >= 1; d >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, kmax, d);
+      kmax = o > kmax ? o : kmax;
     }
-    if (lane == 0) { sm.red[warp][0] = (unsigned long long)s1; sm.red[warp][1] = (unsigned long long)s2; }
+    if (lane == 0) sm.kmax[warp] = kmax;
     __syncthreads();
-    if (tid == 0) {
-      long long a = 0, b = 0;
-      for (int w = 0; w < GB_THREADS / 32; ++w) { a += (long long)sm.red[w][0]; b += (long long)sm.red[w][1]; }
-      gsum[g] = a; gsq[g] = b;
-    }
     const int n_dist = sm.n_distinct;
     const int k = n_dist < n_bins ? n_dist : n_bins;     // metrics.py:59
     const int n_edges = k > 1 ? k - 1 : 0;
@@ -356,6 +374,16 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
     }
     __syncthreads();
     // ---- bin assignment: bin = 1 + #{edges <= x}; packed nibbles, marginals, value rows
+    int fx_shift = 0;                       // val_mode 2: x -> rint(x * 2^fx_shift)
+    if (val_mode == 2) {
+      unsigned long long km = 0;
+      for (int w = 0; w < GB_THREADS / 32; ++w) km = sm.kmax[w] > km ? sm.kmax[w] : km;
+      int ex;
+      frexp(double(K::val(km)), &ex);       // max = f * 2^ex, f in [0.5, 1)
+      fx_shift = n_limbs * limb_bits - ex;
+    }
+    const unsigned long long xi_cap = (1ull << (n_limbs * limb_bits)) - 1ull;
+    long long s1 = 0, s2 = 0;
     uint32_t* brow = bins_packed + int64_t(g) * pitch_words;
     for (int64_t e = e0 + tid; e < e1; e += GB_THREADS) {
       const T v = g_val[e];
@@ -366,18 +394,40 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
       for (int t = 0; t < 14; ++t) bin += (t < n_edges && sm.edges[t] <= vd) ? 1 : 0;
       atomicOr(&brow[cell >> 3], uint32_t(bin) << ((cell & 7) * 4));
       atomicAdd(&sm.marg[bin], 1u);
+      // the integer behind the value rows and the per-gene sums
+      unsigned long long xi;
+      if (val_mode == 2) {
+        xi = (unsigned long long)llrint(ldexp(vd, fx_shift));
+        xi = xi > xi_cap ? xi_cap : xi;
+      } else if (val_mode == 3) {
+        // segments are sorted by value (k_rank path): #{values < x} + #{values <= x}
+        int64_t lo = e0, hi = e;            // first index holding v
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (g_val[mid] < v) lo = mid + 1; else hi = mid; }
+        const int64_t lb0 = lo - e0;
+        lo = e; hi = e1 - 1;                // last index holding v
+        while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if (g_val[mid] > v) hi = mid - 1; else lo = mid; }
+        xi = (unsigned long long)((n_cells - m) + lb0 + (lo - e0 + 1));
+      } else {
+        xi = (unsigned long long)v;         // exact when the data are counts (flagged otherwise)
+      }
+      s1 += (long long)xi; s2 += (long long)(xi * xi);
       if (val_rows != nullptr) {
-        if (val_mode == 1) {
-          val_rows[int64_t(g) * val_pitch + cell] = 1;       // detection indicator (jaccard)
-        } else {
-          const unsigned long long xi = (unsigned long long)v;
-          for (int l = 0; l < n_limbs; ++l)
-            val_rows[(int64_t(g) * n_limbs + l) * val_pitch + cell] =
-                int8_t((xi >> (l * limb_bits)) & ((1ull << limb_bits) - 1ull));
-        }
+        if (val_mode == 1) val_rows[int64_t(g) * val_pitch + cell] = 1;   // detection indicator (jaccard)
+        else write_digits(val_rows, val_pitch, g, cell, xi, n_limbs, limb_bits);
       }
     }
+    // block-reduce the sums
+    for (int d = 16; d >= 1; d >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) { sm.red[warp][0] = (unsigned long long)s1; sm.red[warp][1] = (unsigned long long)s2; }
     __syncthreads();
+    if (tid == 32) {
+      long long a = 0, b = 0;
+      for (int w = 0; w < GB_THREADS / 32; ++w) { a += (long long)sm.red[w][0]; b += (long long)sm.red[w][1]; }
+      gsum[g] = a; gsq[g] = b;
+    }
     if (tid == 0) {
       n_bins_per_gene[g] = (k <= 1) ? 2 : k + 1;             // metrics.py:62,67
       marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
@@ -539,7 +589,8 @@ __global__ void k_gene_lut(const uint32_t* __restrict__ hist, int G, int n_bins,
                            const double* __restrict__ q_table, uint8_t* __restrict__ lut,
                            int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
                            double* __restrict__ edges_out, int64_t* __restrict__ gsum,
-                           int64_t* __restrict__ gsq) {
+                           int64_t* __restrict__ gsq, uint32_t* __restrict__ rank_lut,
+                           int64_t n_cells) {
   using K = ValKey<T>;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -567,6 +618,27 @@ __global__ void k_gene_lut(const uint32_t* __restrict__ hist, int G, int n_bins,
       nun += __shfl_xor_sync(0xffffffffu, nun, d);
       s1 += __shfl_xor_sync(0xffffffffu, s1, d);
       s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (rank_lut != nullptr) {
+      // val_mode 3: value -> n_zero + #{values < v} + #{values <= v}; the sums are those of the ranks
+      uint32_t rk[8];
+      uint32_t run = lane_excl;
+      s1 = 0; s2 = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long r = (n_cells - m) + 2ll * run + c[i];
+        rk[i] = c[i] ? uint32_t(r) : 0u;
+        s1 += c[i] ? r * (long long)c[i] : 0ll;
+        s2 += c[i] ? r * r * (long long)c[i] : 0ll;
+        run += c[i];
+      }
+      uint4* rp = reinterpret_cast<uint4*>(rank_lut + int64_t(g) * VH + lane * 8);
+      rp[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+      rp[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
+      for (int d = 16; d >= 1; d >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+      }
     }
     if (lane == 0) { gsum[g] = s1; gsq[g] = s2; }
     double edge[14];
@@ -658,7 +730,8 @@ k_assign_csr(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
              const int64_t* __restrict__ row_ptr, int64_t n_cells, int64_t nnz,
              const uint8_t* __restrict__ lut, uint32_t* __restrict__ bins_packed,
              int64_t pitch_words, int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode,
-             int limb_bits, int n_limbs, unsigned long long* __restrict__ ticket) {
+             int limb_bits, int n_limbs, const uint32_t* __restrict__ rank_lut,
+             unsigned long long* __restrict__ ticket) {
   __shared__ unsigned long long s_chunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_chunks = (nnz + ASSIGN_CHUNK - 1) / ASSIGN_CHUNK;
@@ -689,13 +762,9 @@ k_assign_csr(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
         const uint32_t bin = lut[int64_t(g) * VH + xi];
         atomicOr(&bins_packed[int64_t(g) * pitch_words + (r >> 3)], bin << (uint32_t(r & 7) * 4));
         if (val_rows != nullptr) {
-          if (val_mode == 1) {
-            val_rows[int64_t(g) * val_pitch + r] = 1;
-          } else {
-            for (int l = 0; l < n_limbs; ++l)
-              val_rows[(int64_t(g) * n_limbs + l) * val_pitch + r] =
-                  int8_t((xi >> (l * limb_bits)) & ((1u << limb_bits) - 1u));
-          }
+          if (val_mode == 1) val_rows[int64_t(g) * val_pitch + r] = 1;
+          else if (val_mode == 3) write_digits(val_rows, val_pitch, g, r, rank_lut[int64_t(g) * VH + xi], n_limbs, limb_bits);
+          else write_digits(val_rows, val_pitch, g, r, xi, n_limbs, limb_bits);
         }
       }
     }
@@ -757,15 +826,33 @@ __global__ void k_gene_entropy(const uint32_t* __restrict__ hist, int G, int64_t
     if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
   } while (0)
 
+// implemented in gv_rank.cu
+size_t segsort_temp_bytes(int64_t nnz, int G, int value_dtype);
+int segsort_pairs(void* temp, size_t temp_bytes, const void* keys_in, void* keys_out,
+                  const int32_t* cells_in, int32_t* cells_out, int64_t nnz, int G,
+                  const int64_t* gene_ptr, int value_dtype, cudaStream_t st);
+
+// hflags: [0] bit0 negative value seen, bit1 fractional value seen; [1] max ceil(value)
 static int check_val_config(const DiscretizeArgs& a, const unsigned long long* hflags) {
-  if (a.val_rows == nullptr || a.val_mode != 0) return GV_OK;
-  if (hflags[0] != 0)
-    return set_error(GV_ERR_UNSUPPORTED,
-                     "co-moment path needs non-negative integer counts (negative or fractional values found)");
+  if (a.val_rows == nullptr || a.val_mode == 1) return GV_OK;
   const int n_limbs = a.val_limbs, limb_bits = a.val_limb_bits;
-  if (n_limbs < 1 || limb_bits < 1 || limb_bits > 7 ||
-      (n_limbs * limb_bits < 64 && (hflags[1] >> (n_limbs * limb_bits)) != 0))
-    return set_error(GV_ERR_UNSUPPORTED, "co-moment path: values exceed the configured limb range");
+  if (n_limbs < 1 || n_limbs > 4 || limb_bits < 1 || limb_bits > 7)
+    return set_error(GV_ERR_ARG, "value rows: n_limbs must be in [1,4] and limb_bits in [1,7]");
+  const int tb = n_limbs * limb_bits;
+  if (hflags[0] & 1ull)
+    return set_error(GV_ERR_UNSUPPORTED,
+                     "co-moment path needs non-negative values (negative values found)");
+  if (a.val_mode == 0) {
+    if (hflags[0] & 2ull)
+      return set_error(GV_ERR_UNSUPPORTED,
+                       "co-moment path (count digits) needs integer values (fractional values found): "
+                       "use the fixed-point value rows (val_mode 2)");
+    if ((hflags[1] >> tb) != 0)
+      return set_error(GV_ERR_UNSUPPORTED, "co-moment path: values exceed the configured limb range");
+  } else if (a.val_mode == 3) {
+    if (((unsigned long long)(2 * a.n_cells) >> tb) != 0)
+      return set_error(GV_ERR_UNSUPPORTED, "rank rows: 2*n_cells exceeds the configured limb range");
+  }
   return GV_OK;
 }
 
@@ -775,13 +862,15 @@ static int check_val_config(const DiscretizeArgs& a, const unsigned long long* h
     if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
   } while (0)
 
+static inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
+
 template <typename T>
 static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   const int G = a.n_genes;
   // workspace carve-up (all 256-byte aligned); the two paths share the front part
   uint8_t* ws = static_cast<uint8_t*>(a.workspace);
   size_t off = 0;
-  auto take = [&](size_t bytes) { void* p = ws + off; off += (bytes + 255) & ~size_t(255); return p; };
+  auto take = [&](size_t bytes) { void* p = ws + off; off += al256(bytes); return p; };
   unsigned long long* flags = static_cast<unsigned long long*>(take(64));
   double* qtab = static_cast<double*>(take(16 * 16 * 8));
   const size_t front = off;
@@ -789,6 +878,7 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   const int sms = device_sm_count();
   int8_t* val_rows = static_cast<int8_t*>(a.val_rows);
   const int n_limbs = a.val_mode == 1 ? 1 : a.val_limbs;
+  const bool ranks = val_rows != nullptr && a.val_mode == 3;
 
   GV_CUDA_TRY(cudaMemsetAsync(flags, 0, 64, st));
   GV_CUDA_TRY(cudaMemcpyAsync(qtab, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st));
@@ -797,10 +887,12 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     GV_CUDA_TRY(cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st));
   unsigned long long hflags[2] = {0, 0};
 
-  // ---------------- count-data fast path (tried first unless the caller forces the general one)
-  if (a.path != GV_PATH_GENERAL) {
+  // ---------------- count-data fast path (tried first unless the caller forces the general one;
+  // fixed-point value rows are for data that are not counts, so they go straight to the general path)
+  if (a.path != GV_PATH_GENERAL && !(val_rows != nullptr && a.val_mode == 2)) {
     uint32_t* hist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
     uint8_t* lut = static_cast<uint8_t*>(take(size_t(G) * VH));
+    uint32_t* rank_lut = ranks ? static_cast<uint32_t*>(take(size_t(G) * VH * 4)) : nullptr;
     if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
     GV_CUDA_TRY(cudaMemsetAsync(hist, 0, size_t(G) * VH * 4, st));
     if (a.nnz > 0) {
@@ -815,14 +907,14 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
       int rc = check_val_config(a, hflags);
       if (rc != GV_OK) return rc;
       k_gene_lut<T><<<(G + 7) / 8, 256, 0, st>>>(hist, G, a.n_bins, qtab, lut, a.n_bins_per_gene, a.marg,
-                                                  a.edges, a.gsum, a.gsq);
+                                                  a.edges, a.gsum, a.gsq, rank_lut, a.n_cells);
       GV_LAUNCH_CHECK();
       if (a.nnz > 0) {
         // flags[4] is the ticket counter (zeroed with the flags block above)
         k_assign_csr<T><<<sms * 8, ASSIGN_THREADS, 0, st>>>(
             values, a.col_idx, a.row_ptr, a.n_cells, a.nnz, lut, static_cast<uint32_t*>(a.bins_packed),
             int64_t(a.bins_pitch_bytes / 4), val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs,
-            flags + 4);
+            rank_lut, flags + 4);
         GV_LAUNCH_CHECK();
       }
       if (a.path_used) *a.path_used = GV_PATH_COUNTS;
@@ -839,17 +931,18 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   int64_t* gene_ptr = static_cast<int64_t*>(take(size_t(G + 1) * 8));
   int32_t* g_cell = static_cast<int32_t*>(take(size_t(a.nnz) * 4));
   T* g_val = static_cast<T*>(take(size_t(a.nnz) * sizeof(T)));
+  int32_t* s_cell = nullptr; T* s_val = nullptr; void* sort_tmp = nullptr; size_t sort_bytes = 0;
+  if (ranks) {
+    s_cell = static_cast<int32_t*>(take(size_t(a.nnz) * 4));
+    s_val = static_cast<T*>(take(size_t(a.nnz) * sizeof(T)));
+    sort_bytes = segsort_temp_bytes(a.nnz, G, a.value_dtype);
+    sort_tmp = take(sort_bytes);
+  }
   if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
   GV_CUDA_TRY(cudaMemsetAsync(cnt, 0, size_t(G) * 4, st));
   GV_CUDA_TRY(cudaMemsetAsync(flags, 0, 64, st));
   if (a.nnz > 0) {
     k_count_positive<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, cnt, flags);
-    GV_LAUNCH_CHECK();
-  }
-  k_scan_counts<<<1, 1024, 0, st>>>(cnt, gene_ptr, cursor, G);
-  GV_LAUNCH_CHECK();
-  if (a.nnz > 0) {
-    k_scatter<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, cursor, g_cell, g_val);
     GV_LAUNCH_CHECK();
   }
   // data flags decide the limb layout of the value rows; read them back (one small sync)
@@ -858,46 +951,132 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
   int rc = check_val_config(a, hflags);
   if (rc != GV_OK) return rc;
+  k_scan_counts<<<1, 1024, 0, st>>>(cnt, gene_ptr, cursor, G);
+  GV_LAUNCH_CHECK();
+  if (a.nnz > 0) {
+    k_scatter<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, cursor, g_cell, g_val);
+    GV_LAUNCH_CHECK();
+  }
+  if (ranks) {
+    // explicit zeros / negatives are dropped by k_scatter, so the segments hold positives only
+    rc = segsort_pairs(sort_tmp, sort_bytes, g_val, s_val, g_cell, s_cell, a.nnz, G, gene_ptr,
+                       a.value_dtype, st);
+    if (rc != GV_OK) return rc;
+    g_cell = s_cell; g_val = s_val;
+  }
   k_gene_bins<T><<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, 0, st>>>(
       gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
       int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
-      a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs);
+      a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, a.n_cells);
   GV_LAUNCH_CHECK();
   if (a.path_used) *a.path_used = GV_PATH_GENERAL;
   return GV_OK;
 }
 
+// ---------------------------------------------------------------- gene entropy, general data
+// Sorted gene segments (positives only): runs of equal values are the unique values, their lengths
+// the counts; the zero count is n_cells - m and is the one np.unique lists first (data.py:201-202
+// drops it); a gene without zeros loses its smallest positive value's count instead.
 template <typename T>
-static int gene_entropy_impl(const void* values, const int32_t* col_idx, int64_t nnz, int64_t n_cells,
-                             int G, double* ent, void* workspace, size_t ws_bytes, cudaStream_t st) {
+__global__ void __launch_bounds__(256)
+k_gene_entropy_sorted(const int64_t* __restrict__ gene_ptr, const T* __restrict__ s_val, int G,
+                      int64_t n_cells, double* __restrict__ ent) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const int64_t e0 = gene_ptr[g], e1 = gene_ptr[g + 1];
+    const int64_t m = e1 - e0;
+    auto run_end = [&](int64_t e) {          // last index holding s_val[e]
+      const T v = s_val[e];
+      int64_t lo = e, hi = e1 - 1;
+      while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if (s_val[mid] > v) hi = mid - 1; else lo = mid; }
+      return lo;
+    };
+    int64_t first_kept = e0;                 // a gene without zeros drops its first run
+    if (m > 0 && m == n_cells) first_kept = run_end(e0) + 1;
+    const double kept = double(e1 - first_kept);
+    double h = 0.0;
+    for (int64_t e = first_kept + tid; e < e1; e += 256) {
+      if (e == first_kept || s_val[e - 1] != s_val[e]) {
+        const double pk = double(run_end(e) - e + 1) / kept;
+        h -= pk * log(pk);
+      }
+    }
+    for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    __syncthreads();
+    if (lane == 0) red[warp] = h;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      ent[g] = t;
+    }
+  }
+}
+
+template <typename T>
+static int gene_entropy_impl(const void* values_v, const int32_t* col_idx, const int64_t* row_ptr,
+                             int64_t nnz, int64_t n_cells, int G, double* ent, void* workspace,
+                             size_t ws_bytes, cudaStream_t st) {
+  const T* values = static_cast<const T*>(values_v);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  const size_t need = 256 + ((size_t(G) * VH * 4 + 255) & ~size_t(255));
-  if (ws_bytes < need) return set_error(GV_ERR_ARG, "gene entropy: workspace too small");
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(ws);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + 256);
-  GV_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = ws + off; off += al256(bytes); return p; };
+  unsigned long long* flags = static_cast<unsigned long long*>(take(64));
+  const size_t front = off;
+  uint32_t* hist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
+  if (off > ws_bytes) return set_error(GV_ERR_ARG, "gene entropy: workspace too small");
+  GV_CUDA_TRY(cudaMemsetAsync(ws, 0, off, st));
   const int sms = device_sm_count();
   if (nnz > 0) {
-    k_hist2d<T><<<sms * 8, 256, 0, st>>>(static_cast<const T*>(values), col_idx, nnz, hist, flags);
+    k_hist2d<T><<<sms * 8, 256, 0, st>>>(values, col_idx, nnz, hist, flags);
     GV_LAUNCH_CHECK();
   }
   unsigned long long hflags[2] = {0, 0};
   GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
   GV_CUDA_TRY(cudaStreamSynchronize(st));
-  if (hflags[0] != 0 || hflags[1] >= (unsigned long long)VH)
-    return set_error(GV_ERR_UNSUPPORTED, "gene entropy needs non-negative integer counts <= 255");
-  k_gene_entropy<<<(G + 7) / 8, 256, 0, st>>>(hist, G, n_cells, ent);
+  if (hflags[0] & 1ull)
+    return set_error(GV_ERR_UNSUPPORTED, "gene entropy needs non-negative values");
+  if ((hflags[0] & 2ull) == 0 && hflags[1] < (unsigned long long)VH) {
+    k_gene_entropy<<<(G + 7) / 8, 256, 0, st>>>(hist, G, n_cells, ent);
+    GV_LAUNCH_CHECK();
+    return GV_OK;
+  }
+  // general data: gene-major regroup, per-gene sort, run lengths
+  if (!row_ptr) return set_error(GV_ERR_ARG, "gene entropy of non-count data needs row_ptr");
+  off = front;
+  uint32_t* cnt = static_cast<uint32_t*>(take(size_t(G) * 4));
+  unsigned long long* cursor = static_cast<unsigned long long*>(take(size_t(G) * 8));
+  int64_t* gene_ptr = static_cast<int64_t*>(take(size_t(G + 1) * 8));
+  int32_t* g_cell = static_cast<int32_t*>(take(size_t(nnz) * 4));
+  T* g_val = static_cast<T*>(take(size_t(nnz) * sizeof(T)));
+  int32_t* s_cell = static_cast<int32_t*>(take(size_t(nnz) * 4));
+  T* s_val = static_cast<T*>(take(size_t(nnz) * sizeof(T)));
+  const int dt = sizeof(T) == 8 ? GV_F64 : GV_F32;
+  const size_t sort_bytes = segsort_temp_bytes(nnz, G, dt);
+  void* sort_tmp = take(sort_bytes);
+  if (off > ws_bytes) return set_error(GV_ERR_ARG, "gene entropy: workspace too small");
+  GV_CUDA_TRY(cudaMemsetAsync(cnt, 0, size_t(G) * 4, st));
+  k_count_positive<T><<<sms * 8, 256, 0, st>>>(values, col_idx, nnz, cnt, flags);
+  GV_LAUNCH_CHECK();
+  k_scan_counts<<<1, 1024, 0, st>>>(cnt, gene_ptr, cursor, G);
+  GV_LAUNCH_CHECK();
+  k_scatter<T><<<sms * 8, 256, 0, st>>>(values, col_idx, row_ptr, n_cells, cursor, g_cell, g_val);
+  GV_LAUNCH_CHECK();
+  int rc = segsort_pairs(sort_tmp, sort_bytes, g_val, s_val, g_cell, s_cell, nnz, G, gene_ptr, dt, st);
+  if (rc != GV_OK) return rc;
+  k_gene_entropy_sorted<T><<<G < sms * 8 ? G : sms * 8, 256, 0, st>>>(gene_ptr, s_val, G, n_cells, ent);
   GV_LAUNCH_CHECK();
   return GV_OK;
 }
 
-int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
-                          int64_t n_cells, int G, double* ent, void* workspace, size_t ws_bytes,
-                          cudaStream_t st) {
+int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx,
+                          const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int G, double* ent,
+                          void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (value_dtype == GV_F32)
-    return gene_entropy_impl<float>(values, col_idx, nnz, n_cells, G, ent, workspace, ws_bytes, st);
+    return gene_entropy_impl<float>(values, col_idx, row_ptr, nnz, n_cells, G, ent, workspace, ws_bytes, st);
   if (value_dtype == GV_F64)
-    return gene_entropy_impl<double>(values, col_idx, nnz, n_cells, G, ent, workspace, ws_bytes, st);
+    return gene_entropy_impl<double>(values, col_idx, row_ptr, nnz, n_cells, G, ent, workspace, ws_bytes, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
@@ -910,13 +1089,16 @@ int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
-size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype) {
-  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+// sorted = the caller will need the per-gene sort (rank value rows, entropy of non-count data)
+size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype, int sorted) {
   const size_t vs = value_dtype == GV_F64 ? 8 : 4;
-  const size_t front = al(64) + al(16 * 16 * 8);
-  const size_t counts = al(size_t(G) * VH * 4) + al(size_t(G) * VH);
-  const size_t general = al(size_t(G) * 4) + al(size_t(G) * 8) + al(size_t(G + 1) * 8) +
-                         al(size_t(nnz) * 4) + al(size_t(nnz) * vs);
+  const size_t front = al256(64) + al256(16 * 16 * 8);
+  const size_t counts = al256(size_t(G) * VH * 4) + al256(size_t(G) * VH) +
+                        (sorted ? al256(size_t(G) * VH * 4) : 0);
+  size_t general = al256(size_t(G) * 4) + al256(size_t(G) * 8) + al256(size_t(G + 1) * 8) +
+                   al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs);
+  if (sorted)
+    general += al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs) + al256(segsort_temp_bytes(nnz, G, value_dtype));
   return front + (counts > general ? counts : general) + 256;
 }
 

@@ -248,14 +248,29 @@ struct MomentParams {
   int limb_bits;         // digit width of the value rows (two-digit operands)
 };
 
-// L = operand rows per gene: base-2^limb_bits digits of the count, least significant first
-// (row = gene*L + digit).  Sum_c x_i x_j = Sum_{p,q} 2^{limb_bits (p+q)} acc[(i,p),(j,q)]: the q sum
-// is taken in registers (adjacent columns), the p sum across adjacent lanes.
+// 128-bit integers keep n*Sum(xy) - Sum(x)*Sum(y) exact for 21-bit fixed-point values over 2^18 cells.
+typedef __int128 i128;
+__device__ __forceinline__ double i128_to_double(i128 v) {
+  const bool neg = v < 0;
+  const unsigned __int128 m = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+  const double d = double((unsigned long long)(m >> 64)) * 18446744073709551616.0 +
+                   double((unsigned long long)m);
+  return neg ? -d : d;
+}
+
+// L = operand rows per gene: base-2^limb_bits digits of the (count / fixed-point / doubled rank)
+// value, least significant first.  The value rows use the same 32-row block layout as the one-hot
+// operand: a block holds GPB = 32/L genes (row = block*32 + slot*L + digit; L = 3 leaves two zero
+// rows per block), so a gene's digits never straddle a 32-lane TMEM quarter.
+// Sum_c x_i x_j = Sum_{p,q} 2^{limb_bits (p+q)} acc[(i,p),(j,q)]: the q sum is taken in registers
+// (adjacent columns), the p sum across the L adjacent lanes of gene i.
 template <int KIND, int L>
 struct MomentEpi {
-  static_assert(L == 1 || L == 2, "one or two digits per gene");
+  static_assert(L >= 1 && L <= 4, "one to four digits per gene");
   using Params = MomentParams;
-  static constexpr int GENES_PER_TILE = GRAM_TILE_N / L;
+  static constexpr int GPB = 32 / L;              // genes per 32-row block
+  static constexpr int ACTIVE = GPB * L;          // data rows per block
+  static constexpr int GENES_PER_TILE = 8 * GPB;  // column genes per tile
   struct Meta {
     int64_t csum[GENES_PER_TILE];
     int64_t csq[GENES_PER_TILE];
@@ -272,7 +287,7 @@ struct MomentEpi {
     epi_bar_sync();
     const int c = et.epi_tid;
     if (c < GENES_PER_TILE) {
-      const int gj = et.col0 / L + c;
+      const int gj = (et.col0 >> 5) * GPB + c;
       if constexpr (KIND == MOM_JACCARD) {
         meta->csum[c] = gj < p.G ? int64_t(p.marg[int64_t(gj) * MARG_STRIDE]) : 0;
         meta->csq[c] = 0;
@@ -284,10 +299,10 @@ struct MomentEpi {
     epi_bar_sync();
   }
   __device__ void run(const EpiTile& et) {
-    const int row = et.row0 + et.quarter * 32 + et.lane;
-    const int gi = row / L;
-    const int digit = row - gi * L;
-    const bool row_ok = gi < p.G;
+    const int si = et.lane / L;
+    const int digit = et.lane - si * L;
+    const int gi = ((et.row0 >> 5) + et.quarter) * GPB + si;
+    const bool row_ok = et.lane < ACTIVE && gi < p.G;
     int64_t sx = 0, sxx = 0;
     if (row_ok) {
       if constexpr (KIND == MOM_JACCARD) {
@@ -297,8 +312,8 @@ struct MomentEpi {
         sxx = p.gsq[gi];
       }
     }
-    const int64_t n = p.n_cells;
-    const int64_t var_i = n * sxx - sx * sx;
+    const i128 n = i128(p.n_cells);
+    const i128 var_i = n * sxx - i128(sx) * sx;
     const int lb = p.limb_bits;
 #pragma unroll 1
     for (int cbi = 0; cbi < 4; ++cbi) {
@@ -307,15 +322,16 @@ struct MomentEpi {
       tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32 / L; ++c) {
-        const int cg = (cb * 32) / L + c;       // column gene within the tile
-        const int gj = et.col0 / L + cg;
+      for (int c = 0; c < GPB; ++c) {
+        const int cg = cb * GPB + c;            // column gene within the tile
+        const int gj = ((et.col0 >> 5) + cb) * GPB + c;
         // accumulators are read as unsigned 32-bit (sums of digit products < 2^32)
         int64_t sxy = int64_t(v[c * L]);
-        if constexpr (L == 2) {
-          sxy += int64_t(v[c * L + 1]) << lb;
+        if constexpr (L > 1) {
+#pragma unroll
+          for (int q = 1; q < L; ++q) sxy += int64_t(v[c * L + q]) << (q * lb);
           sxy <<= (digit * lb);
-          sxy += __shfl_xor_sync(0xffffffffu, sxy, 1);   // add the other digit row of gene i
+          sxy = seg_reduce<L>(sxy, digit);      // add the other digit rows of gene i
         }
         if (digit != 0 || !row_ok || gj >= p.G || gi > gj) continue;
         const int64_t sy = meta->csum[cg];
@@ -323,8 +339,8 @@ struct MomentEpi {
           int8_t s = 0;
           if (gi != gj) {
             const int64_t syy = meta->csq[cg];
-            const int64_t var_j = n * syy - sy * sy;
-            const int64_t cov = n * sxy - sx * sy;
+            const i128 var_j = n * syy - i128(sy) * sy;
+            const i128 cov = n * sxy - i128(sx) * sy;
             s = (var_i == 0 || var_j == 0) ? 0 : (cov > 0 ? 1 : (cov < 0 ? -1 : 0));
           }
           p.sgn[int64_t(gi) * p.ld_sgn + gj] = s;
@@ -334,9 +350,10 @@ struct MomentEpi {
           if (gi != gj) {
             if constexpr (KIND == MOM_PEARSON) {
               const int64_t syy = meta->csq[cg];
-              const int64_t var_j = n * syy - sy * sy;
-              const int64_t cov = n * sxy - sx * sy;
-              double q = double(cov) / sqrt(double(var_i) * double(var_j));  // 0/0 -> NaN as np.corrcoef
+              const i128 var_j = n * syy - i128(sy) * sy;
+              const i128 cov = n * sxy - i128(sx) * sy;
+              // 0/0 -> NaN as np.corrcoef
+              double q = i128_to_double(cov) / sqrt(i128_to_double(var_i) * i128_to_double(var_j));
               q = q > 1.0 ? 1.0 : (q < -1.0 ? -1.0 : q);
               r = float(q);
             } else if constexpr (KIND == MOM_COSINE) {

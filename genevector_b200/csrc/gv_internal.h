@@ -30,10 +30,10 @@ struct DiscretizeArgs {
 };
 
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st);
-size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype);
-int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
-                          int64_t n_cells, int G, double* ent, void* workspace, size_t ws_bytes,
-                          cudaStream_t st);
+size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype, int sorted);
+int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx,
+                          const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int G, double* ent,
+                          void* workspace, size_t ws_bytes, cudaStream_t st);
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
                            void* onehot, int64_t kp, int n_blocks, int operand_format,
                            cudaStream_t st);

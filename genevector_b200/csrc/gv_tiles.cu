@@ -187,13 +187,23 @@ int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64
   if (kind == GV_MOM_JACCARD && (!out || !marg || n_limbs != 1))
     return set_error(GV_ERR_ARG, "jaccard needs out, marg and one detection row per gene");
   if (limb_bits < 1 || limb_bits > 7) return set_error(GV_ERR_ARG, "limb_bits must be in [1,7]");
-  // exactness: every digit product summed over all cells must fit the (unsigned) 32-bit accumulator
+  if (n_limbs < 1 || n_limbs > 4)
+    return set_error(GV_ERR_UNSUPPORTED, "co-moment path supports one to four digits per gene");
+  // exactness: every digit product summed over all cells must fit the (unsigned) 32-bit accumulator,
+  // and the recombined Sum x_i x_j (values < 2^(n_limbs*limb_bits)) the signed 64-bit sums
   const uint64_t dmax = (1ull << limb_bits) - 1ull;
   if (uint64_t(n_cells) * dmax * dmax >= (1ull << 32))
     return set_error(GV_ERR_UNSUPPORTED, "co-moment accumulators would overflow: lower limb_bits");
-  if (n_limbs == 1) return moment_dispatch_l<1>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
-  if (n_limbs == 2) return moment_dispatch_l<2>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
-  return set_error(GV_ERR_UNSUPPORTED, "co-moment path supports one or two digits per gene");
+  const int tb = n_limbs * limb_bits;
+  if (tb > 31 || (long double)n_cells * (long double)((1ull << tb) - 1ull) * (long double)((1ull << tb) - 1ull) >=
+                     9.2e18L)
+    return set_error(GV_ERR_UNSUPPORTED, "co-moment sums would overflow 64 bits: fewer value bits needed");
+  switch (n_limbs) {
+    case 1: return moment_dispatch_l<1>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    case 2: return moment_dispatch_l<2>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    case 3: return moment_dispatch_l<3>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    default: return moment_dispatch_l<4>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+  }
 }
 
 }  // namespace gv

@@ -79,19 +79,20 @@ def build_training_tensors(scores, genes, c=100.0, signed_mi=True, device="cuda"
 
 def get_gene_entropy(X, gene_names, device="cuda"):
     """GeneVectorDataset.get_gene_entropy (data.py:186-203) on the device: {gene: entropy in nats of
-    the counts of its unique values after dropping the first}.  Count data (non-negative integers
-    <= 255); anything else raises GvError (no CPU fallback)."""
+    the counts of its unique values after dropping the first}.  Integer counts <= 255 go through a
+    per-gene value histogram, any other non-negative data through a per-gene sort; negative values
+    raise GvError (no CPU fallback)."""
     eng = get_engine(device if device not in (None, "cpu") else None)
     csr = eng.upload_csr(X)
     if len(gene_names) != csr.n_genes:
         raise ValueError("gene_names must have one entry per column of X")
     with torch.cuda.device(eng.device):
         dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
-        ws_bytes = eng.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt)
+        ws_bytes = eng.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt, 1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=eng.device)
         ent = torch.empty(csr.n_genes, dtype=torch.float64, device=eng.device)
-        _lib.call("gv_gene_entropy", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(), csr.nnz,
-                  csr.n_cells, csr.n_genes, ent.data_ptr(), ws.data_ptr(), ws_bytes,
-                  torch.cuda.current_stream(eng.device).cuda_stream)
+        _lib.call("gv_gene_entropy", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(),
+                  csr.row_ptr.data_ptr(), csr.nnz, csr.n_cells, csr.n_genes, ent.data_ptr(),
+                  ws.data_ptr(), ws_bytes, torch.cuda.current_stream(eng.device).cuda_stream)
         vals = ent.cpu().numpy()
     return {g: float(v) for g, v in zip(gene_names, vals)}

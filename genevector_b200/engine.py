@@ -47,6 +47,18 @@ def limb_bits_for(n_cells: int) -> int:
     raise GvError("limb_bits_for", _lib.GV_OK - 4, f"n_cells={n_cells} too large for the exact co-moment path")
 
 
+def value_rows(n_genes: int, n_limbs: int) -> int:
+    """Operand rows of the value matrix: 32-row blocks of 32 // n_limbs genes (gv_value_rows)."""
+    gpb = 32 // n_limbs
+    return (n_genes + gpb - 1) // gpb * 32
+
+
+def max_limbs_for(n_cells: int, limb_bits: int) -> int:
+    """Most digits per gene (<= 4) for which Sum x_i*x_j over all cells still fits 63 bits."""
+    tb_max = (63 - max(int(n_cells), 1).bit_length()) // 2
+    return max(0, min(4, tb_max // limb_bits))
+
+
 @dataclasses.dataclass
 class CsrDevice:
     """A cells x genes CSR matrix resident on the device."""
@@ -77,12 +89,23 @@ class BinBlock:
     edges: torch.Tensor          # float64 [G][16]
     gsum: torch.Tensor           # int64 [G]
     gsq: torch.Tensor            # int64 [G]
-    val_rows: Optional[torch.Tensor]   # int8 [G * n_limbs][kp] or None
-    val_mode: int                # -1 none, 0 count digits, 1 detection indicator
-    n_limbs: int                 # INT8 rows per gene in val_rows (1 or 2)
+    val_rows: Optional[torch.Tensor]   # int8 [value_rows(G, n_limbs)][kp] or None
+    val_mode: int                # -1 none, 0 count digits, 1 detection indicator, 2 fixed point, 3 ranks
+    n_limbs: int                 # INT8 rows per gene in val_rows (1..4)
     limb_bits: int
     data_flags: tuple            # (flag bits, max value)
     path_used: int = 0           # gv_disc_path the discretisation took (1 counts, 2 general)
+
+    def gene_values(self) -> np.ndarray:
+        """The integers behind the value rows, int64 [n_genes][n_cells] (tests)."""
+        vr = self.val_rows.cpu().numpy().astype(np.int64)
+        L, gpb = self.n_limbs, 32 // self.n_limbs
+        g = np.arange(self.n_genes)
+        row0 = (g // gpb) * 32 + (g % gpb) * L
+        out = np.zeros((self.n_genes, self.n_cells), dtype=np.int64)
+        for d in range(L):
+            out += vr[row0 + d, :self.n_cells] << (d * self.limb_bits)
+        return out
 
     def x_disc(self) -> np.ndarray:
         """Unpack to the reference's layout: int32 [n_cells][n_genes] (tests / small cases)."""
@@ -93,7 +116,7 @@ class BinBlock:
         return np.ascontiguousarray(full[:, :self.n_cells].T)
 
 
-HEADER_BYTES = 256   # int64[0] = n_limbs, [1] = limb_bits, [2] = data flag bits, [3] = max value
+HEADER_BYTES = 256   # int64[0] = n_limbs, [1] = limb_bits, [2] = data flag bits, [3] = max value, [4] = val_mode
 
 
 def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1):
@@ -105,7 +128,7 @@ def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1):
     for name, nbytes in (("header", HEADER_BYTES), ("bins", n_genes * pitch),
                          ("marg", n_genes * 16 * 4), ("nbpg", n_genes * 4),
                          ("edges", n_genes * 16 * 8), ("gsum", n_genes * 8), ("gsq", n_genes * 8),
-                         ("val", (n_genes * n_limbs * kp) if val_mode >= 0 else 0)):
+                         ("val", (value_rows(n_genes, n_limbs) * kp) if val_mode >= 0 else 0)):
         lay[name] = (off, nbytes)
         off += _align(nbytes)
     return kp, pitch, lay, off
@@ -124,7 +147,7 @@ def _views(buf, n_cells, n_genes, n_bins, val_mode, n_limbs, limb_bits, flags=(0
         n_bins_per_gene=v("nbpg", torch.int32, (n_genes,)),
         edges=v("edges", torch.float64, (n_genes, 16)), gsum=v("gsum", torch.int64, (n_genes,)),
         gsq=v("gsq", torch.int64, (n_genes,)),
-        val_rows=v("val", torch.int8, (n_genes * n_limbs, kp)) if val_mode >= 0 else None,
+        val_rows=v("val", torch.int8, (value_rows(n_genes, n_limbs), kp)) if val_mode >= 0 else None,
         val_mode=val_mode, n_limbs=n_limbs, limb_bits=limb_bits, data_flags=flags)
 
 
@@ -241,27 +264,45 @@ class Engine:
     def discretize(self, csr: CsrDevice, n_bins: int = 10, val_mode: int = -1,
                    buf: Optional[torch.Tensor] = None, path: int = _lib.GV_PATH_AUTO,
                    n_limbs: Optional[int] = None) -> BinBlock:
-        """gv_discretize_csr.  val_mode: -1 no value rows, 0 count digits (sign / pearson / cosine),
-        1 detection indicator (jaccard).  n_limbs None = one digit per gene, retried with two when
-        the counts do not fit one (values up to 2^(2*limb_bits) - 1)."""
+        """gv_discretize_csr.  val_mode: -1 no value rows; 0 the values themselves (sign / pearson /
+        cosine): count digits, one per gene, retried with more digits when the counts need them and
+        with fixed-point rows (mode 2) when the data are not integers; 1 detection indicator
+        (jaccard); 2 fixed point; 3 doubled average ranks (spearman).  n_limbs fixes the digit count
+        (no retry).  The block's val_mode / n_limbs say what was produced."""
         if not 1 <= n_bins <= 15:
             raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
         if csr.values.dtype not in (torch.float32, torch.float64):
             raise GvError("discretize", -1, "values must be float32 or float64")
-        auto_limbs = n_limbs is None and val_mode == 0
-        L = 1 if (n_limbs is None or val_mode != 0) else n_limbs
         with torch.cuda.device(self.device):
-            lb = limb_bits_for(max(csr.n_cells, 1)) if val_mode == 0 else 7
+            lb = limb_bits_for(max(csr.n_cells, 1)) if val_mode in (0, 2, 3) else 7
+            l_max = max_limbs_for(csr.n_cells, lb)
+            l_fixed = min(3, l_max)
+            auto = n_limbs is None and val_mode == 0
+            if val_mode in (-1, 1):
+                L = 1
+            elif n_limbs is not None:
+                L = n_limbs
+            elif val_mode == 2:
+                L = l_fixed
+            elif val_mode == 3:
+                L = -(-(2 * max(csr.n_cells, 1)).bit_length() // lb)
+            else:
+                L = 1
+            if val_mode >= 0 and not 1 <= L <= max(l_max, 1):
+                raise GvError("discretize", -4, f"value rows would need {L} digits per gene; at most "
+                              f"{l_max} keep the co-moments of {csr.n_cells} cells exact")
             dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
-            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt)
+            sorted_ws = 1 if val_mode == 3 else 0
+            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt, sorted_ws)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             q = quantile_table()
+            mode = val_mode
             while True:
-                kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, val_mode, L)
+                kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, mode, L)
                 b = buf if (buf is not None and buf.numel() >= total) else \
                     torch.empty(total, dtype=torch.uint8, device=self.device)
                 assert b.device == self.device
-                blk = _views(b, csr.n_cells, csr.n_genes, n_bins, val_mode, L, lb)
+                blk = _views(b, csr.n_cells, csr.n_genes, n_bins, mode, L, lb)
                 flags = np.zeros(2, dtype=np.uint64)
                 used = np.zeros(1, dtype=np.int32)
                 vr = blk.val_rows
@@ -271,21 +312,30 @@ class Engine:
                                q.ctypes.data, blk.bins.data_ptr(), pitch, blk.n_bins_per_gene.data_ptr(),
                                blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(),
                                blk.gsq.data_ptr(), vr.data_ptr() if vr is not None else None, kp,
-                               csr.n_genes * L if vr is not None else 0, max(val_mode, 0), L, lb,
+                               vr.shape[0] if vr is not None else 0, max(mode, 0), L, lb,
                                flags.ctypes.data, ws.data_ptr(), ws_bytes, path, used.ctypes.data,
                                self._stream())
                 except GvError as e:
-                    fits_two = int(flags[0]) == 0 and int(flags[1]) < (1 << (2 * lb))
-                    if auto_limbs and L == 1 and e.status == -4 and "limb range" in str(e) and fits_two:
-                        L = 2          # counts above one digit: redo with two INT8 rows per gene
-                        continue
-                    raise
+                    negative, fractional = int(flags[0]) & 1, int(flags[0]) & 2
+                    if not (auto and mode == 0 and e.status == -4) or negative:
+                        raise
+                    need = -(-int(flags[1]).bit_length() // lb)      # digits the largest count needs
+                    if fractional or need > l_max:
+                        if l_fixed < 1:
+                            raise
+                        mode, L = 2, l_fixed       # not counts (or too large): fixed-point rows
+                    elif need > L:
+                        L = need                   # larger counts: more INT8 digits per gene, still exact
+                    else:
+                        raise
+                    continue
                 break
             blk.data_flags = (int(flags[0]), int(flags[1]))
             blk.path_used = int(used[0])
-            hdr = torch.tensor([L, lb, int(flags[0]), int(flags[1]) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64)
+            hdr = torch.tensor([L, lb, int(flags[0]), int(flags[1]) & 0x7FFFFFFFFFFFFFFF, mode],
+                               dtype=torch.int64)
             o, _ = lay["header"]
-            b[o:o + 32].view(torch.int64).copy_(hdr)
+            b[o:o + 40].view(torch.int64).copy_(hdr)
             return blk
 
     def _fmt(self, operand: Optional[str], blk: Optional[BinBlock] = None) -> int:
@@ -330,12 +380,13 @@ class Engine:
             return out
 
     def sign_tiles_for(self, mi_tiles: np.ndarray, B: int, n_limbs: int = 1) -> torch.Tensor:
-        """Sign-map tiles (operand rows of the value matrix: n_limbs rows per gene) that cover the
+        """Sign-map tiles (operand rows of the value matrix: 32 // n_limbs genes per 32 rows) that cover the
         gene pairs of the given MI tiles (one-hot operand rows), so a rank only computes the part
         of the sign map it reads."""
         gpb = 32 // B
         tm = _lib.call("gv_tile_m", self.cta_group)
-        gr, gc = tm // n_limbs, 256 // n_limbs          # genes per sign tile side
+        vgpb = 32 // n_limbs                            # genes per 32-row block of the value rows
+        gr, gc = tm // 32 * vgpb, 8 * vgpb              # genes per sign tile side
         r_lo = mi_tiles[:, 0].astype(np.int64) // 32 * gpb
         r_hi = (mi_tiles[:, 0].astype(np.int64) + tm) // 32 * gpb - 1
         c_lo = mi_tiles[:, 1].astype(np.int64) // 32 * gpb
@@ -354,12 +405,12 @@ class Engine:
     def sign_matrix(self, blk: BinBlock, tiles: Optional[torch.Tensor] = None) -> torch.Tensor:
         """int8 [G][ld] Pearson sign from the INT8 value rows (exact integer co-moments).
         `tiles`: optional subset of sign tiles (see sign_tiles_for); default the whole triangle."""
-        assert blk.val_rows is not None and blk.val_mode == 0
+        assert blk.val_rows is not None and blk.val_mode in (0, 2)
         with torch.cuda.device(self.device):
             G = blk.n_genes
             ld = _align(G, 16)
             sgn = torch.zeros((G, ld), dtype=torch.int8, device=self.device)
-            rows = G * blk.n_limbs
+            rows = value_rows(G, blk.n_limbs)
             if tiles is None:
                 tiles, n, _ = self.schedule(rows)
             else:
@@ -378,7 +429,7 @@ class Engine:
             G = blk.n_genes
             if out is None:
                 out = torch.zeros((G, G), dtype=torch.float32, device=self.device)
-            rows = G * blk.n_limbs
+            rows = value_rows(G, blk.n_limbs)
             tiles, n, _ = self.schedule(rows, rank=rank, world=world)
             self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), rows, blk.kp,
                        blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
@@ -407,27 +458,30 @@ class Engine:
     # ------------------------------------------------------------------ whole paths
     def _replicate(self, blk_or_none, n_cells, n_genes, n_bins, val_mode, group) -> BinBlock:
         """The single collective of the path: broadcast the bin block from rank 0.  The header at
-        the front of the block says whether the value rows have one or two digits per gene; only in
-        the two-digit case (counts > 2^limb_bits - 1) is the extra tail sent by a second broadcast."""
+        the front of the block says how many digits per gene the value rows have; only when there is
+        more than one (counts > 2^limb_bits - 1, or data that are not counts) is the extra tail sent
+        by a second broadcast."""
+        import torch.distributed as dist
         _, _, lay, total1 = block_layout(n_cells, n_genes, val_mode, 1)
-        _, _, _, total2 = block_layout(n_cells, n_genes, val_mode, 2)
         if blk_or_none is not None:
             buf = blk_or_none.buf
         else:
             buf = torch.empty(total1, dtype=torch.uint8, device=self.device)
         broadcast_block(buf, total1, group)
         o, _ = lay["header"]
-        hdr = buf[o:o + 32].view(torch.int64).cpu()
-        L, lb, flags = int(hdr[0]), int(hdr[1]), (int(hdr[2]), int(hdr[3]))
-        if L == 2:
+        hdr = buf[o:o + 40].view(torch.int64).cpu()
+        L, lb, flags, mode = int(hdr[0]), int(hdr[1]), (int(hdr[2]), int(hdr[3])), int(hdr[4])
+        if val_mode < 0:
+            mode = val_mode
+        if L > 1:
+            _, _, _, total_l = block_layout(n_cells, n_genes, val_mode, L)
             if blk_or_none is None:
-                big = torch.empty(total2, dtype=torch.uint8, device=self.device)
+                big = torch.empty(total_l, dtype=torch.uint8, device=self.device)
                 big[:total1].copy_(buf)
                 buf = big
-            import torch.distributed as dist
             src = dist.get_global_rank(group, 0) if group is not None else 0
-            dist.broadcast(buf[total1:total2], src=src, group=group)
-        return _views(buf, n_cells, n_genes, n_bins, val_mode, L, lb, flags)
+            dist.broadcast(buf[total1:total_l], src=src, group=group)
+        return _views(buf, n_cells, n_genes, n_bins, mode, L, lb, flags)
 
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
                     signed: bool = False, rank: int = 0, world: int = 1, group=None,
@@ -459,8 +513,10 @@ class Engine:
         onehot, B = self.expand_onehot(blk)
         return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world)
 
-    def target_from_csr(self, csr: CsrDevice, kind: int) -> torch.Tensor:
-        blk = self.discretize(csr, 10, 1 if kind == _lib.GV_MOM_JACCARD else 0)
+    def target_from_csr(self, csr: CsrDevice, kind: int, ranks: bool = False) -> torch.Tensor:
+        """Pearson / cosine / Jaccard matrix; ranks=True with GV_MOM_PEARSON is Spearman."""
+        mode = 1 if kind == _lib.GV_MOM_JACCARD else (3 if ranks else 0)
+        blk = self.discretize(csr, 10, mode)
         return self.moment_scores(blk, kind)
 
 

@@ -9,6 +9,7 @@ same argument meaning, same error behaviour, so that `GeneVectorDataset(mi_backe
     compute_mi_b200(X, gene_names, n_bins, signed)      new tier next to compute_mi_rust (:312-339)
     target_mi(X, gene_names, signed, backend, device, n_bins)     :381-411
     target_pearson / target_cosine / target_jaccard     :414-420, :452-461, :434-449
+    target_spearman                                     :423-431
     TARGETS / register_target / get_target_function     :344-376
 
 There is one backend and no fallback: backend must be "b200" (or "auto", which here can only
@@ -95,13 +96,13 @@ def target_mi(X, gene_names, signed=False, backend="b200", device="cuda", n_bins
     raise ValueError(f"Unknown MI backend: {backend}")
 
 
-def _moment_target(X, gene_names, kind, device=None):
+def _moment_target(X, gene_names, kind, device=None, ranks=False):
     import torch
     eng = get_engine(_device_of(device))
     if len(gene_names) != X.shape[1]:
         raise ValueError("gene_names must have one entry per column of X")
     csr = eng.upload_csr(X)
-    out = eng.target_from_csr(csr, kind)
+    out = eng.target_from_csr(csr, kind, ranks=ranks)
     torch.cuda.synchronize(eng.device)
     return ScoreMatrix(out.cpu().numpy(), gene_names)
 
@@ -110,6 +111,13 @@ def _moment_target(X, gene_names, kind, device=None):
 def target_pearson(X, gene_names, device=None, **kwargs):
     """Pearson correlation between all gene pairs (metrics.py:414-420)."""
     return _moment_target(X, gene_names, _lib.GV_MOM_PEARSON, device)
+
+
+@register_target("spearman")
+def target_spearman(X, gene_names, device=None, **kwargs):
+    """Spearman rank correlation between all gene pairs (metrics.py:423-431): the Pearson
+    correlation of the per-gene average ranks, computed from exact integer rank co-moments."""
+    return _moment_target(X, gene_names, _lib.GV_MOM_PEARSON, device, ranks=True)
 
 
 @register_target("jaccard")
@@ -127,6 +135,6 @@ def target_cosine(X, gene_names, device=None, **kwargs):
 def install_into_reference(ref_metrics_module):
     """Plug the B200 tier into an imported `genevector.metrics`: overrides the
     registry entries through the reference's own register_target hook."""
-    for name in ("mi", "pearson", "cosine", "jaccard"):
+    for name in ("mi", "pearson", "spearman", "cosine", "jaccard"):
         ref_metrics_module.register_target(name)(TARGETS[name])
     return ref_metrics_module

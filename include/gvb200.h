@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GV_ABI_VERSION 2
+#define GV_ABI_VERSION 3
 #define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
 #define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
 #define GV_QTABLE_DIM 16  /* q_table_host is [16][16] float64 */
@@ -55,6 +55,11 @@ typedef enum gv_disc_path { GV_PATH_AUTO = 0, GV_PATH_COUNTS = 1, GV_PATH_GENERA
  *   GV_OPERAND_FP4   4-bit E2M1 (two cells per byte); tcgen05 kind::mxf4.block_scale with unit scales,
  *                    FP32 accumulators (exact below 2^24 cells), half the operand bytes and twice the
  *                    cells per MMA; needs 10 or 5 rows per gene */
+/* What gv_discretize_csr writes into the value rows (see there). */
+typedef enum gv_value_mode {
+  GV_VAL_COUNTS = 0, GV_VAL_DETECTED = 1, GV_VAL_FIXED_POINT = 2, GV_VAL_RANKS = 3
+} gv_value_mode;
+
 typedef enum gv_operand_format { GV_OPERAND_INT8 = 0, GV_OPERAND_FP4 = 1 } gv_operand_format;
 
 /* Score kinds of gv_moment_tiles. */
@@ -83,16 +88,29 @@ int gv_device_check(void);
  *   n_bins_per_gene        : out, int32 [n_genes]  (second return value of discretize_genes)
  *   marg                   : out, int32 [n_genes][16]; [0] = #cells with x > 0, [a] = #cells in bin a
  *   edges                  : out, float64 [n_genes][16] bin edges (unused slots = DBL_MAX)
- *   gsum, gsq              : out, int64 [n_genes]  Sum x and Sum x^2 over cells (integer data)
- *   val_rows (optional)    : out, int8 [val_rows_alloc][val_pitch] K-major rows for
- *                            gv_moment_tiles: val_mode 0 = n_limbs rows per gene holding base-2^limb_bits
- *                            digits of the counts; val_mode 1 = one 0/1 detection row per gene.
+ *   gsum, gsq              : out, int64 [n_genes]  Sum x and Sum x^2 over cells of the value-row integer
+ *   val_rows (optional)    : out, int8 [val_rows_alloc][val_pitch] K-major operand of gv_moment_tiles:
+ *                            val_limbs rows per gene holding the base-2^val_limb_bits digits (least
+ *                            significant first) of one non-negative integer per cell, in 32-row blocks of
+ *                            32/val_limbs genes: row = (g / gpb)*32 + (g % gpb)*val_limbs + digit,
+ *                            gpb = 32/val_limbs; val_rows_alloc >= gv_value_rows(n_genes, val_limbs).
+ *                            The integer is, by val_mode (gv_value_mode):
+ *                              0 the count itself (integer data; exact co-moments);
+ *                              1 1 where the gene is detected (one row per gene; Jaccard);
+ *                              2 fixed point rint(x * 2^e_g), e_g per gene such that the gene's largest
+ *                                value lands just below 2^(val_limbs*val_limb_bits) (any non-negative
+ *                                float data; Pearson / cosine / the sign do not depend on e_g);
+ *                              3 doubled average rank minus (n_zero + 1) (Spearman; needs
+ *                                2*n_cells < 2^(val_limbs*val_limb_bits)).
+ *                            gsum / gsq are then the sums of that integer and of its square.
  *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen;
  *                            [1] = max ceil(value)
- *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype) bytes
+ *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype, sorted) bytes,
+ *                            sorted = 1 when val_mode is 3 (the rank rows of non-count data need a
+ *                            per-gene sort: twice the regroup scratch)
  *   path / path_used_host  : gv_disc_path to use; the one taken is written to *path_used_host (optional)
  * n_bins must be in [1, 15] (bins are stored in 4 bits). */
-size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype);
+size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype, int sorted);
 int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
                       const int64_t* row_ptr, int64_t n_cells, int n_genes, int64_t nnz, int n_bins,
                       const double* q_table_host, void* bins_packed, int64_t bins_pitch_bytes,
@@ -105,11 +123,12 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
 /* ---------------------------------------------------------------- gene entropy
  * Replaces GeneVectorDataset.get_gene_entropy (data.py:186-203), which runs before every score
  * computation (data.py:349): per gene the entropy (nats) of the counts of its unique values after
- * dropping the first.  Count data only (non-negative integers <= 255).  entropy_out float64 [n_genes];
- * workspace >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype) bytes. */
-int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx, int64_t nnz,
-                    int64_t n_cells, int n_genes, double* entropy_out, void* workspace,
-                    size_t workspace_bytes, void* stream);
+ * dropping the first.  Non-negative data: integer counts <= 255 take a value-histogram path, anything
+ * else a per-gene sort (needs row_ptr and nnz < 2^31).  entropy_out float64 [n_genes];
+ * workspace >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype, 1) bytes. */
+int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
+                    const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int n_genes,
+                    double* entropy_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- operand layout
  * rows_per_gene B for a given n_bins: 5 (n_bins<=5), 8 (<=8), 10 (<=10), 16 (<=15).
@@ -117,6 +136,8 @@ int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
 int gv_rows_per_gene(int n_bins);
 /* number of 32-row blocks / operand rows for n_genes */
 int64_t gv_onehot_rows(int n_genes, int rows_per_gene);
+/* operand rows of the value matrix for n_limbs digits per gene (32-row blocks of 32/n_limbs genes) */
+int64_t gv_value_rows(int n_genes, int n_limbs);
 /* packed 4-bit bins -> one-hot operand rows.  kp = K extent in cells.
  *   GV_OPERAND_INT8: int8 [gv_onehot_rows][kp], kp % 128 == 0
  *   GV_OPERAND_FP4 : uint8 [gv_onehot_rows][kp / 2], kp % 256 == 0 */
@@ -160,11 +181,12 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t row_bytes, const 
                  int operand_format, void* stream);
 
 /* ---------------------------------------------------------------- co-moment targets
- * val_rows from gv_discretize_csr: n_limbs INT8 rows per gene (row = gene*n_limbs + digit, base
- * 2^limb_bits digits of the count; one 0/1 row for GV_MOM_JACCARD), op_rows >= n_genes*n_limbs;
- * tiles are in operand rows.  kind GV_MOM_SIGN writes int8 `sgn` (both triangles, 0 on the
- * diagonal); the other kinds write float32 `out` like gv_mi_tiles.  The co-moments are exact
- * integers: requires n_cells * (2^limb_bits - 1)^2 < 2^32 and n_limbs in {1, 2}. */
+ * val_rows from gv_discretize_csr: n_limbs INT8 rows per gene (layout there; one 0/1 row for
+ * GV_MOM_JACCARD), op_rows >= gv_value_rows(n_genes, n_limbs); tiles are in operand rows.  kind
+ * GV_MOM_SIGN writes int8 `sgn` (both triangles, 0 on the diagonal); the other kinds write float32
+ * `out` like gv_mi_tiles.  GV_MOM_PEARSON on rank rows (val_mode 3) is the Spearman correlation
+ * (metrics.py:423-431).  The co-moments are exact integers (128-bit covariance arithmetic): requires
+ * n_cells * (2^limb_bits - 1)^2 < 2^32, n_limbs in 1..4 and n_cells * 4^(n_limbs*limb_bits) < 2^63. */
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
                     int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,

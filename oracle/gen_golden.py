@@ -4,7 +4,7 @@ Run in the build container only (needs /root/reference):  python oracle/gen_gold
 It imports the reference's genevector/metrics.py with the package __init__ bypassed (the
 __init__ pulls matplotlib/scanpy, absent here), runs the reference's own functions
 (discretize_genes, compute_mi_vectorized, _mi_from_joint, _compute_all_mi_numba, target_pearson,
-target_cosine, target_jaccard) on seeded inputs and stores inputs + outputs.  It also checks the
+target_spearman, target_cosine, target_jaccard) on seeded inputs and stores inputs + outputs.  It also checks the
 oracle (oracle/oracle.py, gv_oracle.c) against those outputs before writing, so a golden file is
 only ever produced by a run in which oracle == reference.
 """
@@ -147,6 +147,16 @@ def make_case(refm, name, X, n_bins, with_targets=True, with_numba=True):
         out["pearson"] = dict_to_matrix(refm.target_pearson(X, genes), genes)
         out["cosine"] = dict_to_matrix(refm.target_cosine(X, genes), genes)
         out["jaccard"] = dict_to_matrix(refm.target_jaccard(X, genes), genes)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out["spearman"] = dict_to_matrix(refm.target_spearman(X, genes), genes)
+        assert np.allclose(orc.round5_dict_matrix(orc.spearman_np(X)), out["spearman"], atol=1e-12, equal_nan=True)
+        # the integer rank rows reproduce spearmanr exactly (up to the float64 quotient)
+        sp_int = orc.int_pearson_exact(orc.rank_rows_np(X))
+        ref_sp = orc.spearman_np(X)
+        ok = ~np.isnan(ref_sp)
+        assert np.abs(sp_int[ok] - ref_sp[ok]).max() < 1e-12 and np.array_equal(np.isnan(sp_int), np.isnan(ref_sp)), name
         assert np.allclose(orc.round5_dict_matrix(orc.pearson_np(X)), out["pearson"], atol=1e-12, equal_nan=True)
         assert np.allclose(orc.round5_dict_matrix(orc.cosine_np(X)), out["cosine"], atol=1e-12)
         assert np.allclose(orc.round5_dict_matrix(orc.jaccard_np(X)), out["jaccard"], atol=1e-12)
@@ -187,12 +197,12 @@ def main():
     Xc = synth_counts(300, 40, seed=3).toarray().astype(np.float64)
     tot = Xc.sum(axis=1, keepdims=True) + 1.0
     Xl = np.log1p(Xc / tot * 1e4)
-    make_case(refm, "lognorm_f64_300x40_b10", Xl, 10, with_targets=False)
+    make_case(refm, "lognorm_f64_300x40_b10", Xl, 10)
     # 5. float32 log-normalised (float32 subtraction inside the lerp)
-    make_case(refm, "lognorm_f32_300x40_b7", Xl.astype(np.float32), 7, with_targets=False)
+    make_case(refm, "lognorm_f32_300x40_b7", Xl.astype(np.float32), 7)
     # 6. wider bins
     X = synth_counts(400, 30, seed=5).toarray()
-    make_case(refm, "synth_counts_400x30_b15", X * 3.0, 15, with_targets=False)
+    make_case(refm, "synth_counts_400x30_b15", X * 3.0, 15)
 
 
 if __name__ == "__main__":

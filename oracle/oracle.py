@@ -250,6 +250,81 @@ def pearson_np(X):
         return np.corrcoef(_dense(X).T)
 
 
+def spearman_np(X):
+    """target_spearman (metrics.py:423-431) without the dict: scipy.stats.spearmanr(X_dense)."""
+    from scipy.stats import spearmanr
+    with np.errstate(invalid="ignore", divide="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            corr, _ = spearmanr(_dense(X))
+    if np.ndim(corr) == 0:
+        corr = np.array([[1.0, corr], [corr, 1.0]])
+    return np.asarray(corr)
+
+
+def rank_rows_np(X):
+    """What the B200 path contracts for Spearman (checker for the value rows, not reference code):
+    per gene, 2 * average rank - (n_zero + 1) as integers [n_genes][n_cells]; zero cells map to 0."""
+    from scipy.stats import rankdata
+    Xd = _dense(X)
+    n_cells = Xd.shape[0]
+    out = np.zeros(Xd.T.shape, dtype=np.int64)
+    for g in range(Xd.shape[1]):
+        col = Xd[:, g]
+        n_zero = int((col <= 0).sum())
+        r2 = np.rint(2 * rankdata(col, method="average")).astype(np.int64) - (n_zero + 1)
+        out[g] = np.where(col > 0, r2, 0)
+    return out
+
+
+def fixed_point_rows_np(X, total_bits):
+    """What the B200 path contracts for Pearson / cosine / the sign of non-count data (checker for
+    the value rows): per gene rint(x * 2^e), e = total_bits - exponent(max) with max = f * 2^exponent,
+    f in [0.5, 1); capped at 2^total_bits - 1.  [n_genes][n_cells] int64."""
+    Xd = _dense(X).astype(np.float64)
+    out = np.zeros(Xd.T.shape, dtype=np.int64)
+    for g in range(Xd.shape[1]):
+        col = np.where(Xd[:, g] > 0, Xd[:, g], 0.0)
+        mx = col.max()
+        if mx <= 0:
+            continue
+        _, ex = np.frexp(mx)
+        out[g] = np.minimum(np.rint(np.ldexp(col, int(total_bits - ex))).astype(np.int64),
+                            (1 << total_bits) - 1)
+    return out
+
+
+def int_moment_matrices(V):
+    """Exact integer co-moment statistics of an integer matrix V [n_genes][n_cells] (Python ints):
+    returns (cov, var) with cov[i,j] = n*Sum(v_i v_j) - Sum(v_i) Sum(v_j) as object arrays."""
+    V = np.asarray(V).astype(object)
+    n = V.shape[1]
+    s = V.sum(axis=1)
+    cov = n * (V @ V.T) - np.outer(s, s)
+    return cov, np.diag(cov).copy()
+
+
+def int_sign_exact(V):
+    """np.sign of the exact integer covariance, 0 where either variance is 0, zero diagonal."""
+    cov, var = int_moment_matrices(V)
+    G = cov.shape[0]
+    sg = np.zeros((G, G), dtype=np.int8)
+    for i in range(G):
+        for j in range(G):
+            if i != j and var[i] != 0 and var[j] != 0:
+                sg[i, j] = (cov[i, j] > 0) - (cov[i, j] < 0)
+    return sg
+
+
+def int_pearson_exact(V):
+    """Pearson correlation from the exact integer moments (float64 quotient), NaN where a variance is 0."""
+    cov, var = int_moment_matrices(V)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c = cov.astype(np.float64) / np.sqrt(np.outer(var.astype(np.float64), var.astype(np.float64)))
+    return np.clip(c, -1.0, 1.0)
+
+
 def cosine_np(X):
     """target_cosine (metrics.py:452-461): sklearn cosine_similarity(X.T), diagonal zeroed."""
     from sklearn.metrics.pairwise import cosine_similarity

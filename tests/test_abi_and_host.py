@@ -104,7 +104,12 @@ def test_block_layout_and_limbs():
     # a two-digit block is the one-digit block plus a tail (what the second broadcast sends)
     _, _, lay2, total2 = block_layout(5000, 2000, 0, 2)
     assert all(lay2[k] == lay[k] for k in lay if k != "val")
-    assert lay2["val"][0] == lay["val"][0] and lay2["val"][1] == 2 * lay["val"][1] and total2 > total
+    assert lay2["val"][0] == lay["val"][0] and total2 > total
+    # value rows: 32-row blocks of 32 // n_limbs genes (three digits leave two zero rows per block)
+    from genevector_b200.engine import value_rows, max_limbs_for
+    assert [value_rows(2000, L) for L in (1, 2, 3, 4)] == [2016, 4000, 6400, 8000]
+    assert lay["val"][1] == 2016 * kp and lay2["val"][1] == 4000 * kp
+    assert max_limbs_for(200000, 7) == 3 and max_limbs_for(5000, 7) == 3 and max_limbs_for(100, 7) == 4
     assert limb_bits_for(200000) == 7 and limb_bits_for(266287) == 7 and limb_bits_for(300000) == 6
     q = quantile_table()
     assert np.array_equal(q[10, :9], np.linspace(0, 100, 11)[1:-1] / 100)

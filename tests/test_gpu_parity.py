@@ -201,7 +201,7 @@ def test_mi_seeded_vs_oracle(engine, n_cells, n_genes, n_bins, seed):
         Xd = np.asarray(X.todense())
         assert np.array_equal(blk.gsum.cpu().numpy(), Xd.sum(axis=0).astype(np.int64))
         assert np.array_equal(blk.gsq.cpu().numpy(), (Xd.astype(np.int64) ** 2).sum(axis=0))
-        assert np.array_equal(blk.val_rows.cpu().numpy()[:, :n_cells], Xd.T.astype(np.int8))
+        assert np.array_equal(blk.val_rows.cpu().numpy()[:n_genes, :n_cells], Xd.T.astype(np.int8))
     err = np.abs(out.astype(np.float64) - want)
     assert err.max() <= MI_TOL, f"max err {err.max():.3e}"
 
@@ -330,20 +330,22 @@ def test_count_path_falls_back_and_refuses(engine):
         engine.discretize(csr, 10, path=_lib.GV_PATH_COUNTS)
     # signed MI on such data takes two 7-bit digits per gene (counts up to 16383)
     blk2 = engine.discretize(csr, 10, val_mode=0)
-    assert blk2.n_limbs == 2 and blk2.val_rows.shape[0] == 40
+    assert blk2.n_limbs == 2 and blk2.val_rows.shape[0] == 64
     Xd = np.asarray(X.todense()).astype(np.int64)
     vr = blk2.val_rows.cpu().numpy()[:, :300].astype(np.int64)
-    assert np.array_equal(vr[0::2] + (vr[1::2] << blk2.limb_bits), Xd.T)
+    assert np.array_equal(vr[0:40:2] + (vr[1:40:2] << blk2.limb_bits), Xd.T)
+    assert np.array_equal(blk2.gene_values(), Xd.T)
     want, _ = orc.mi_pairs_c(xd, nb, corr=orc.sign_int_c(X).astype(np.float64), sign_mode=1)
     out = engine.mi_from_csr(csr, 300, 20, signed=True).cpu().numpy()
     assert np.abs(out - want).max() <= MI_TOL
-    # counts beyond two digits are refused loudly
+    # larger counts take a third digit (still exact); negative values are refused loudly
     Xbig = X.copy(); Xbig.data[0] = 20000.0
-    with pytest.raises(GvError, match="limb range"):
-        engine.mi_from_csr(engine.upload_csr(Xbig), 300, 20, signed=True)
-    with pytest.raises(GvError, match="non-negative integer"):
-        Xf = X.copy(); Xf.data[0] = 2.5
-        engine.mi_from_csr(engine.upload_csr(Xf), 300, 20, signed=True)
+    blk3 = engine.discretize(engine.upload_csr(Xbig), 10, val_mode=0)
+    assert blk3.n_limbs == 3 and blk3.val_mode == 0
+    assert np.array_equal(blk3.gene_values(), np.asarray(Xbig.todense()).astype(np.int64).T)
+    with pytest.raises(GvError, match="non-negative"):
+        Xn = X.copy(); Xn.data[0] = -2.0
+        engine.mi_from_csr(engine.upload_csr(Xn), 300, 20, signed=True)
 
 
 @pytest.mark.parametrize("n_cells,n_genes,seed", [(900, 300, 31), (1300, 150, 32)])
@@ -380,9 +382,15 @@ def test_gene_entropy_matches_reference(engine):
     assert np.array_equal(want, z["gene_entropy"])          # the reference's own output
     assert list(got) == genes
     assert np.abs(np.array([got[g] for g in genes]) - want).max() < 1e-12
-    zl = load_golden("lognorm_f32_300x40_b7")
-    with pytest.raises(GvError, match="integer counts"):
-        get_gene_entropy(zl["X"], [f"G{i}" for i in range(40)])
+    # data that are not small counts go through the per-gene sort
+    for case in ("lognorm_f32_300x40_b7", "lognorm_f64_300x40_b10", "synth_counts_400x30_b15"):
+        zl = load_golden(case)
+        gl = [f"G{i}" for i in range(zl["X"].shape[1])]
+        e = get_gene_entropy(zl["X"], gl)
+        assert np.abs(np.array([e[g] for g in gl]) - zl["gene_entropy"]).max() < 1e-12, case
+    Xn = zl["X"].copy(); Xn.data[3] = -1.0
+    with pytest.raises(GvError, match="non-negative"):
+        get_gene_entropy(Xn, gl)
 
 
 @pytest.mark.parametrize("cg", [1, 2])
