@@ -40,7 +40,7 @@ SIGNATURES = {
     "gv_abi_version": (_i32, []),
     "gv_last_error": (C.c_char_p, []),
     "gv_device_check": (_i32, []),
-    "gv_discretize_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "gv_discretize_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _i32, _vp, _vp]),

@@ -67,8 +67,8 @@ int gv_abi_version(void) { return GV_ABI_VERSION; }
 const char* gv_last_error(void) { return g_last_error.c_str(); }
 int gv_device_check(void) { return check_device(); }
 
-size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype, int sorted) {
-  return discretize_workspace_bytes(nnz < 0 ? 0 : nnz, n_genes < 0 ? 0 : n_genes, value_dtype, sorted);
+size_t gv_discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int n_genes, int value_dtype, int sorted) {
+  return discretize_workspace_bytes(nnz < 0 ? 0 : nnz, n_cells, n_genes < 0 ? 0 : n_genes, value_dtype, sorted);
 }
 
 int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,

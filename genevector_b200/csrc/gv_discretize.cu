@@ -541,16 +541,23 @@ __global__ void k_expand_onehot_fp4(const uint32_t* __restrict__ bins_packed, in
 
 // ================================================================ count-data fast path
 // For non-negative integer data with values <= 255 (scRNA-seq counts, the documented input) the
-// order statistics follow from a per-gene VALUE histogram, so the gene-major regroup is not
-// needed at all:
-//   k_hist2d      one pass over the CSR values: hist[gene][value]++ (20 MB at 20k genes: the
-//                 atomics resolve in L2) + the data flags
-//   k_gene_lut    one warp per gene: n_unique, k, the 2(k-1) order statistics from the cumulative
-//                 histogram, numpy-exact edges, a value -> bin lookup table, marginals, Sum x, Sum x^2
-//   k_assign_csr  second pass over the CSR in cell order: bin = lut[gene][value] -> packed nibble
-//                 (RED.OR; the 64 cells of a 32-byte sector are written while it sits in L2) and the
-//                 optional INT8 value rows
+// order statistics follow from a per-gene VALUE histogram, and the cell-major -> gene-major regroup
+// can be a dense byte transposition staged through shared memory, with no global atomics at all:
+//   k_transpose_counts  CSR (cell-major, sorted columns) -> dense uint8 rows raw[gene][cell]: a CTA
+//                       owns 128 consecutive cells and walks the genes in ranges of TP_GR; entries
+//                       are scattered into a shared-memory tile [gene][cell] and the tile leaves as
+//                       full 128-byte lines, so every byte of `raw` is written exactly once (zeros
+//                       included: no memset) and the CSR is read once, coalesced
+//                       the per-gene value histogram is accumulated on the way in packed byte
+//                       counters in shared memory (one flush of a few atomics per gene and cell block)
+//   k_rows_to_bins      one CTA per gene: value histogram -> n_unique, k, the 2(k-1) order
+//                       statistics, numpy-exact edges, a value -> bin lookup table, marginals, Sum x,
+//                       Sum x^2 (gene_lut_warp); then one sweep of the gene's dense row: packed 4-bit
+//                       bins and, when they differ from `raw`, the value rows (count digits /
+//                       detection / rank digits)
+// For signed MI with counts <= 127 `raw` IS the INT8 value-row operand of the sign pass.
 // Results are bit-identical to the general path (tests compare both with the oracle).
+// k_hist2d (scatter histogram with global atomics) remains for the gene-entropy entry point.
 constexpr int VH = 256;   // histogram slots per gene: integer values 1..255
 
 template <typename T>
@@ -583,191 +590,334 @@ __global__ void k_hist2d(const T* __restrict__ values, const int32_t* __restrict
   }
 }
 
-// One warp per gene.  Lane l owns the 8 histogram slots v = 8l .. 8l+7.
+// One warp per gene.  Lane l owns the 8 histogram slots v = 8l .. 8l+7 (c[i] = #cells with value
+// 8l+i; c[0] of lane 0 is ignored).  Writes the value -> bin table (and value -> doubled rank when
+// rank_lut != nullptr) and the per-gene outputs of discretize_genes.
 template <typename T>
-__global__ void k_gene_lut(const uint32_t* __restrict__ hist, int G, int n_bins,
-                           const double* __restrict__ q_table, uint8_t* __restrict__ lut,
-                           int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
-                           double* __restrict__ edges_out, int64_t* __restrict__ gsum,
-                           int64_t* __restrict__ gsq, uint32_t* __restrict__ rank_lut,
-                           int64_t n_cells) {
+__device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bins,
+                              const double* __restrict__ q_table, int64_t n_cells,
+                              uint8_t* lut, uint32_t* rank_lut,
+                              int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
+                              double* __restrict__ edges_out, int64_t* __restrict__ gsum,
+                              int64_t* __restrict__ gsq) {
   using K = ValKey<T>;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
-    uint32_t c[8];
-    const uint4* hp = reinterpret_cast<const uint4*>(hist + int64_t(g) * VH + lane * 8);
-    const uint4 h0 = hp[0], h1 = hp[1];
-    c[0] = h0.x; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w; c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
-    uint32_t tot = 0, nun = 0;
-    long long s1 = 0, s2 = 0;
+  uint32_t tot = 0, nun = 0;
+  long long s1 = 0, s2 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    tot += c[i]; nun += c[i] ? 1u : 0u;
+    const long long v = lane * 8 + i;
+    s1 += v * (long long)c[i]; s2 += v * v * (long long)c[i];
+  }
+  uint32_t inc = tot;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += y;
+  }
+  const uint32_t lane_excl = inc - tot;
+  const int64_t m = __shfl_sync(0xffffffffu, inc, 31);
+  for (int d = 16; d >= 1; d >>= 1) nun += __shfl_xor_sync(0xffffffffu, nun, d);
+  if (rank_lut != nullptr) {
+    // val_mode 3: value -> n_zero + #{values < v} + #{values <= v}; the sums are those of the ranks
+    uint32_t run = lane_excl;
+    s1 = 0; s2 = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      tot += c[i]; nun += c[i] ? 1u : 0u;
-      const long long v = lane * 8 + i;
-      s1 += v * (long long)c[i]; s2 += v * v * (long long)c[i];
+      const long long r = (n_cells - m) + 2ll * run + c[i];
+      rank_lut[lane * 8 + i] = c[i] ? uint32_t(r) : 0u;
+      s1 += c[i] ? r * (long long)c[i] : 0ll;
+      s2 += c[i] ? r * r * (long long)c[i] : 0ll;
+      run += c[i];
     }
-    uint32_t inc = tot;
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += y;
-    }
-    const uint32_t lane_excl = inc - tot;
-    const int64_t m = __shfl_sync(0xffffffffu, inc, 31);
-    for (int d = 16; d >= 1; d >>= 1) {
-      nun += __shfl_xor_sync(0xffffffffu, nun, d);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-    }
-    if (rank_lut != nullptr) {
-      // val_mode 3: value -> n_zero + #{values < v} + #{values <= v}; the sums are those of the ranks
-      uint32_t rk[8];
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane == 0) { gsum[g] = s1; gsq[g] = s2; }
+  double edge[14];
+#pragma unroll
+  for (int t = 0; t < 14; ++t) edge[t] = DBL_MAX;
+  int k = 0, n_edges = 0;
+  if (m > 0) {
+    k = int(nun) < n_bins ? int(nun) : n_bins;          // metrics.py:59
+    n_edges = k > 1 ? k - 1 : 0;
+    // value (as the integer it is) holding sorted rank r: the slot whose cumulative range has r
+    auto value_at = [&](int64_t r) -> int {
+      int found = 0;
       uint32_t run = lane_excl;
-      s1 = 0; s2 = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const long long r = (n_cells - m) + 2ll * run + c[i];
-        rk[i] = c[i] ? uint32_t(r) : 0u;
-        s1 += c[i] ? r * (long long)c[i] : 0ll;
-        s2 += c[i] ? r * r * (long long)c[i] : 0ll;
+        if (r >= int64_t(run) && r < int64_t(run) + int64_t(c[i])) found = lane * 8 + i;
         run += c[i];
       }
-      uint4* rp = reinterpret_cast<uint4*>(rank_lut + int64_t(g) * VH + lane * 8);
-      rp[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
-      rp[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
       for (int d = 16; d >= 1; d >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+        const int o = __shfl_xor_sync(0xffffffffu, found, d);
+        found = o > found ? o : found;
+      }
+      return found;
+    };
+#pragma unroll
+    for (int t = 0; t < 14; ++t) {
+      if (t < n_edges) {                                 // warp-uniform
+        const double q = q_table[k * 16 + t];
+        const double vi = __dmul_rn(double(m - 1), q);
+        int64_t ra, rb; double gam;
+        if (vi >= double(m - 1)) { ra = rb = m - 1; gam = __dadd_rn(vi, 1.0); }
+        else { const double fl = floor(vi); ra = int64_t(fl); rb = ra + 1; gam = __dsub_rn(vi, fl); }
+        const T a = T(value_at(ra));
+        const T b = T(value_at(rb));
+        const T d = K::sub(b, a);
+        edge[t] = (gam >= 0.5) ? __dsub_rn(double(b), __dmul_rn(double(d), __dsub_rn(1.0, gam)))
+                               : __dadd_rn(double(a), __dmul_rn(double(d), gam));
       }
     }
-    if (lane == 0) { gsum[g] = s1; gsq[g] = s2; }
-    double edge[14];
+  }
+  // lookup table + marginals
+  uint32_t mg[16];
 #pragma unroll
-    for (int t = 0; t < 14; ++t) edge[t] = DBL_MAX;
-    int k = 0, n_edges = 0;
-    if (m > 0) {
-      k = int(nun) < n_bins ? int(nun) : n_bins;          // metrics.py:59
-      n_edges = k > 1 ? k - 1 : 0;
-      // value (as the integer it is) holding sorted rank r: the slot whose cumulative range has r
-      auto value_at = [&](int64_t r) -> int {
-        int found = 0;
-        uint32_t run = lane_excl;
+  for (int a = 0; a < 16; ++a) mg[a] = 0;
+  uint32_t packed[2] = {0, 0};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (r >= int64_t(run) && r < int64_t(run) + int64_t(c[i])) found = lane * 8 + i;
-          run += c[i];
-        }
-        for (int d = 16; d >= 1; d >>= 1) {
-          const int o = __shfl_xor_sync(0xffffffffu, found, d);
-          found = o > found ? o : found;
-        }
-        return found;
-      };
+  for (int i = 0; i < 8; ++i) {
+    const double vd = double(lane * 8 + i);
+    int bin = 1;
 #pragma unroll
-      for (int t = 0; t < 14; ++t) {
-        if (t < n_edges) {                                 // warp-uniform
-          const double q = q_table[k * 16 + t];
-          const double vi = __dmul_rn(double(m - 1), q);
-          int64_t ra, rb; double gam;
-          if (vi >= double(m - 1)) { ra = rb = m - 1; gam = __dadd_rn(vi, 1.0); }
-          else { const double fl = floor(vi); ra = int64_t(fl); rb = ra + 1; gam = __dsub_rn(vi, fl); }
-          const T a = T(value_at(ra));
-          const T b = T(value_at(rb));
-          const T d = K::sub(b, a);
-          edge[t] = (gam >= 0.5) ? __dsub_rn(double(b), __dmul_rn(double(d), __dsub_rn(1.0, gam)))
-                                 : __dadd_rn(double(a), __dmul_rn(double(d), gam));
-        }
-      }
-    }
-    // lookup table + marginals
-    uint32_t mg[16];
+    for (int t = 0; t < 14; ++t) bin += (t < n_edges && edge[t] <= vd) ? 1 : 0;
+    if (lane * 8 + i == 0) bin = 0;
+    packed[i >> 2] |= uint32_t(bin) << ((i & 3) * 8);
 #pragma unroll
-    for (int a = 0; a < 16; ++a) mg[a] = 0;
-    uint32_t packed[2] = {0, 0};
+    for (int a = 1; a < 16; ++a) mg[a] += (a == bin) ? c[i] : 0u;
+  }
+  *reinterpret_cast<uint2*>(lut + lane * 8) = make_uint2(packed[0], packed[1]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double vd = double(lane * 8 + i);
-      int bin = 1;
+  for (int a = 1; a < 16; ++a)
+    for (int d = 16; d >= 1; d >>= 1) mg[a] += __shfl_xor_sync(0xffffffffu, mg[a], d);
+  if (lane == 0) {
+    n_bins_per_gene[g] = m == 0 ? 1 : (k <= 1 ? 2 : k + 1);   // metrics.py:55-57,62,67
+    marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
 #pragma unroll
-      for (int t = 0; t < 14; ++t) bin += (t < n_edges && edge[t] <= vd) ? 1 : 0;
-      if (lane * 8 + i == 0) bin = 0;
-      packed[i >> 2] |= uint32_t(bin) << ((i & 3) * 8);
+    for (int a = 1; a < 16; ++a) marg[int64_t(g) * MARG_STRIDE_ + a] = int32_t(mg[a]);
 #pragma unroll
-      for (int a = 1; a < 16; ++a) mg[a] += (a == bin) ? c[i] : 0u;
-    }
-    *reinterpret_cast<uint2*>(lut + int64_t(g) * VH + lane * 8) = make_uint2(packed[0], packed[1]);
-#pragma unroll
-    for (int a = 1; a < 16; ++a)
-      for (int d = 16; d >= 1; d >>= 1) mg[a] += __shfl_xor_sync(0xffffffffu, mg[a], d);
-    if (lane == 0) {
-      n_bins_per_gene[g] = m == 0 ? 1 : (k <= 1 ? 2 : k + 1);   // metrics.py:55-57,62,67
-      marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
-#pragma unroll
-      for (int a = 1; a < 16; ++a) marg[int64_t(g) * MARG_STRIDE_ + a] = int32_t(mg[a]);
-#pragma unroll
-      for (int t = 0; t < 14; ++t) edges_out[int64_t(g) * 16 + t] = edge[t];
-      edges_out[int64_t(g) * 16 + 14] = DBL_MAX;
-      edges_out[int64_t(g) * 16 + 15] = DBL_MAX;
-    }
+    for (int t = 0; t < 14; ++t) edges_out[int64_t(g) * 16 + t] = edge[t];
+    edges_out[int64_t(g) * 16 + 14] = DBL_MAX;
+    edges_out[int64_t(g) * 16 + 15] = DBL_MAX;
   }
 }
 
-// The CSR entries are walked in storage order: CTAs draw consecutive chunks of ASSIGN_CHUNK entries
-// from an atomic ticket counter, so at any time the whole grid works on one compact window of a
-// few hundred consecutive cells.  The packed-bin words and value-row sectors of those cells (a few
-// MB over all genes) are then completed while they sit in L2 and reach DRAM once.  (A plain
-// grid-stride loop lets warps drift apart until that window no longer fits L2:
-// profiles/r01_ncu_assign_c4_gridstride.txt, 36 GB of DRAM reads for a 3.2 GB input.)
-// Each warp finds the row of its first entry with one binary search over row_ptr and walks row
-// boundaries from there.
-constexpr int ASSIGN_THREADS = 256;
-constexpr int ASSIGN_PER_THREAD = 4;
-constexpr int ASSIGN_CHUNK = ASSIGN_THREADS * ASSIGN_PER_THREAD;
+// ---------------------------------------------------------------- k_transpose_counts
+// flags[0] |= 1 negative value, |= 2 fractional value, |= 4 column indices of a row not ascending
+// (the walk below needs canonical CSR; the caller then takes the general path);
+// flags[1] = max over ceil(values).
+constexpr int TP_CB = 128;                 // cells per CTA block = bytes per output line
+constexpr int TP_STRIDE = TP_CB + 4;       // tile row stride: 33 words, conflict-free both ways
+constexpr int TP_GR = 704;                 // genes per range
+constexpr int TP_THREADS = 512;
+constexpr int TP_WARPS = TP_THREADS / 32;
+constexpr int TP_ROWS_PER_WARP = TP_CB / TP_WARPS;   // 8, taken 4 at a time
+constexpr int TP_HV = 16;                  // values below this are counted in shared memory
+constexpr size_t TP_TILE_BYTES = size_t(TP_GR) * TP_STRIDE;
+constexpr size_t TP_HIST_BYTES = size_t(TP_GR) * TP_HV;   // one byte per (gene, value): <= 128 cells
+constexpr size_t TP_SMEM = TP_TILE_BYTES + TP_HIST_BYTES + 2 * TP_CB * sizeof(int64_t);
 
 template <typename T>
-__global__ void __launch_bounds__(ASSIGN_THREADS)
-k_assign_csr(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
-             const int64_t* __restrict__ row_ptr, int64_t n_cells, int64_t nnz,
-             const uint8_t* __restrict__ lut, uint32_t* __restrict__ bins_packed,
-             int64_t pitch_words, int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode,
-             int limb_bits, int n_limbs, const uint32_t* __restrict__ rank_lut,
-             unsigned long long* __restrict__ ticket) {
-  __shared__ unsigned long long s_chunk;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t n_chunks = (nnz + ASSIGN_CHUNK - 1) / ASSIGN_CHUNK;
-  while (true) {
-    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1ull);
-    __syncthreads();
-    const int64_t chunk = int64_t(s_chunk);
-    __syncthreads();
-    if (chunk >= n_chunks) break;
-    // warp w takes ASSIGN_PER_THREAD runs of 32 consecutive entries
-    const int64_t wbase = chunk * ASSIGN_CHUNK + int64_t(warp) * (32 * ASSIGN_PER_THREAD);
-    if (wbase >= nnz) continue;
-    int64_t lo = 0, hi = n_cells - 1;      // largest r with row_ptr[r] <= wbase (warp-uniform)
-    while (lo < hi) {
-      const int64_t mid = (lo + hi + 1) >> 1;
-      if (row_ptr[mid] <= wbase) lo = mid; else hi = mid - 1;
+__global__ void __launch_bounds__(TP_THREADS, 2)
+k_transpose_counts(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+                   const int64_t* __restrict__ row_ptr, int64_t n_cells, int G,
+                   uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t n_blocks,
+                   uint32_t* __restrict__ ghist, unsigned long long* __restrict__ flags) {
+  // ghist [G][256]: per-gene value histogram, accumulated on the way (small values in packed byte
+  // counters in shared memory, flushed once per (cell block, gene range); the rest directly)
+  extern __shared__ __align__(16) uint8_t tp_smem[];
+  uint8_t* tile = tp_smem;
+  uint32_t* hcnt = reinterpret_cast<uint32_t*>(tp_smem + TP_TILE_BYTES);
+  int64_t* cur_s = reinterpret_cast<int64_t*>(tp_smem + TP_TILE_BYTES + TP_HIST_BYTES);
+  int64_t* end_s = cur_s + TP_CB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned f = 0;
+  unsigned long long vmax = 0;
+  for (int i = tid; i < int((TP_TILE_BYTES + TP_HIST_BYTES) / 4); i += TP_THREADS)
+    reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+
+  for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const int64_t c0 = blk * TP_CB;
+    if (tid < TP_CB) {
+      const int64_t r = c0 + tid;
+      cur_s[tid] = r < n_cells ? row_ptr[r] : 0;
+      end_s[tid] = r < n_cells ? row_ptr[r + 1] : 0;
     }
-    int64_t r = lo;
+    __syncthreads();
+    for (int g0 = 0; g0 < G; g0 += TP_GR) {
+      const int g1 = g0 + TP_GR < G ? g0 + TP_GR : G;
+      // ---- scatter this range's entries of my rows into the tile (4 rows in flight per warp)
+#pragma unroll 1
+      for (int rg = 0; rg < TP_ROWS_PER_WARP; rg += 4) {
+        int64_t cur[4], end[4];
 #pragma unroll
-    for (int u = 0; u < ASSIGN_PER_THREAD; ++u) {
-      const int64_t e = wbase + u * 32 + lane;
-      if (e >= nnz) break;
-      while (e >= row_ptr[r + 1]) ++r;        // also skips empty rows
-      const T v = values[e];
-      if (v > T(0)) {
-        const int g = col_idx[e];
-        const unsigned xi = unsigned(v);
-        const uint32_t bin = lut[int64_t(g) * VH + xi];
-        atomicOr(&bins_packed[int64_t(g) * pitch_words + (r >> 3)], bin << (uint32_t(r & 7) * 4));
-        if (val_rows != nullptr) {
-          if (val_mode == 1) val_rows[int64_t(g) * val_pitch + r] = 1;
-          else if (val_mode == 3) write_digits(val_rows, val_pitch, g, r, rank_lut[int64_t(g) * VH + xi], n_limbs, limb_bits);
-          else write_digits(val_rows, val_pitch, g, r, xi, n_limbs, limb_bits);
+        for (int k = 0; k < 4; ++k) {
+          const int rl = warp + (rg + k) * TP_WARPS;
+          cur[k] = cur_s[rl]; end[k] = end_s[rl];
+        }
+        bool more = true;
+        while (more) {
+          int32_t cc[4]; T vv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int64_t e = cur[k] + lane;
+            const bool ok = e < end[k];
+            cc[k] = ok ? col_idx[e] : 0x7fffffff;
+            vv[k] = ok ? values[e] : T(0);
+          }
+          more = false;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool in = cc[k] < g1;
+            const int32_t prev = __shfl_up_sync(0xffffffffu, cc[k], 1);
+            if (in) {
+              if (cc[k] < g0 || (lane > 0 && cc[k] <= prev)) f |= 4u;
+              const T v = vv[k];
+              if (v > T(0)) {
+                const T cl = ceil(v);
+                if (cl != v) f |= 2u;
+                const unsigned long long ci = cl < T(1.8e19) ? (unsigned long long)cl : ~0ull;
+                vmax = ci > vmax ? ci : vmax;
+                if (cc[k] >= g0) {
+                  const int gl = cc[k] - g0;
+                  const unsigned u = unsigned(ci < 255ull ? ci : 255ull);
+                  tile[gl * TP_STRIDE + warp + (rg + k) * TP_WARPS] = uint8_t(u);
+                  if (u < unsigned(TP_HV)) atomicAdd(&hcnt[(gl * TP_HV + int(u)) >> 2], 1u << (8 * (u & 3u)));
+                  else atomicAdd(&ghist[int64_t(cc[k]) * VH + u], 1u);
+                }
+              } else if (v < T(0)) {
+                f |= 1u;
+              }
+            }
+            const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+            cur[k] += cnt;
+            more |= (cnt == 32);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cur_s[warp + (rg + k) * TP_WARPS] = cur[k];
+        }
+      }
+      __syncthreads();
+      // ---- the tile leaves as full 128-byte lines and is zeroed for the next range
+      for (int gl = warp; gl < g1 - g0; gl += TP_WARPS) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(tile + gl * TP_STRIDE) + lane;
+        const uint32_t x = *w;
+        *w = 0u;
+        *reinterpret_cast<uint32_t*>(raw + int64_t(g0 + gl) * raw_pitch + c0 + 4 * lane) = x;
+      }
+      // ---- flush the packed byte counters of this (cell block, gene range)
+      for (int gl = tid; gl < g1 - g0; gl += TP_THREADS) {
+        uint4* hp = reinterpret_cast<uint4*>(hcnt + gl * (TP_HV / 4));
+        const uint4 h = *hp;
+        if ((h.x | h.y | h.z | h.w) != 0u) {
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (hw[q] == 0u) continue;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t cnt = (hw[q] >> (8 * b)) & 0xffu;
+              if (cnt) atomicAdd(&ghist[int64_t(g0 + gl) * VH + q * 4 + b], cnt);
+            }
+          }
+          *hp = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  for (int d = 16; d >= 1; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, vmax, d);
+    vmax = o > vmax ? o : vmax;
+  }
+  if (lane == 0) {
+    if (f) atomicOr(&flags[0], (unsigned long long)f);
+    if (vmax) atomicMax(&flags[1], vmax);
+  }
+}
+
+// ---------------------------------------------------------------- k_rows_to_bins
+constexpr int RB_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(RB_THREADS, 4)
+k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, int64_t n_cells, int G,
+               int n_bins, const double* __restrict__ q_table, uint32_t* __restrict__ bins_packed,
+               int64_t pitch_words, int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
+               double* __restrict__ edges_out, int64_t* __restrict__ gsum, int64_t* __restrict__ gsq,
+               int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode, int limb_bits,
+               int n_limbs, const uint32_t* __restrict__ ghist) {
+  // ghist [G][256]: the per-gene value histogram from k_transpose_counts; the row is swept once
+  __shared__ __align__(8) uint8_t lut[VH];
+  __shared__ uint32_t rlut[VH];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n16 = kp / 16;
+  const bool ranks = val_rows != nullptr && val_mode == 3;
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const uint4* row = reinterpret_cast<const uint4*>(raw + int64_t(g) * raw_pitch);
+    if (warp == 0) {
+      uint32_t c[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        c[i] = (lane * 8 + i) ? ghist[int64_t(g) * VH + lane * 8 + i] : 0u;
+      }
+      gene_lut_warp<T>(c, lane, g, n_bins, q_table, n_cells, lut, ranks ? rlut : nullptr,
+                       n_bins_per_gene, marg, edges_out, gsum, gsq);
+    }
+    __syncthreads();
+    // ---- one sweep of the row: packed bins and, when they are not `raw` itself, value rows
+    uint2* brow = reinterpret_cast<uint2*>(bins_packed + int64_t(g) * pitch_words);
+    const bool digits = val_rows != nullptr && (val_mode == 0 || val_mode == 3) &&
+                        reinterpret_cast<const uint8_t*>(val_rows) != raw;
+    const bool detect = val_rows != nullptr && val_mode == 1;
+    const int64_t vrow0 = val_rows != nullptr ? val_row0(g, val_mode == 1 ? 1 : n_limbs) : 0;
+    const uint32_t dmask = (1u << limb_bits) - 1u;
+    for (int64_t i = tid; i < n16; i += RB_THREADS) {
+      const uint4 w = row[i];
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+      uint32_t pk[2] = {0u, 0u};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t x = ws[k];
+        if (x == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          pk[k >> 1] |= uint32_t(lut[(x >> (8 * b)) & 0xffu]) << (((k & 1) * 4 + b) * 4);
+      }
+      brow[i] = make_uint2(pk[0], pk[1]);
+      if (detect) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = __vcmpne4(ws[k], 0u) & 0x01010101u;
+        *reinterpret_cast<uint4*>(val_rows + vrow0 * val_pitch + 16 * i) = make_uint4(o[0], o[1], o[2], o[3]);
+      } else if (digits) {
+        for (int l = 0; l < n_limbs; ++l) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t acc = 0u;
+            if (ws[k] != 0u) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const uint32_t v = (ws[k] >> (8 * b)) & 0xffu;
+                const uint32_t xi = val_mode == 3 ? rlut[v] : v;
+                acc |= ((xi >> (l * limb_bits)) & dmask) << (8 * b);
+              }
+            }
+            o[k] = acc;
+          }
+          *reinterpret_cast<uint4*>(val_rows + (vrow0 + l) * val_pitch + 16 * i) =
+              make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -882,49 +1032,66 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
 
   GV_CUDA_TRY(cudaMemsetAsync(flags, 0, 64, st));
   GV_CUDA_TRY(cudaMemcpyAsync(qtab, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st));
-  GV_CUDA_TRY(cudaMemsetAsync(a.bins_packed, 0, size_t(G) * a.bins_pitch_bytes, st));
-  if (val_rows != nullptr)
-    GV_CUDA_TRY(cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st));
   unsigned long long hflags[2] = {0, 0};
+  const int64_t kcells = a.bins_pitch_bytes * 2;     // cells covered by a packed-bin row
 
   // ---------------- count-data fast path (tried first unless the caller forces the general one;
   // fixed-point value rows are for data that are not counts, so they go straight to the general path)
-  if (a.path != GV_PATH_GENERAL && !(val_rows != nullptr && a.val_mode == 2)) {
-    uint32_t* hist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
-    uint8_t* lut = static_cast<uint8_t*>(take(size_t(G) * VH));
-    uint32_t* rank_lut = ranks ? static_cast<uint32_t*>(take(size_t(G) * VH * 4)) : nullptr;
+  if (a.path != GV_PATH_GENERAL && !(val_rows != nullptr && a.val_mode == 2) && kcells % TP_CB == 0 &&
+      (val_rows == nullptr || a.val_pitch == kcells)) {
+    // dense uint8 rows: the value-row operand itself when that is what the caller wants
+    const bool raw_is_val = val_rows != nullptr && a.val_mode == 0 && n_limbs == 1;
+    uint8_t* raw = raw_is_val ? reinterpret_cast<uint8_t*>(val_rows)
+                              : static_cast<uint8_t*>(take(size_t(G) * size_t(kcells)));
+    uint32_t* ghist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
     if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
-    GV_CUDA_TRY(cudaMemsetAsync(hist, 0, size_t(G) * VH * 4, st));
-    if (a.nnz > 0) {
-      k_hist2d<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, hist, flags);
-      GV_LAUNCH_CHECK();
-    }
+    GV_CUDA_TRY(cudaMemsetAsync(ghist, 0, size_t(G) * VH * 4, st));
+    auto kt = k_transpose_counts<T>;
+    GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
+    const int64_t n_blocks = kcells / TP_CB;
+    const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
+    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, G, raw,
+                                                     kcells, n_blocks, ghist, flags);
+    GV_LAUNCH_CHECK();
     GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
     GV_CUDA_TRY(cudaStreamSynchronize(st));
-    const bool eligible = (hflags[0] & 2ull) == 0 && hflags[1] < (unsigned long long)VH;
+    const bool eligible = (hflags[0] & 6ull) == 0 && hflags[1] < (unsigned long long)VH;
     if (eligible) {
       if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
       int rc = check_val_config(a, hflags);
       if (rc != GV_OK) return rc;
-      k_gene_lut<T><<<(G + 7) / 8, 256, 0, st>>>(hist, G, a.n_bins, qtab, lut, a.n_bins_per_gene, a.marg,
-                                                  a.edges, a.gsum, a.gsq, rank_lut, a.n_cells);
-      GV_LAUNCH_CHECK();
-      if (a.nnz > 0) {
-        // flags[4] is the ticket counter (zeroed with the flags block above)
-        k_assign_csr<T><<<sms * 8, ASSIGN_THREADS, 0, st>>>(
-            values, a.col_idx, a.row_ptr, a.n_cells, a.nnz, lut, static_cast<uint32_t*>(a.bins_packed),
-            int64_t(a.bins_pitch_bytes / 4), val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs,
-            rank_lut, flags + 4);
-        GV_LAUNCH_CHECK();
+      if (val_rows != nullptr) {
+        // rows no gene writes: the two spare rows of every 32-row block when a gene has three
+        // digits, and everything past the last gene
+        if (n_limbs == 3)
+          GV_CUDA_TRY(cudaMemset2DAsync(val_rows + 30 * a.val_pitch, size_t(32) * a.val_pitch, 0,
+                                        size_t(2) * a.val_pitch, size_t(a.val_rows_alloc / 32), st));
+        const int gpb = 32 / n_limbs;
+        const int64_t used = int64_t(G / gpb) * 32 + int64_t(G % gpb) * n_limbs;
+        if (a.val_rows_alloc > used)
+          GV_CUDA_TRY(cudaMemsetAsync(val_rows + used * a.val_pitch, 0,
+                                      size_t(a.val_rows_alloc - used) * a.val_pitch, st));
       }
+      k_rows_to_bins<T><<<G < sms * 8 ? G : sms * 8, RB_THREADS, 0, st>>>(
+          raw, kcells, kcells, a.n_cells, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
+          int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
+          a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, ghist);
+      GV_LAUNCH_CHECK();
       if (a.path_used) *a.path_used = GV_PATH_COUNTS;
       return GV_OK;
     }
     if (a.path == GV_PATH_COUNTS)
-      return set_error(GV_ERR_UNSUPPORTED, "count-data path requested but the values are not integers <= 255");
+      return set_error(GV_ERR_UNSUPPORTED,
+                       "count-data path requested but the values are not integers <= 255 in canonical CSR");
     off = front;   // fall through to the general path, reusing the workspace
+  } else if (a.path == GV_PATH_COUNTS) {
+    return set_error(GV_ERR_UNSUPPORTED, "count-data path needs a bins pitch of a multiple of 64 bytes "
+                                         "matching val_pitch, and count value rows");
   }
 
+  GV_CUDA_TRY(cudaMemsetAsync(a.bins_packed, 0, size_t(G) * a.bins_pitch_bytes, st));
+  if (val_rows != nullptr)
+    GV_CUDA_TRY(cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st));
   // ---------------- general path: gene-major regroup + radix select (any float data)
   uint32_t* cnt = static_cast<uint32_t*>(take(size_t(G) * 4));
   unsigned long long* cursor = static_cast<unsigned long long*>(take(size_t(G) * 8));
@@ -1089,17 +1256,21 @@ int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
-// sorted = the caller will need the per-gene sort (rank value rows, entropy of non-count data)
-size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype, int sorted) {
+// sorted = the caller will need the per-gene sort (rank value rows, entropy of non-count data).
+// Sized for packed-bin rows of the engine's pitch (n_cells rounded up to 256 cells).
+size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value_dtype, int sorted) {
   const size_t vs = value_dtype == GV_F64 ? 8 : 4;
   const size_t front = al256(64) + al256(16 * 16 * 8);
-  const size_t counts = al256(size_t(G) * VH * 4) + al256(size_t(G) * VH) +
-                        (sorted ? al256(size_t(G) * VH * 4) : 0);
+  const size_t kcells = (size_t(n_cells > 0 ? n_cells : 1) + 255) / 256 * 256;
+  const size_t counts = al256(size_t(G) * kcells) + al256(size_t(G) * VH * 4);
+  const size_t entropy = al256(size_t(G) * VH * 4);
   size_t general = al256(size_t(G) * 4) + al256(size_t(G) * 8) + al256(size_t(G + 1) * 8) +
                    al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs);
   if (sorted)
     general += al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs) + al256(segsort_temp_bytes(nnz, G, value_dtype));
-  return front + (counts > general ? counts : general) + 256;
+  size_t m = counts > general ? counts : general;
+  m = m > entropy ? m : entropy;
+  return front + m + 256;
 }
 
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,

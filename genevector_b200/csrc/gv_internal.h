@@ -30,7 +30,7 @@ struct DiscretizeArgs {
 };
 
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st);
-size_t discretize_workspace_bytes(int64_t nnz, int G, int value_dtype, int sorted);
+size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value_dtype, int sorted);
 int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx,
                           const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int G, double* ent,
                           void* workspace, size_t ws_bytes, cudaStream_t st);

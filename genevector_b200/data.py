@@ -88,7 +88,7 @@ def get_gene_entropy(X, gene_names, device="cuda"):
         raise ValueError("gene_names must have one entry per column of X")
     with torch.cuda.device(eng.device):
         dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
-        ws_bytes = eng.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt, 1)
+        ws_bytes = eng.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_cells, csr.n_genes, dt, 1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=eng.device)
         ent = torch.empty(csr.n_genes, dtype=torch.float64, device=eng.device)
         _lib.call("gv_gene_entropy", csr.values.data_ptr(), dt, csr.col_idx.data_ptr(),

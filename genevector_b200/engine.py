@@ -200,7 +200,7 @@ class Engine:
         self.kernel_events = None
 
     # kernels launched by each entry point (memsets / copies not counted)
-    _LAUNCHES = {"gv_discretize_csr": 3, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
+    _LAUNCHES = {"gv_discretize_csr": 2, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
                  "gv_mi_tiles": 1, "gv_gram_dump": 1}
 
     def _call(self, name, *args):
@@ -293,7 +293,7 @@ class Engine:
                               f"{l_max} keep the co-moments of {csr.n_cells} cells exact")
             dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
             sorted_ws = 1 if val_mode == 3 else 0
-            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_genes, dt, sorted_ws)
+            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_cells, csr.n_genes, dt, sorted_ws)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             q = quantile_table()
             mode = val_mode

@@ -45,7 +45,8 @@ typedef enum gv_status {
 typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
 
 /* Discretisation strategies (same results, bit for bit):
- *   GV_PATH_COUNTS  per-gene value histogram + lookup table; needs integer values in 1..255
+ *   GV_PATH_COUNTS  dense uint8 transposition through shared memory + per-gene value histogram and
+ *                   lookup table; needs integer values <= 255 in canonical CSR (ascending columns)
  *   GV_PATH_GENERAL gene-major regroup + multi-target radix select; any float32/float64 data
  *   GV_PATH_AUTO    try COUNTS, fall back to GENERAL when the data do not qualify */
 typedef enum gv_disc_path { GV_PATH_AUTO = 0, GV_PATH_COUNTS = 1, GV_PATH_GENERAL = 2 } gv_disc_path;
@@ -105,12 +106,12 @@ int gv_device_check(void);
  *                            gsum / gsq are then the sums of that integer and of its square.
  *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen;
  *                            [1] = max ceil(value)
- *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype, sorted) bytes,
+ *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_cells, n_genes, value_dtype, sorted) bytes,
  *                            sorted = 1 when val_mode is 3 (the rank rows of non-count data need a
  *                            per-gene sort: twice the regroup scratch)
  *   path / path_used_host  : gv_disc_path to use; the one taken is written to *path_used_host (optional)
  * n_bins must be in [1, 15] (bins are stored in 4 bits). */
-size_t gv_discretize_workspace_bytes(int64_t nnz, int n_genes, int value_dtype, int sorted);
+size_t gv_discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int n_genes, int value_dtype, int sorted);
 int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
                       const int64_t* row_ptr, int64_t n_cells, int n_genes, int64_t nnz, int n_bins,
                       const double* q_table_host, void* bins_packed, int64_t bins_pitch_bytes,
@@ -125,7 +126,7 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
  * computation (data.py:349): per gene the entropy (nats) of the counts of its unique values after
  * dropping the first.  Non-negative data: integer counts <= 255 take a value-histogram path, anything
  * else a per-gene sort (needs row_ptr and nnz < 2^31).  entropy_out float64 [n_genes];
- * workspace >= gv_discretize_workspace_bytes(nnz, n_genes, value_dtype, 1) bytes. */
+ * workspace >= gv_discretize_workspace_bytes(nnz, n_cells, n_genes, value_dtype, 1) bytes. */
 int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
                     const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int n_genes,
                     double* entropy_out, void* workspace, size_t workspace_bytes, void* stream);
