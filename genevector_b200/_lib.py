@@ -54,6 +54,7 @@ SIGNATURES = {
     "gv_mi_tiles": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
                            _i32, _i32, _vp, _vp]),
     "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "gv_mma_peak": (_i32, [_i32, _i32, _i32, _vp, _vp]),
     "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -54,6 +54,7 @@ int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, co
                           const int32_t*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
                           int64_t, float*, int64_t, int, void*, cudaStream_t);
 
+int mma_peak_dispatch(int, int, int, double*, cudaStream_t);
 int build_pairs_dispatch(const float*, int64_t, int, float, int, int, int64_t*, int64_t*, float*,
                          cudaStream_t);
 
@@ -222,6 +223,12 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
   return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, n_limbs,
                                limb_bits, tiles, n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
                                static_cast<cudaStream_t>(stream));
+}
+
+int gv_mma_peak(int operand_format, int cta_group, int iters, double* tops_out_host, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  return mma_peak_dispatch(operand_format, cta_group, iters, tops_out_host, static_cast<cudaStream_t>(stream));
 }
 
 int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_genes, float c,

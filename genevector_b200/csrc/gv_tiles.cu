@@ -206,4 +206,111 @@ int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64
   }
 }
 
+// ------------------------------------------------------------------ instruction-rate probe
+// Issues the MI contraction's own tcgen05.mma (same instruction descriptor, M = 256, N = 240,
+// one-hot-like zero operands already in shared memory) back to back with no loads in between: the
+// rate the tensor pipe sustains when nothing else is in the way, i.e. the live roofline denominator
+// bench.py divides by.  Diagnostic only; not on the product path.
+template <int CG, bool FP4>
+__global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters) {
+  using Cfg = GramCfg<CG, 0, 30, FP4>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar = smem_base + Cfg::STAGE_BYTES;
+  const uint32_t tmem_slot = bar + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGE_BYTES + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = (CG == 2) ? cluster_ctarank() == 0 : true;
+  for (int i = threadIdx.x; i < Cfg::STAGE_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  if constexpr (FP4) {
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    tmem_fill_32x16(tmem_base + lane_base + Cfg::SFA_COL, 0x7F7F7F7Fu);
+    tmem_fill_32x16(tmem_base + lane_base + Cfg::SFB_COL, 0x7F7F7F7Fu);
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 1 && lane == 0 && leader) {
+    const uint64_t adesc = smem_desc_k128(smem_base);
+    const uint64_t bdesc = smem_desc_k128(smem_base + Cfg::A_BYTES);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d_tmem = tmem_base + uint32_t(it & 1) * GRAM_TILE_N;
+#pragma unroll
+      for (int k = 0; k < GRAM_BK / 32; ++k) {
+        if constexpr (FP4)
+          mma_mxf4<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
+                       tmem_base + Cfg::SFA_COL, tmem_base + Cfg::SFB_COL, 1u);
+        else
+          mma_i8<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, 1u);
+      }
+    }
+    mma_commit<CG>(bar);
+    mbar_wait(bar, 0);
+  }
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+template <int CG, bool FP4>
+static int mma_peak_launch(int iters, double* tops_out, cudaStream_t st) {
+  using Cfg = GramCfg<CG, 0, 30, FP4>;
+  auto kern = mma_peak_kernel<CG, FP4>;
+  const size_t smem = 1024 + Cfg::STAGE_BYTES + 64;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  const int sms = device_sm_count();
+  const int clusters = sms / CG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(unsigned(clusters * CG));
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  if ((e = cudaEventCreate(&e0)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  if ((e = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return set_cuda_error(e, __FILE__, __LINE__); }
+  float best = 1e30f;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {       // first launch is the warm-up
+    cudaEventRecord(e0, st);
+    e = cudaLaunchKernelEx(&cfg, kern, iters);
+    cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+  // cells per MMA: 32 bytes of K = 32 (INT8) or 64 (FP4)
+  const double ops = double(clusters) * double(iters) * (GRAM_BK / 32) * 2.0 * Cfg::TILE_M * Cfg::N_COLS *
+                     (FP4 ? 64.0 : 32.0);
+  *tops_out = ops / (double(best) * 1e-3) / 1e12;
+  return GV_OK;
+}
+
+int mma_peak_dispatch(int operand_format, int cta_group, int iters, double* tops_out, cudaStream_t st) {
+  if (!tops_out || iters < 1) return set_error(GV_ERR_ARG, "gv_mma_peak: bad argument");
+  const bool fp4 = operand_format == GV_OPERAND_FP4;
+  if (!fp4 && operand_format != GV_OPERAND_INT8) return set_error(GV_ERR_ARG, "unknown operand format");
+  if (cta_group == 2) return fp4 ? mma_peak_launch<2, true>(iters, tops_out, st) : mma_peak_launch<2, false>(iters, tops_out, st);
+  if (cta_group == 1) return fp4 ? mma_peak_launch<1, true>(iters, tops_out, st) : mma_peak_launch<1, false>(iters, tops_out, st);
+  return set_error(GV_ERR_ARG, "cta_group must be 1 or 2");
+}
+
 }  // namespace gv

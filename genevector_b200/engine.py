@@ -455,6 +455,15 @@ class Engine:
                       self._sync_ptr(rows * row_bytes), self._stream())
             return out
 
+    def mma_peak(self, operand: str = "fp4", iters: int = 60000) -> float:
+        """Diagnostic: TOP/s the tensor pipe sustains on the MI contraction's own MMA instruction
+        issued back to back (gv_mma_peak); bench.py's live roofline denominator."""
+        with torch.cuda.device(self.device):
+            out = np.zeros(1, dtype=np.float64)
+            _lib.call("gv_mma_peak", self._fmt(operand), self.cta_group, iters, out.ctypes.data,
+                      self._stream())
+            return float(out[0])
+
     # ------------------------------------------------------------------ whole paths
     def _replicate(self, blk_or_none, n_cells, n_genes, n_bins, val_mode, group) -> BinBlock:
         """The single collective of the path: broadcast the bin block from rank 0.  The header at
@@ -513,11 +522,22 @@ class Engine:
         onehot, B = self.expand_onehot(blk)
         return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world)
 
-    def target_from_csr(self, csr: CsrDevice, kind: int, ranks: bool = False) -> torch.Tensor:
-        """Pearson / cosine / Jaccard matrix; ranks=True with GV_MOM_PEARSON is Spearman."""
+    def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,
+                        n_cells: Optional[int] = None, n_genes: Optional[int] = None,
+                        rank: int = 0, world: int = 1, group=None,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pearson / cosine / Jaccard matrix; ranks=True with GV_MOM_PEARSON is Spearman.  With
+        world > 1 only rank 0 needs `csr` (pass n_cells / n_genes elsewhere): rank 0 builds the value
+        rows, one broadcast replicates the block, every rank computes its slice of the tile schedule."""
+        import torch.distributed as dist
         mode = 1 if kind == _lib.GV_MOM_JACCARD else (3 if ranks else 0)
-        blk = self.discretize(csr, 10, mode)
-        return self.moment_scores(blk, kind)
+        if csr is not None:
+            n_cells, n_genes = csr.n_cells, csr.n_genes
+        distributed = world > 1 and dist.is_available() and dist.is_initialized()
+        blk = self.discretize(csr, 10, mode) if (rank == 0 or not distributed) else None
+        if distributed:
+            blk = self._replicate(blk, n_cells, n_genes, 10, mode, group)
+        return self.moment_scores(blk, kind, out=out, rank=rank, world=world)
 
 
 _engines = {}

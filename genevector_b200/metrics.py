@@ -96,13 +96,21 @@ def target_mi(X, gene_names, signed=False, backend="b200", device="cuda", n_bins
     raise ValueError(f"Unknown MI backend: {backend}")
 
 
-def _moment_target(X, gene_names, kind, device=None, ranks=False):
+def _moment_target(X, gene_names, kind, device=None, ranks=False, gather=True):
+    """Shared body of the matrix targets; under torch.distributed the tile space is split over the
+    ranks like compute_mi_b200 (one broadcast of the value rows, optional result assembly)."""
     import torch
     eng = get_engine(_device_of(device))
-    if len(gene_names) != X.shape[1]:
+    rank, world = _dist_info()
+    n_cells, n_genes = X.shape
+    if len(gene_names) != n_genes:
         raise ValueError("gene_names must have one entry per column of X")
-    csr = eng.upload_csr(X)
-    out = eng.target_from_csr(csr, kind, ranks=ranks)
+    csr = eng.upload_csr(X) if rank == 0 else None
+    out = eng.target_from_csr(csr, kind, ranks=ranks, n_cells=n_cells, n_genes=n_genes, rank=rank, world=world)
+    if world > 1 and gather:
+        import torch.distributed as dist
+        # every entry is computed by exactly one rank and is 0 elsewhere (NaN + 0 stays NaN)
+        dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize(eng.device)
     return ScoreMatrix(out.cpu().numpy(), gene_names)
 

@@ -181,6 +181,12 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t row_bytes, const 
                  int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
                  int operand_format, void* stream);
 
+/* Diagnostic: the rate (TOP/s, whole device) at which the tensor pipe executes the MI contraction's
+ * own tcgen05.mma instruction (M = 256 per CTA pair, N = 240, operands resident in shared memory)
+ * when issued back to back with no loads: the live roofline denominator of bench.py.  Synchronous
+ * (times `iters` x 4 MMAs per CTA pair with CUDA events on `stream`, best of 3). */
+int gv_mma_peak(int operand_format, int cta_group, int iters, double* tops_out_host, void* stream);
+
 /* ---------------------------------------------------------------- co-moment targets
  * val_rows from gv_discretize_csr: n_limbs INT8 rows per gene (layout there; one 0/1 row for
  * GV_MOM_JACCARD), op_rows >= gv_value_rows(n_genes, n_limbs); tiles are in operand rows.  kind
