@@ -55,6 +55,14 @@ int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, co
                           int64_t, float*, int64_t, int, void*, cudaStream_t);
 
 int mma_peak_dispatch(int, int, int, double*, cudaStream_t);
+int xcorr_tiles_dispatch(const void*, int64_t, int, const void*, int64_t, int, int64_t, int, const int64_t*,
+                         const int64_t*, const double*, int64_t, const int64_t*, const int64_t*,
+                         const double*, int64_t, int, const int32_t*, int64_t, float*, int64_t, int, void*,
+                         cudaStream_t);
+int graph_aggregate_dispatch(const void*, int64_t, int, int, const double*, int64_t, const int64_t*,
+                             const int32_t*, const double*, double*, int, int64_t, int, void*, int64_t, int,
+                             int64_t*, int64_t*, double*, cudaStream_t);
+int symmetrize_dispatch(const float*, int64_t, int, float*, int64_t, cudaStream_t);
 int build_pairs_dispatch(const float*, int64_t, int, float, int, int, int64_t*, int64_t*, float*,
                          cudaStream_t);
 
@@ -223,6 +231,66 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
   return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, n_limbs,
                                limb_bits, tiles, n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
                                static_cast<cudaStream_t>(stream));
+}
+
+int64_t gv_tile_schedule_rect(int64_t rows_a, int64_t rows_b, int tile_m, int32_t* out_pairs_host,
+                              int64_t capacity) {
+  if (rows_a <= 0 || rows_b <= 0 || (tile_m != 128 && tile_m != 256))
+    return set_error(GV_ERR_ARG, "bad tile schedule argument");
+  const int64_t tr = (rows_a + tile_m - 1) / tile_m, tc = (rows_b + 255) / 256;
+  int64_t n = 0;
+  for (int64_t b0 = 0; b0 < tr; b0 += 8)
+    for (int64_t c = 0; c < tc; ++c)
+      for (int64_t r = b0; r < (b0 + 8 < tr ? b0 + 8 : tr); ++r, ++n)
+        if (out_pairs_host && n < capacity) {
+          out_pairs_host[2 * n] = int32_t(r * tile_m);
+          out_pairs_host[2 * n + 1] = int32_t(c * 256);
+        }
+  return n;
+}
+
+int gv_graph_aggregate(const void* x_rows, int64_t op_rows_x, int64_t kp, int x_limbs, int limb_bits,
+                       const double* x_scale, int64_t x_scale_stride, const int64_t* w_row_ptr,
+                       const int32_t* w_col, const double* w_val, double* w_inv_ws, int include_self,
+                       int64_t n_cells, int n_genes, void* y_rows, int64_t op_rows_y, int y_limbs,
+                       int64_t* ysum, int64_t* ysq, double* yscale, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!x_rows || !w_row_ptr || !w_inv_ws || !y_rows || !ysum || !ysq || !yscale || n_genes <= 0 ||
+      n_cells < 0 || kp < n_cells || x_limbs < 1 || x_limbs > 4 || y_limbs < 1 || y_limbs > 4 ||
+      limb_bits < 1 || limb_bits > 7)
+    return set_error(GV_ERR_ARG, "gv_graph_aggregate: bad argument");
+  if (op_rows_x < gv_value_rows(n_genes, x_limbs) || op_rows_y < gv_value_rows(n_genes, y_limbs))
+    return set_error(GV_ERR_ARG, "gv_graph_aggregate: value rows too short");
+  return graph_aggregate_dispatch(x_rows, kp, x_limbs, limb_bits, x_scale, x_scale_stride, w_row_ptr, w_col,
+                                  w_val, w_inv_ws, include_self, n_cells, n_genes, y_rows, op_rows_y,
+                                  y_limbs, ysum, ysq, yscale, static_cast<cudaStream_t>(stream));
+}
+
+int gv_xcorr_tiles(const void* x_rows, int64_t op_rows_x, int x_limbs, const void* y_rows,
+                   int64_t op_rows_y, int y_limbs, int64_t kp, int limb_bits, const int64_t* xsum,
+                   const int64_t* xsq, const double* x_scale, int64_t x_scale_stride,
+                   const int64_t* ysum, const int64_t* ysq, const double* yscale, int64_t n_cells,
+                   int n_genes, const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out,
+                   int cta_group, void* sync_ws, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!x_rows || !y_rows || !xsum || !xsq || !ysum || !ysq || !yscale || !tiles || !out || n_genes <= 0 ||
+      ld_out < n_genes || x_limbs < 1 || x_limbs > 4 || y_limbs < 1 || y_limbs > 4)
+    return set_error(GV_ERR_ARG, "gv_xcorr_tiles: bad argument");
+  if (op_rows_x < gv_value_rows(n_genes, x_limbs) || op_rows_y < gv_value_rows(n_genes, y_limbs))
+    return set_error(GV_ERR_ARG, "gv_xcorr_tiles: value rows too short");
+  return xcorr_tiles_dispatch(x_rows, op_rows_x, x_limbs, y_rows, op_rows_y, y_limbs, kp, limb_bits, xsum, xsq,
+                              x_scale, x_scale_stride, ysum, ysq, yscale, n_cells, n_genes, tiles, n_tiles,
+                              out, ld_out, cta_group, sync_ws, static_cast<cudaStream_t>(stream));
+}
+
+int gv_symmetrize(const float* t, int64_t ld_t, int n_genes, float* out, int64_t ld_out, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!t || !out || n_genes <= 0 || ld_t < n_genes || ld_out < n_genes)
+    return set_error(GV_ERR_ARG, "gv_symmetrize: bad argument");
+  return symmetrize_dispatch(t, ld_t, n_genes, out, ld_out, static_cast<cudaStream_t>(stream));
 }
 
 int gv_mma_peak(int operand_format, int cta_group, int iters, double* tops_out_host, void* stream) {

@@ -156,6 +156,7 @@ __global__ void k_scatter(const T* __restrict__ values, const int32_t* __restric
 }
 
 // ---------------------------------------------------------------- k_gene_bins
+constexpr int EDGE_SCALE_SLOT = 15;   // GV_EDGE_SCALE_SLOT
 constexpr int GB_THREADS = 256;
 constexpr int H0_BITS = 11;
 constexpr int H0_SIZE = 1 << H0_BITS;
@@ -208,7 +209,7 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
         gsum[g] = 0; gsq[g] = 0;
       }
       if (tid < MARG_STRIDE_) marg[int64_t(g) * MARG_STRIDE_ + tid] = 0;
-      if (tid < 16) edges_out[int64_t(g) * 16 + tid] = DBL_MAX;
+      if (tid < 16) edges_out[int64_t(g) * 16 + tid] = tid == EDGE_SCALE_SLOT ? 1.0 : DBL_MAX;
       continue;
     }
     // ---- pass 0: level-0 histogram, distinct set, integer sums
@@ -434,7 +435,10 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
     } else if (tid < 16) {
       marg[int64_t(g) * MARG_STRIDE_ + tid] = int32_t(sm.marg[tid]);
     }
-    if (tid < 16) edges_out[int64_t(g) * 16 + tid] = sm.edges[tid];
+    // slot 15 is never an edge (n_bins <= 15): it carries the real value of one value-row unit
+    if (tid < 16)
+      edges_out[int64_t(g) * 16 + tid] =
+          tid == EDGE_SCALE_SLOT ? (val_mode == 2 ? ldexp(1.0, -fx_shift) : 1.0) : sm.edges[tid];
   }
 }
 
@@ -701,7 +705,7 @@ __device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bin
 #pragma unroll
     for (int t = 0; t < 14; ++t) edges_out[int64_t(g) * 16 + t] = edge[t];
     edges_out[int64_t(g) * 16 + 14] = DBL_MAX;
-    edges_out[int64_t(g) * 16 + 15] = DBL_MAX;
+    edges_out[int64_t(g) * 16 + EDGE_SCALE_SLOT] = 1.0;   // one value-row unit = 1 (counts, ranks)
   }
 }
 

@@ -374,4 +374,89 @@ struct MomentEpi {
   }
 };
 
+// ------------------------------------------------------------------ XcorrEpi
+// Cross-correlation between expression (A side: LA digit rows per gene) and graph-aggregated
+// expression (B side: LB digit rows per gene), genevector/_graph_targets.py:45-50:
+//   X_std = (X - mean) / (std + 1e-8), likewise X_agg;  xcorr = X_std^T @ X_agg_std / n_cells
+// from exact integer co-moments: Sum (x - mx)(y - my) = (n Sxy - Sx Sy) / n in value-row units, times
+// the per-gene unit scales.  Writes the non-symmetric xcorr[a][b]; gv_symmetrize finishes (:51-52).
+struct XcorrParams {
+  const int64_t* asum; const int64_t* asq; const double* ascale; int64_t ascale_stride;   // A side per gene
+  const int64_t* bsum; const int64_t* bsq; const double* bscale;                          // B side per gene
+  float* out; int64_t ld_out;
+  int G; int64_t n_cells; int limb_bits;
+};
+
+template <int LA, int LB>
+struct XcorrEpi {
+  using Params = XcorrParams;
+  static constexpr int GPB_A = 32 / LA, ACTIVE_A = GPB_A * LA;
+  static constexpr int GPB_B = 32 / LB;
+  static constexpr int GENES_PER_TILE_B = 8 * GPB_B;
+  struct Meta {
+    int64_t csum[GENES_PER_TILE_B];
+    double cfac[GENES_PER_TILE_B];      // scale_b / (std_b + 1e-8)
+  };
+  static constexpr size_t SMEM_BYTES = sizeof(Meta) + 16;
+  static constexpr int ACTIVE_ROWS = 32;
+  static constexpr bool OPERAND_FP4 = false;
+  const Params& p;
+  Meta* meta;
+  __device__ XcorrEpi(const Params& p_, uint8_t* smem) : p(p_) { meta = reinterpret_cast<Meta*>(smem); }
+
+  // scale / (population std + 1e-8) of a gene from its integer sums
+  __device__ static double std_factor(int64_t s, int64_t sq, double scale, int64_t n) {
+    const i128 var = i128(n) * sq - i128(s) * s;
+    const double sd = sqrt(i128_to_double(var)) / double(n) * scale;
+    return scale / (sd + 1e-8);
+  }
+  __device__ void prepare(const EpiTile& et) {
+    epi_bar_sync();
+    const int c = et.epi_tid;
+    if (c < GENES_PER_TILE_B) {
+      const int gj = (et.col0 >> 5) * GPB_B + c;
+      const bool ok = gj < p.G;
+      meta->csum[c] = ok ? p.bsum[gj] : 0;
+      meta->cfac[c] = ok ? std_factor(p.bsum[gj], p.bsq[gj], p.bscale[gj], p.n_cells) : 0.0;
+    }
+    epi_bar_sync();
+  }
+  __device__ void run(const EpiTile& et) {
+    const int si = et.lane / LA;
+    const int digit = et.lane - si * LA;
+    const int gi = ((et.row0 >> 5) + et.quarter) * GPB_A + si;
+    const bool row_ok = et.lane < ACTIVE_A && gi < p.G;
+    int64_t sx = 0;
+    double fx = 0.0;
+    if (row_ok) {
+      sx = p.asum[gi];
+      fx = std_factor(sx, p.asq[gi], p.ascale ? p.ascale[int64_t(gi) * p.ascale_stride] : 1.0, p.n_cells);
+    }
+    const double inv_n2 = 1.0 / (double(p.n_cells) * double(p.n_cells));
+    const int lb = p.limb_bits;
+#pragma unroll 1
+    for (int cbi = 0; cbi < 4; ++cbi) {
+      const int cb = et.half * 4 + cbi;
+      uint32_t v[32];
+      tmem_ld_32x32(et.tmem_acc + (uint32_t(et.quarter * 32) << 16) + uint32_t(cb * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < GPB_B; ++c) {
+        const int cg = cb * GPB_B + c;
+        const int gj = ((et.col0 >> 5) + cb) * GPB_B + c;
+        int64_t sxy = int64_t(v[c * LB]);
+#pragma unroll
+        for (int q = 1; q < LB; ++q) sxy += int64_t(v[c * LB + q]) << (q * lb);
+        if constexpr (LA > 1) {
+          sxy <<= (digit * lb);
+          sxy = seg_reduce<LA>(sxy, digit);
+        }
+        if (digit != 0 || !row_ok || gj >= p.G) continue;
+        const i128 cov = i128(p.n_cells) * sxy - i128(sx) * meta->csum[cg];
+        p.out[int64_t(gi) * p.ld_out + gj] = float(i128_to_double(cov) * inv_n2 * fx * meta->cfac[cg]);
+      }
+    }
+  }
+};
+
 }  // namespace gv

@@ -97,8 +97,10 @@ template <int CG, class Epi>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
                   const GramArgs ga, const typename Epi::Params ep) {
-  // tmap: 2-D, 128-row boxes (A side, and B side when ACTIVE == 32);
-  // tmap_b: 3-D view [block][32 rows][K] with a box of B_BLOCKS blocks x ACTIVE rows x 128 bytes
+  // tmap: 2-D, 128-row boxes over the A-side operand;
+  // tmap_b: the B-side operand (the same matrix for the symmetric products, another one for the
+  // cross-correlation target): 2-D 128-row boxes when ACTIVE == 32, else a 3-D view
+  // [block][32 rows][K] with a box of B_BLOCKS blocks x ACTIVE rows x 128 bytes
   using Cfg = GramCfg<CG, int(Epi::SMEM_BYTES), Epi::ACTIVE_ROWS, Epi::OPERAND_FP4>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -180,7 +182,7 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           if constexpr (CG == 2) {
             tma_load_2d_pair(&tmap, fb, sa, kb * GRAM_BK, arow);
             if constexpr (Epi::ACTIVE_ROWS == 32) {
-              tma_load_2d_pair(&tmap, fb, sb, kb * GRAM_BK, brow);
+              tma_load_2d_pair(&tmap_b, fb, sb, kb * GRAM_BK, brow);
             } else {
               // one 3-D box: 128 bytes of K x ACTIVE rows x B_BLOCKS blocks, landing back to back
               tma_load_3d_pair(&tmap_b, fb, sb, kb * GRAM_BK, 0, brow >> 5);
@@ -191,8 +193,8 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             tma_load_2d(&tmap, fb, sa, kb * GRAM_BK, arow);
             if constexpr (Epi::ACTIVE_ROWS == 32) {
               // TMA boxes are at most 256 rows; 256 rows here and the box is 128 rows
-              tma_load_2d(&tmap, fb, sb, kb * GRAM_BK, brow);
-              tma_load_2d(&tmap, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
+              tma_load_2d(&tmap_b, fb, sb, kb * GRAM_BK, brow);
+              tma_load_2d(&tmap_b, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
             } else {
               tma_load_3d(&tmap_b, fb, sb, kb * GRAM_BK, 0, brow >> 5);
             }

@@ -63,16 +63,18 @@ static int make_block_map(CUtensorMap* map, const void* operand, int64_t op_rows
   return GV_OK;
 }
 
+// operand_b / op_rows_b: the B-side matrix when it is not the A-side one (cross-correlation target)
 template <int CG, class Epi>
 static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,
                        int64_t n_tiles, const typename Epi::Params& ep, void* sync_ws,
-                       cudaStream_t st) {
+                       cudaStream_t st, const void* operand_b = nullptr, int64_t op_rows_b = 0) {
   if (n_tiles <= 0) return GV_OK;
+  if (operand_b == nullptr) { operand_b = operand; op_rows_b = op_rows; }
   CUtensorMap map, map_b;
   int rc = make_operand_map(&map, operand, op_rows, kp);
   if (rc != GV_OK) return rc;
-  if (Epi::ACTIVE_ROWS == 32) rc = make_operand_map(&map_b, operand, op_rows, kp, 128);
-  else rc = make_block_map(&map_b, operand, op_rows, kp, Epi::ACTIVE_ROWS, 8 / CG);
+  if (Epi::ACTIVE_ROWS == 32) rc = make_operand_map(&map_b, operand_b, op_rows_b, kp, 128);
+  else rc = make_block_map(&map_b, operand_b, op_rows_b, kp, Epi::ACTIVE_ROWS, 8 / CG);
   if (rc != GV_OK) return rc;
   GramArgs ga;
   ga.tiles = reinterpret_cast<const int2*>(tiles);
@@ -111,9 +113,12 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
 template <class Epi>
 static int launch_cg(int cta_group, const void* operand, int64_t op_rows, int64_t kp,
                      const int32_t* tiles, int64_t n_tiles, const typename Epi::Params& ep,
-                     void* sync_ws, cudaStream_t st) {
-  if (cta_group == 2) return launch_gram<2, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, sync_ws, st);
-  if (cta_group == 1) return launch_gram<1, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, sync_ws, st);
+                     void* sync_ws, cudaStream_t st, const void* operand_b = nullptr,
+                     int64_t op_rows_b = 0) {
+  if (cta_group == 2)
+    return launch_gram<2, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, sync_ws, st, operand_b, op_rows_b);
+  if (cta_group == 1)
+    return launch_gram<1, Epi>(operand, op_rows, kp, tiles, n_tiles, ep, sync_ws, st, operand_b, op_rows_b);
   return set_error(GV_ERR_ARG, "cta_group must be 1 or 2");
 }
 
@@ -204,6 +209,32 @@ int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64
     case 3: return moment_dispatch_l<3>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     default: return moment_dispatch_l<4>(kind, cta_group, val_rows, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
   }
+}
+
+int xcorr_tiles_dispatch(const void* x_rows, int64_t op_rows_x, int x_limbs, const void* y_rows,
+                         int64_t op_rows_y, int y_limbs, int64_t kp, int limb_bits, const int64_t* xsum,
+                         const int64_t* xsq, const double* xscale, int64_t xscale_stride,
+                         const int64_t* ysum, const int64_t* ysq, const double* yscale, int64_t n_cells,
+                         int n_genes, const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out,
+                         int cta_group, void* sync_ws, cudaStream_t st) {
+  XcorrParams p;
+  p.asum = xsum; p.asq = xsq; p.ascale = xscale; p.ascale_stride = xscale_stride;
+  p.bsum = ysum; p.bsq = ysq; p.bscale = yscale; p.out = out; p.ld_out = ld_out; p.G = n_genes;
+  p.n_cells = n_cells; p.limb_bits = limb_bits;
+  if (limb_bits < 1 || limb_bits > 7) return set_error(GV_ERR_ARG, "limb_bits must be in [1,7]");
+  const uint64_t dmax = (1ull << limb_bits) - 1ull;
+  if (uint64_t(n_cells) * dmax * dmax >= (1ull << 32))
+    return set_error(GV_ERR_UNSUPPORTED, "co-moment accumulators would overflow: lower limb_bits");
+  const int tb = (x_limbs > y_limbs ? x_limbs : y_limbs) * limb_bits;
+  if (tb > 31 || (long double)n_cells * (long double)((1ull << tb) - 1ull) * (long double)((1ull << tb) - 1ull) >= 9.2e18L)
+    return set_error(GV_ERR_UNSUPPORTED, "co-moment sums would overflow 64 bits: fewer value bits needed");
+  if (y_limbs != 3) return set_error(GV_ERR_UNSUPPORTED, "xcorr: the aggregated rows must have three digits");
+  switch (x_limbs) {
+    case 1: return launch_cg<XcorrEpi<1, 3>>(cta_group, x_rows, op_rows_x, kp, tiles, n_tiles, p, sync_ws, st, y_rows, op_rows_y);
+    case 2: return launch_cg<XcorrEpi<2, 3>>(cta_group, x_rows, op_rows_x, kp, tiles, n_tiles, p, sync_ws, st, y_rows, op_rows_y);
+    case 3: return launch_cg<XcorrEpi<3, 3>>(cta_group, x_rows, op_rows_x, kp, tiles, n_tiles, p, sync_ws, st, y_rows, op_rows_y);
+  }
+  return set_error(GV_ERR_UNSUPPORTED, "xcorr: the expression rows must have one to three digits");
 }
 
 // ------------------------------------------------------------------ instruction-rate probe

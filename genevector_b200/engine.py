@@ -201,7 +201,8 @@ class Engine:
 
     # kernels launched by each entry point (memsets / copies not counted)
     _LAUNCHES = {"gv_discretize_csr": 2, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
-                 "gv_mi_tiles": 1, "gv_gram_dump": 1}
+                 "gv_mi_tiles": 1, "gv_gram_dump": 1, "gv_graph_aggregate": 2, "gv_xcorr_tiles": 1,
+                 "gv_symmetrize": 1}
 
     def _call(self, name, *args):
         """Call a kernel-launching entry point, optionally bracketed by CUDA events recorded on
@@ -453,6 +454,64 @@ class Engine:
                       sgn.stride(0) if sgn is not None else 0, G, tiles.data_ptr(), n,
                       out.data_ptr(), out.stride(0), self.cta_group, fmt,
                       self._sync_ptr(rows * row_bytes), self._stream())
+            return out
+
+    # ------------------------------------------------------------------ graph cross-correlation
+    def upload_graph(self, graph, n_cells: int):
+        """scipy sparse adjacency [n_cells, n_cells] -> device CSR (int64 row_ptr, int32 col, float64 val)."""
+        import scipy.sparse as sp
+        W = sp.csr_matrix(graph)
+        if W.shape != (n_cells, n_cells):
+            raise ValueError(f"graph must be {n_cells} x {n_cells}, got {W.shape}")
+        if W.nnz and float(W.data.min()) < 0:
+            raise GvError("upload_graph", -4, "graph weights must be non-negative")
+        ptr = torch.from_numpy(np.ascontiguousarray(W.indptr, dtype=np.int64)).to(self.device)
+        col = torch.from_numpy(np.ascontiguousarray(W.indices, dtype=np.int32)).to(self.device)
+        val = torch.from_numpy(np.ascontiguousarray(W.data, dtype=np.float64)).to(self.device)
+        return ptr, col, val
+
+    def rect_schedule(self, rows_a: int, rows_b: int):
+        key = ("rect", rows_a, rows_b, self.cta_group)
+        if key not in self._sched_cache:
+            tm = _lib.call("gv_tile_m", self.cta_group)
+            n = _lib.check("gv_tile_schedule_rect", self.lib.gv_tile_schedule_rect(rows_a, rows_b, tm, None, 0))
+            host = np.zeros((max(n, 1), 2), dtype=np.int32)
+            _lib.check("gv_tile_schedule_rect",
+                       self.lib.gv_tile_schedule_rect(rows_a, rows_b, tm, host.ctypes.data, n))
+            self._sched_cache[key] = (torch.from_numpy(host).to(self.device), n)
+        return self._sched_cache[key]
+
+    def graph_xcorr(self, csr: CsrDevice, graph_dev, include_self: bool = False) -> torch.Tensor:
+        """float32 [G][G] symmetrised cross-correlation between expression and graph-neighbour mean
+        expression (_graph_targets.py:10-55, aggregation "mean")."""
+        w_ptr, w_col, w_val = graph_dev
+        with torch.cuda.device(self.device):
+            blk = self.discretize(csr, 10, val_mode=0)        # count digits, or fixed point for floats
+            G, N, kp, lb = blk.n_genes, blk.n_cells, blk.kp, blk.limb_bits
+            ly = min(3, max_limbs_for(N, lb))
+            if ly != 3:
+                raise GvError("graph_xcorr", -4, f"{N} cells leave fewer than three exact digits per value")
+            rows_x, rows_y = value_rows(G, blk.n_limbs), value_rows(G, ly)
+            y_rows = torch.empty((rows_y, kp), dtype=torch.int8, device=self.device)
+            ysum = torch.empty(G, dtype=torch.int64, device=self.device)
+            ysq = torch.empty_like(ysum)
+            yscale = torch.empty(G, dtype=torch.float64, device=self.device)
+            w_inv = torch.empty(max(N, 1), dtype=torch.float64, device=self.device)
+            xscale_ptr = blk.edges.data_ptr() + 8 * _lib.GV_EDGE_SCALE_SLOT
+            self._call("gv_graph_aggregate", blk.val_rows.data_ptr(), rows_x, kp, blk.n_limbs, lb, xscale_ptr,
+                       _lib.GV_EDGE_STRIDE, w_ptr.data_ptr(), w_col.data_ptr(), w_val.data_ptr(),
+                       w_inv.data_ptr(), 1 if include_self else 0, N, G, y_rows.data_ptr(), rows_y, ly,
+                       ysum.data_ptr(), ysq.data_ptr(), yscale.data_ptr(), self._stream())
+            tiles, n = self.rect_schedule(rows_x, rows_y)
+            xc = torch.empty((G, G), dtype=torch.float32, device=self.device)
+            self._call("gv_xcorr_tiles", blk.val_rows.data_ptr(), rows_x, blk.n_limbs, y_rows.data_ptr(), rows_y,
+                       ly, kp, lb, blk.gsum.data_ptr(), blk.gsq.data_ptr(), xscale_ptr, _lib.GV_EDGE_STRIDE,
+                       ysum.data_ptr(), ysq.data_ptr(), yscale.data_ptr(), N, G, tiles.data_ptr(), n,
+                       xc.data_ptr(), xc.stride(0), self.cta_group,
+                       self._sync_ptr(max(rows_x, rows_y) * kp), self._stream())
+            out = torch.empty_like(xc)
+            self._call("gv_symmetrize", xc.data_ptr(), xc.stride(0), G, out.data_ptr(), out.stride(0),
+                       self._stream())
             return out
 
     def mma_peak(self, operand: str = "fp4", iters: int = 60000) -> float:

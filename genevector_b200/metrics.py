@@ -10,6 +10,7 @@ same argument meaning, same error behaviour, so that `GeneVectorDataset(mi_backe
     target_mi(X, gene_names, signed, backend, device, n_bins)     :381-411
     target_pearson / target_cosine / target_jaccard     :414-420, :452-461, :434-449
     target_spearman                                     :423-431
+    target_graph_xcorr                                  genevector/_graph_targets.py:10-55
     TARGETS / register_target / get_target_function     :344-376
 
 There is one backend and no fallback: backend must be "b200" (or "auto", which here can only
@@ -140,9 +141,36 @@ def target_cosine(X, gene_names, device=None, **kwargs):
     return _moment_target(X, gene_names, _lib.GV_MOM_COSINE, device)
 
 
+@register_target("graph_xcorr")
+def target_graph_xcorr(X, gene_names, graph=None, aggr="mean", aggr_params=None, device=None, **kwargs):
+    """Cross-correlation between self-expression and graph-neighbour-aggregated expression, symmetrised
+    (genevector/_graph_targets.py:10-55).  The built-in "mean" aggregation (with its include_self
+    option, _aggregation.py:88-109) runs on the device; host callables cannot."""
+    import torch
+    if graph is None:
+        raise ValueError(
+            "graph required. Pass any scipy sparse adjacency matrix "
+            "via target_kwargs={'graph': G}"
+        )
+    if callable(aggr):
+        raise ValueError("the b200 backend runs the built-in 'mean' aggregation on the device; "
+                         "callable aggregations are host functions and are not supported")
+    if aggr != "mean":
+        raise ValueError(f"Unknown aggregation '{aggr}'. Available: mean")
+    params = dict(aggr_params or {})
+    include_self = bool(params.pop("include_self", False))
+    eng = get_engine(_device_of(device))
+    if len(gene_names) != X.shape[1]:
+        raise ValueError("gene_names must have one entry per column of X")
+    csr = eng.upload_csr(X)
+    out = eng.graph_xcorr(csr, eng.upload_graph(graph, X.shape[0]), include_self=include_self)
+    torch.cuda.synchronize(eng.device)
+    return ScoreMatrix(out.cpu().numpy(), gene_names)
+
+
 def install_into_reference(ref_metrics_module):
     """Plug the B200 tier into an imported `genevector.metrics`: overrides the
     registry entries through the reference's own register_target hook."""
-    for name in ("mi", "pearson", "spearman", "cosine", "jaccard"):
+    for name in ("mi", "pearson", "spearman", "cosine", "jaccard", "graph_xcorr"):
         ref_metrics_module.register_target(name)(TARGETS[name])
     return ref_metrics_module

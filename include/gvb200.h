@@ -29,9 +29,10 @@
 extern "C" {
 #endif
 
-#define GV_ABI_VERSION 3
+#define GV_ABI_VERSION 4
 #define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
 #define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
+#define GV_EDGE_SCALE_SLOT 15 /* edges[g][15]: real value of one unit of the gene's value-row integer */
 #define GV_QTABLE_DIM 16  /* q_table_host is [16][16] float64 */
 
 typedef enum gv_status {
@@ -88,7 +89,8 @@ int gv_device_check(void);
  *                            bins_pitch_bytes % 16 == 0 and 2*bins_pitch_bytes >= padded K extent.
  *   n_bins_per_gene        : out, int32 [n_genes]  (second return value of discretize_genes)
  *   marg                   : out, int32 [n_genes][16]; [0] = #cells with x > 0, [a] = #cells in bin a
- *   edges                  : out, float64 [n_genes][16] bin edges (unused slots = DBL_MAX)
+ *   edges                  : out, float64 [n_genes][16] bin edges (unused slots = DBL_MAX); slot
+ *                            GV_EDGE_SCALE_SLOT holds the value-row scale (1.0, or 2^-e_g for val_mode 2)
  *   gsum, gsq              : out, int64 [n_genes]  Sum x and Sum x^2 over cells of the value-row integer
  *   val_rows (optional)    : out, int8 [val_rows_alloc][val_pitch] K-major operand of gv_moment_tiles:
  *                            val_limbs rows per gene holding the base-2^val_limb_bits digits (least
@@ -199,6 +201,36 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
                     int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
                     void* sync_ws, void* stream);
+
+/* ---------------------------------------------------------------- graph cross-correlation target
+ * Replaces target_graph_xcorr (genevector/_graph_targets.py:10-55) with the built-in "mean"
+ * aggregation (genevector/_aggregation.py:48-109) for non-negative data.
+ *
+ * gv_graph_aggregate: X_agg = (D^-1 W) X (0.5 X + 0.5 that with include_self) on the gene-major value
+ *   rows: x_rows / x_limbs / limb_bits / x_scale as produced by gv_discretize_csr (x_scale = the
+ *   `edges` array + GV_EDGE_SCALE_SLOT with x_scale_stride 16, or NULL for unit scale); W is the
+ *   adjacency in CSR (w_row_ptr int64 [n_cells+1], w_col int32, w_val float64, any non-negative
+ *   weights); w_inv_ws: n_cells doubles of scratch.  Out: y_rows (fixed point, y_limbs digits per
+ *   gene, op_rows_y >= gv_value_rows(n_genes, y_limbs)), ysum / ysq int64 [n_genes], yscale float64
+ *   [n_genes] (real value of one y unit).
+ * gv_xcorr_tiles: xcorr[a][b] = X_std[:,a] . X_agg_std[:,b] / n_cells over the full tile rectangle
+ *   (gv_tile_schedule_rect), exact integer co-moments, non-symmetric float32 [n_genes][ld_out];
+ *   y_limbs must be 3.
+ * gv_symmetrize: out = (t + t^T) / 2 with a zero diagonal (_graph_targets.py:51-52). */
+int64_t gv_tile_schedule_rect(int64_t rows_a, int64_t rows_b, int tile_m, int32_t* out_pairs_host,
+                              int64_t capacity);
+int gv_graph_aggregate(const void* x_rows, int64_t op_rows_x, int64_t kp, int x_limbs, int limb_bits,
+                       const double* x_scale, int64_t x_scale_stride, const int64_t* w_row_ptr,
+                       const int32_t* w_col, const double* w_val, double* w_inv_ws, int include_self,
+                       int64_t n_cells, int n_genes, void* y_rows, int64_t op_rows_y, int y_limbs,
+                       int64_t* ysum, int64_t* ysq, double* yscale, void* stream);
+int gv_xcorr_tiles(const void* x_rows, int64_t op_rows_x, int x_limbs, const void* y_rows,
+                   int64_t op_rows_y, int y_limbs, int64_t kp, int limb_bits, const int64_t* xsum,
+                   const int64_t* xsq, const double* x_scale, int64_t x_scale_stride,
+                   const int64_t* ysum, const int64_t* ysq, const double* yscale, int64_t n_cells,
+                   int n_genes, const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out,
+                   int cta_group, void* sync_ws, void* stream);
+int gv_symmetrize(const float* t, int64_t ld_t, int n_genes, float* out, int64_t ld_out, void* stream);
 
 /* ---------------------------------------------------------------- score-building fast path
  * Replaces GeneVectorDataset._build_training_tensors (data.py:377-411) for a dense device score

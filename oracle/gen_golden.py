@@ -29,6 +29,10 @@ def import_reference_metrics():
     return importlib.import_module("genevector.metrics")
 
 
+def import_reference_graph_targets():
+    return importlib.import_module("genevector._graph_targets")
+
+
 def import_reference_data():
     return importlib.import_module("genevector.data")
 
@@ -160,6 +164,17 @@ def make_case(refm, name, X, n_bins, with_targets=True, with_numba=True):
         assert np.allclose(orc.round5_dict_matrix(orc.pearson_np(X)), out["pearson"], atol=1e-12, equal_nan=True)
         assert np.allclose(orc.round5_dict_matrix(orc.cosine_np(X)), out["cosine"], atol=1e-12)
         assert np.allclose(orc.round5_dict_matrix(orc.jaccard_np(X)), out["jaccard"], atol=1e-12)
+    if with_targets:
+        # graph cross-correlation straight from the reference's target_graph_xcorr (aggr="mean")
+        refg = import_reference_graph_targets()
+        Wg = orc.seeded_graph(X.shape[0], seed=len(name))
+        out["graph_data"], out["graph_indices"], out["graph_indptr"] = (
+            Wg.data, Wg.indices.astype(np.int32), Wg.indptr.astype(np.int64))
+        out["graph_xcorr"] = dict_to_matrix(refg.target_graph_xcorr(X, genes, graph=Wg), genes)
+        out["graph_xcorr_self"] = dict_to_matrix(
+            refg.target_graph_xcorr(X, genes, graph=Wg, aggr_params={"include_self": True}), genes)
+        assert np.allclose(orc.round5_dict_matrix(orc.graph_xcorr_np(X, Wg)), out["graph_xcorr"], atol=1e-12)
+        assert np.allclose(orc.round5_dict_matrix(orc.graph_xcorr_np(X, Wg, True)), out["graph_xcorr_self"], atol=1e-12)
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, f"{name}.npz")
     np.savez_compressed(path, **out)

@@ -20,6 +20,7 @@ import os
 import subprocess
 
 import numpy as np
+import scipy.sparse as _sp
 from scipy.sparse import issparse
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -323,6 +324,39 @@ def int_pearson_exact(V):
     with np.errstate(invalid="ignore", divide="ignore"):
         c = cov.astype(np.float64) / np.sqrt(np.outer(var.astype(np.float64), var.astype(np.float64)))
     return np.clip(c, -1.0, 1.0)
+
+
+def seeded_graph(n_cells, seed):
+    """Sparse neighbour graph with 0..6 weighted neighbours per cell (some cells isolated)."""
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for c in range(n_cells):
+        deg = int(rng.integers(0, 7))
+        nb = rng.choice(n_cells, size=deg, replace=False)
+        rows += [c] * deg
+        cols += nb.tolist()
+        vals += rng.choice([1.0, 1.0, 0.5, 2.0], size=deg).tolist()
+    return _sp.csr_matrix((vals, (rows, cols)), shape=(n_cells, n_cells), dtype=np.float64)
+
+
+def graph_xcorr_np(X, graph, include_self=False):
+    """target_graph_xcorr with aggr="mean" (genevector/_graph_targets.py:38-52 and
+    genevector/_aggregation.py:48-109) without the dict: float64 [G][G], zero diagonal."""
+    from scipy.sparse import diags
+    X_dense = np.asarray(_dense(X), dtype=np.float64)                   # _aggregation.py:66-84
+    row_sums = np.asarray(graph.sum(axis=1)).ravel()                    # :59-63
+    row_sums[row_sums == 0] = 1.0
+    W = diags(1.0 / row_sums) @ graph
+    X_agg = W @ X_dense                                                 # :105-106
+    if include_self:
+        X_agg = 0.5 * X_dense + 0.5 * X_agg                             # :107-108
+    n_cells = X_dense.shape[0]
+    X_std = (X_dense - X_dense.mean(axis=0)) / (X_dense.std(axis=0) + 1e-8)      # _graph_targets.py:45
+    X_agg_std = (X_agg - X_agg.mean(axis=0)) / (X_agg.std(axis=0) + 1e-8)        # :46
+    xcorr = (X_std.T @ X_agg_std) / n_cells                             # :48
+    sym = (xcorr + xcorr.T) / 2                                         # :49
+    np.fill_diagonal(sym, 0)
+    return np.asarray(sym)
 
 
 def cosine_np(X):

@@ -22,6 +22,9 @@ def load_golden(name):
     z = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     z["X"] = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
     z["n_bins"] = int(z["n_bins"])
+    if "graph_data" in z:
+        n = int(z["shape"][0])
+        z["graph"] = sp.csr_matrix((z["graph_data"], z["graph_indices"], z["graph_indptr"]), shape=(n, n))
     return z
 
 

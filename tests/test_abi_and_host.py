@@ -216,3 +216,19 @@ def test_sign_tiles_cover_every_pair_of_the_rank(monkeypatch):
                 m = ii < jj
                 assert cover[ii[m] // 256, jj[m] // 256].all()
             assert len(st) < 0.75 * len(E.tile_slice(G, 2, 8, 0, 1)[0]) or world == 2
+
+
+def test_graph_xcorr_argument_errors_match_the_reference():
+    """genevector/_graph_targets.py:38-42 and _aggregation.py:40-43: same exceptions, raised before
+    any device work."""
+    import pytest
+    from genevector_b200.metrics import target_graph_xcorr, TARGETS
+    assert "graph_xcorr" in TARGETS and "spearman" in TARGETS
+    X = np.array([[1, 2], [3, 4]], dtype=np.float64)
+    with pytest.raises(ValueError, match="graph required"):
+        target_graph_xcorr(X, ["a", "b"])
+    import scipy.sparse as sp
+    with pytest.raises(ValueError, match="Unknown aggregation"):
+        target_graph_xcorr(X, ["a", "b"], graph=sp.identity(2, format="csr"), aggr="nonexistent")
+    with pytest.raises(ValueError, match="callable"):
+        target_graph_xcorr(X, ["a", "b"], graph=sp.identity(2, format="csr"), aggr=lambda X, G, **kw: X)

@@ -188,3 +188,72 @@ def test_spearman_seeded_larger(engine):
         ok = ~np.isnan(raw)
         assert np.abs(s[ok] - raw[ok]).max() <= 1e-7
         assert np.array_equal(np.isnan(s), np.isnan(raw))
+
+
+# ------------------------------------------------------------------ graph cross-correlation
+@pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "synth_counts_700x96_b10",
+                                  "synth_counts_400x30_b15", "lognorm_f32_300x40_b7",
+                                  "lognorm_f64_300x40_b10"])
+def test_graph_xcorr_matches_reference(engine, case):
+    """target_graph_xcorr (genevector/_graph_targets.py:10-55, aggr="mean" with and without
+    include_self) against the reference's own output on a seeded neighbour graph with weights and
+    isolated cells."""
+    from genevector_b200.metrics import target_graph_xcorr, get_target_function
+    from oracle import oracle as orc
+    z = load_golden(case)
+    X, W = z["X"], z["graph"]
+    genes = [f"GENE{i}" for i in range(X.shape[1])]
+    assert get_target_function("graph_xcorr") is target_graph_xcorr
+    for key, params in (("graph_xcorr", None), ("graph_xcorr_self", {"include_self": True})):
+        s = target_graph_xcorr(X, genes, graph=W, aggr_params=params)
+        assert np.abs(s.rounded() - z[key]).max() <= ROUND_TOL, (case, key)
+        raw = orc.graph_xcorr_np(X, W, include_self=bool(params))
+        assert np.abs(s.matrix.astype(np.float64) - raw).max() <= F32_TOL, (case, key)
+        assert np.array_equal(s.matrix, s.matrix.T) and not np.diag(s.matrix).any()
+
+
+def test_graph_xcorr_reference_test_cases(engine):
+    """The structural checks of the reference's tests/test_graph_targets.py on non-negative data."""
+    from genevector_b200.metrics import target_graph_xcorr
+    from oracle import oracle as orc
+    adj = sp.csr_matrix(np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=np.float64))
+    X = np.array([[1, 0], [0, 2], [3, 1]], dtype=np.float64)
+    for Xin in (X, sp.csr_matrix(X)):
+        s = target_graph_xcorr(Xin, ["g0", "g1"], graph=adj)
+        assert "g0" in s and "g1" in s and "g0" not in s["g0"]
+        assert s["g0"]["g1"] == s["g1"]["g0"]
+        assert abs(s["g0"]["g1"] - round(float(orc.graph_xcorr_np(X, adj)[0, 1]), 5)) <= ROUND_TOL
+    # chain graph: A high in even cells, B in odd cells (the neighbours) -> |xcorr(A,B)| is large
+    n = 50
+    row = list(range(n - 1)) + list(range(1, n))
+    col = list(range(1, n)) + list(range(n - 1))
+    chain = sp.csr_matrix(([1.0] * len(row), (row, col)), shape=(n, n))
+    rng = np.random.default_rng(0)
+    Xc = np.column_stack([[5.0 if i % 2 == 0 else 0.0 for i in range(n)],
+                          [5.0 if i % 2 == 1 else 0.0 for i in range(n)], rng.random(n)])
+    s = target_graph_xcorr(Xc, ["A", "B", "C"], graph=chain)
+    assert abs(s["A"]["B"]) > abs(s["A"]["C"])
+    assert np.abs(s.matrix.astype(np.float64) - orc.graph_xcorr_np(Xc, chain)).max() <= F32_TOL
+    # values stay in [-1, 1]
+    Xr = rng.random((60, 12))
+    Wr = sp.csr_matrix(rng.integers(0, 2, size=(60, 60)).astype(np.float64))
+    s = target_graph_xcorr(Xr, [f"g{i}" for i in range(12)], graph=Wr)
+    assert np.abs(s.matrix).max() <= 1.0 + 1e-6
+    assert np.abs(s.matrix.astype(np.float64) - orc.graph_xcorr_np(Xr, Wr)).max() <= F32_TOL
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_graph_xcorr_several_tiles(engine, cg):
+    """350 genes: 2 x 5 tiles of the rectangle (256 count rows per A tile, 80 genes per B tile)."""
+    from genevector_b200.metrics import target_graph_xcorr
+    from genevector_b200.synth import synth_counts
+    from oracle import oracle as orc
+    X = synth_counts(1800, 350, seed=17)
+    W = orc.seeded_graph(1800, seed=5)
+    old = engine.cta_group
+    engine.cta_group = cg
+    try:
+        s = target_graph_xcorr(X, [f"g{i}" for i in range(350)], graph=W)
+    finally:
+        engine.cta_group = old
+    assert np.abs(s.matrix.astype(np.float64) - orc.graph_xcorr_np(X, W)).max() <= F32_TOL

@@ -94,3 +94,21 @@ def test_matrix_target_oracles():
 def test_gene_entropy_oracle_matches_reference(case):
     z = load_golden(case)
     assert np.array_equal(orc.gene_entropy_np(z["X"]), z["gene_entropy"], equal_nan=True)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_spearman_and_graph_xcorr_oracles_match_reference(case):
+    """scipy.stats.spearmanr as the reference calls it (metrics.py:423-431) and target_graph_xcorr
+    (_graph_targets.py:10-55, aggr mean with / without include_self) against the reference's output;
+    the integer rank rows the B200 path contracts reproduce spearmanr."""
+    z = load_golden(case)
+    if "spearman" not in z:
+        pytest.skip("no matrix targets in this case")
+    sp_np = orc.spearman_np(z["X"])
+    assert np.allclose(orc.round5_dict_matrix(sp_np), z["spearman"], atol=1e-12, equal_nan=True)
+    ri = orc.int_pearson_exact(orc.rank_rows_np(z["X"]))
+    ok = ~np.isnan(sp_np)
+    assert np.abs(ri[ok] - sp_np[ok]).max() < 1e-12 and np.array_equal(np.isnan(ri), np.isnan(sp_np))
+    assert np.allclose(orc.round5_dict_matrix(orc.graph_xcorr_np(z["X"], z["graph"])), z["graph_xcorr"], atol=1e-12)
+    assert np.allclose(orc.round5_dict_matrix(orc.graph_xcorr_np(z["X"], z["graph"], True)),
+                       z["graph_xcorr_self"], atol=1e-12)
