@@ -162,6 +162,46 @@ def test_c5_matrix_targets_sampled(engine):
         del out
 
 
+def test_c5_spearman_and_lognorm_targets_sampled(engine):
+    """configs[4] shape with the value-row modes beyond single-digit counts: Spearman (three rank
+    digits, 2*N = 200,000) and Pearson / signed-MI sign on log-normalised float32 input (three
+    fixed-point digits): 128-bit covariances and 63-bit co-moment sums at full size."""
+    from genevector_b200 import _lib
+    from genevector_b200.engine import CsrDevice
+    from oracle import oracle as orc
+    csr = _make(engine, 100000, 10000, seed=6)
+    rng = np.random.default_rng(6)
+    genes = np.sort(rng.choice(10000, size=32, replace=False))
+    gi = torch.as_tensor(genes, device=engine.device)
+    D = _dense_columns(csr, genes)
+    out = engine.target_from_csr(csr, _lib.GV_MOM_PEARSON, ranks=True)
+    got = out[gi][:, gi].cpu().numpy().astype(np.float64)
+    want = orc.spearman_np(D); np.fill_diagonal(want, 0.0)
+    assert np.abs(got - want).max() <= 1e-6, np.abs(got - want).max()
+    idx = torch.arange(0, 10000, 7, device=out.device)
+    assert torch.equal(out[idx][:, idx], out[idx][:, idx].T)
+    del out
+    # log-normalised values: log1p(count / cell total * 1e4), computed on the device
+    tot = torch.zeros(csr.n_cells, dtype=torch.float32, device=engine.device)
+    rows = torch.repeat_interleave(torch.arange(csr.n_cells, device=engine.device),
+                                   csr.row_ptr[1:] - csr.row_ptr[:-1])
+    tot.index_add_(0, rows, csr.values)
+    vals = torch.log1p(csr.values / (tot[rows] + 1.0) * 1e4)
+    csr_l = CsrDevice(vals, csr.col_idx, csr.row_ptr, csr.n_cells, csr.n_genes)
+    blk = engine.discretize(csr_l, 10, val_mode=0)
+    assert (blk.val_mode, blk.n_limbs) == (2, 3) and blk.path_used == _lib.GV_PATH_GENERAL
+    Dl = _dense_columns(csr_l, genes)
+    xd, nb = orc.discretize_genes_c(Dl, 10)
+    assert np.array_equal(_unpack_rows(blk, genes).T.astype(np.int32), xd)
+    p = engine.moment_scores(blk, _lib.GV_MOM_PEARSON)
+    got = p[gi][:, gi].cpu().numpy().astype(np.float64)
+    want = orc.pearson_np(Dl); np.fill_diagonal(want, 0.0)
+    assert np.abs(got - want).max() <= 2e-6, np.abs(got - want).max()
+    sgn = engine.sign_matrix(blk)[gi][:, gi].cpu().numpy()
+    ref_sign = np.sign(orc.pearson_sign_np(Dl)).astype(np.int8); np.fill_diagonal(ref_sign, 0)
+    assert np.array_equal(sgn, ref_sign)
+
+
 def test_c1_pbmc_like_full_vs_oracle_and_training_handoff(engine):
     """configs[0] stand-in (example/PBMC.h5ad is a missing blob): 1,000 genes x 13,000 cells,
     seed 42; every pair against the oracle, then the hand-off to the trainer: the (i_idx, j_idx,
