@@ -350,9 +350,13 @@ def main():
         if rank == 0:
             c = CsrDevice(host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
                           host[2].to(dev, non_blocking=True), N, G)
-        eng.mi_from_csr(c, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out)
-        if g_hi > g_lo:
-            res_host[:g_hi - g_lo].copy_(out[g_lo:g_hi], non_blocking=True)
+        if world == 1:
+            # single rank: the result rows stream to the pinned host matrix under the computation
+            eng.mi_from_csr(c, N, G, n_bins=N_BINS, signed=signed, out=out, out_host=res_host)
+        else:
+            eng.mi_from_csr(c, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out)
+            if g_hi > g_lo:
+                res_host[:g_hi - g_lo].copy_(out[g_lo:g_hi], non_blocking=True)
 
     def timed(fn, steps):
         barrier()

@@ -440,8 +440,15 @@ class Engine:
 
     def mi_scores(self, blk: BinBlock, onehot: torch.Tensor, B: int,
                   sgn: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                  rank: int = 0, world: int = 1) -> torch.Tensor:
-        """float32 [G][G] MI (times the Pearson sign when `sgn` is given)."""
+                  rank: int = 0, world: int = 1, out_host: Optional[torch.Tensor] = None,
+                  host_chunks: int = 6) -> torch.Tensor:
+        """float32 [G][G] MI (times the Pearson sign when `sgn` is given).
+
+        out_host (pinned float32 [G][G], single rank): the result is streamed to the host while it
+        is computed.  The tile schedule walks the triangle band by band, and a tile of band b only
+        writes rows of bands >= b, so once the tiles of a band have run its rows are final: the
+        schedule is launched in `host_chunks` pieces cut at band boundaries and every finished piece
+        is copied on a second stream under the next one."""
         with torch.cuda.device(self.device):
             G = blk.n_genes
             if out is None:
@@ -449,11 +456,48 @@ class Engine:
             rows, row_bytes = onehot.shape
             fmt = _lib.GV_OPERAND_FP4 if onehot.dtype == torch.uint8 else _lib.GV_OPERAND_INT8
             tiles, n, _ = self.schedule(rows, rank=rank, world=world)
-            self._call("gv_mi_tiles", onehot.data_ptr(), rows, row_bytes, B, blk.marg.data_ptr(),
-                      sgn.data_ptr() if sgn is not None else None,
-                      sgn.stride(0) if sgn is not None else 0, G, tiles.data_ptr(), n,
-                      out.data_ptr(), out.stride(0), self.cta_group, fmt,
-                      self._sync_ptr(rows * row_bytes), self._stream())
+
+            def launch(t0, t1):
+                self._call("gv_mi_tiles", onehot.data_ptr(), rows, row_bytes, B, blk.marg.data_ptr(),
+                           sgn.data_ptr() if sgn is not None else None,
+                           sgn.stride(0) if sgn is not None else 0, G, tiles.data_ptr() + 8 * t0, t1 - t0,
+                           out.data_ptr(), out.stride(0), self.cta_group, fmt,
+                           self._sync_ptr(rows * row_bytes), self._stream())
+
+            if out_host is None or world > 1 or n == 0:
+                launch(0, n)
+                if out_host is not None:
+                    out_host.copy_(out, non_blocking=True)
+                return out
+            # cut points: first tiles of bands, nearest to equal shares of the schedule
+            key = ("cuts", rows, self.cta_group, self.band, host_chunks)
+            if key not in self._sched_cache:
+                th, _ = tile_slice(rows, self.cta_group, self.band)
+                tm = _lib.call("gv_tile_m", self.cta_group)
+                band_of = th[:, 0] // (tm * self.band)
+                starts = np.flatnonzero(np.diff(band_of, prepend=-1))          # first tile of each band
+                cuts = sorted({int(starts[np.abs(starts - n * k // host_chunks).argmin()])
+                               for k in range(1, host_chunks)} - {0})
+                gpb = 32 // B
+                genes_at = [min(G, int(th[c, 0]) // 32 * gpb) for c in cuts]    # first gene of the band
+                self._sched_cache[key] = (cuts + [n], genes_at + [G])
+            cuts, gene_ends = self._sched_cache[key]
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            t0, g0 = 0, 0
+            for t1, g1 in zip(cuts, gene_ends):
+                launch(t0, t1)
+                if g1 > g0:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self._copy_stream.wait_event(ev)
+                    with torch.cuda.stream(self._copy_stream):
+                        out_host[g0:g1].copy_(out[g0:g1], non_blocking=True)
+                t0, g0 = t1, g1
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+            main.wait_event(done)
             return out
 
     # ------------------------------------------------------------------ graph cross-correlation
@@ -553,7 +597,8 @@ class Engine:
 
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
                     signed: bool = False, rank: int = 0, world: int = 1, group=None,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None,
+                    out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All-pairs (signed) MI.  With world > 1 only rank 0 needs `csr`; each rank returns a
         [G][G] matrix in which the entries of its own tiles are filled."""
         import torch.distributed as dist
@@ -579,7 +624,7 @@ class Engine:
                 st = self._sched_cache[key]
             sgn = self.sign_matrix(blk, tiles=st)
         onehot, B = self.expand_onehot(blk)
-        return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world)
+        return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, out_host=out_host)
 
     def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,
                         n_cells: Optional[int] = None, n_genes: Optional[int] = None,

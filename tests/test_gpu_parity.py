@@ -437,3 +437,18 @@ def test_fp4_operand_seeded_vs_oracle(engine):
     finally:
         engine.operand = old
     assert np.abs(out.astype(np.float64) - want).max() <= MI_TOL
+
+
+def test_streamed_host_result_equals_device_result(engine):
+    """mi_from_csr(out_host=...): the result rows are copied band by band under the computation;
+    the pinned host matrix must equal the device matrix and the one-launch result."""
+    import torch
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(1500, 2600, seed=23)          # 867 blocks -> 109 tile rows = 14 bands
+    csr = engine.upload_csr(X)
+    ref = engine.mi_from_csr(csr, 1500, 2600, signed=True)
+    host = torch.full((2600, 2600), float("nan"), dtype=torch.float32).pin_memory()
+    out = engine.mi_from_csr(csr, 1500, 2600, signed=True, out_host=host)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert torch.equal(host, ref.cpu())
