@@ -98,13 +98,18 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
   cfg.blockDim = dim3(GRAM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // the wave barrier spins on all clusters of the grid: ask for a cooperative launch so that the
+  // grid is only started when every CTA can be resident at once (a launch error instead of a hang
+  // if something else holds SMs)
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = sync_ws != nullptr ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, map, map_b, ga, ep);
   if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
   return GV_OK;
