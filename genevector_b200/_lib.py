@@ -21,6 +21,7 @@ GV_VAL_COUNTS, GV_VAL_DETECTED, GV_VAL_FIXED_POINT, GV_VAL_RANKS = 0, 1, 2, 3
 GV_MARG_STRIDE = 16
 GV_EDGE_STRIDE = 16
 GV_EDGE_SCALE_SLOT = 15
+GV_EDGE_OFFSET_SLOT = 14
 GV_QTABLE_DIM = 16
 GV_ABI_VERSION = 4
 GV_OPERAND_INT8, GV_OPERAND_FP4 = 0, 1
@@ -56,13 +57,13 @@ SIGNATURES = {
                            _i32, _i32, _vp, _vp]),
     "gv_gram_dump": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "gv_tile_schedule_rect": (_i64, [_i64, _i64, _i32, _vp, _i64]),
-    "gv_graph_aggregate": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32,
+    "gv_graph_aggregate": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32,
                                   _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "gv_xcorr_tiles": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                               _i64, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_symmetrize": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "gv_mma_peak": (_i32, [_i32, _i32, _i32, _vp, _vp]),
-    "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
+    "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),
 }

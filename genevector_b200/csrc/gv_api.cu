@@ -51,7 +51,7 @@ int mi_tiles_dispatch(const void*, int64_t, int64_t, int, const int32_t*, const 
 int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, int32_t*, int64_t, int,
                        int, int, cudaStream_t);
 int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
-                          const int32_t*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
+                          const int32_t*, const double*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
                           int64_t, float*, int64_t, int, void*, cudaStream_t);
 
 int mma_peak_dispatch(int, int, int, double*, cudaStream_t);
@@ -59,7 +59,7 @@ int xcorr_tiles_dispatch(const void*, int64_t, int, const void*, int64_t, int, i
                          const int64_t*, const double*, int64_t, const int64_t*, const int64_t*,
                          const double*, int64_t, int, const int32_t*, int64_t, float*, int64_t, int, void*,
                          cudaStream_t);
-int graph_aggregate_dispatch(const void*, int64_t, int, int, const double*, int64_t, const int64_t*,
+int graph_aggregate_dispatch(const void*, int64_t, int, int, const double*, const double*, int64_t, const int64_t*,
                              const int32_t*, const double*, double*, int, int64_t, int, void*, int64_t, int,
                              int64_t*, int64_t*, double*, cudaStream_t);
 int symmetrize_dispatch(const float*, int64_t, int, float*, int64_t, cudaStream_t);
@@ -217,7 +217,8 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t
 }
 
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
-                    const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
+                    const int64_t* gsum, const int64_t* gsq, const int32_t* marg, const double* edges,
+                    int64_t n_cells,
                     int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
                     int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
                     void* sync_ws, void* stream) {
@@ -228,7 +229,7 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
     return set_error(GV_ERR_ARG, "gv_moment_tiles: bad argument");
   if ((sgn && ld_sgn < n_genes) || (out && ld_out < n_genes))
     return set_error(GV_ERR_ARG, "gv_moment_tiles: leading dimension < n_genes");
-  return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, n_cells, n_genes, n_limbs,
+  return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, edges, n_cells, n_genes, n_limbs,
                                limb_bits, tiles, n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
                                static_cast<cudaStream_t>(stream));
 }
@@ -250,7 +251,8 @@ int64_t gv_tile_schedule_rect(int64_t rows_a, int64_t rows_b, int tile_m, int32_
 }
 
 int gv_graph_aggregate(const void* x_rows, int64_t op_rows_x, int64_t kp, int x_limbs, int limb_bits,
-                       const double* x_scale, int64_t x_scale_stride, const int64_t* w_row_ptr,
+                       const double* x_scale, const double* x_offset, int64_t x_scale_stride,
+                       const int64_t* w_row_ptr,
                        const int32_t* w_col, const double* w_val, double* w_inv_ws, int include_self,
                        int64_t n_cells, int n_genes, void* y_rows, int64_t op_rows_y, int y_limbs,
                        int64_t* ysum, int64_t* ysq, double* yscale, void* stream) {
@@ -262,7 +264,7 @@ int gv_graph_aggregate(const void* x_rows, int64_t op_rows_x, int64_t kp, int x_
     return set_error(GV_ERR_ARG, "gv_graph_aggregate: bad argument");
   if (op_rows_x < gv_value_rows(n_genes, x_limbs) || op_rows_y < gv_value_rows(n_genes, y_limbs))
     return set_error(GV_ERR_ARG, "gv_graph_aggregate: value rows too short");
-  return graph_aggregate_dispatch(x_rows, kp, x_limbs, limb_bits, x_scale, x_scale_stride, w_row_ptr, w_col,
+  return graph_aggregate_dispatch(x_rows, kp, x_limbs, limb_bits, x_scale, x_offset, x_scale_stride, w_row_ptr, w_col,
                                   w_val, w_inv_ws, include_self, n_cells, n_genes, y_rows, op_rows_y,
                                   y_limbs, ysum, ysq, yscale, static_cast<cudaStream_t>(stream));
 }

@@ -973,6 +973,131 @@ __global__ void k_gene_entropy(const uint32_t* __restrict__ hist, int G, int64_t
   }
 }
 
+// ================================================================ signed fixed-point value rows
+// Data with negative values (centred / scaled matrices): the discretisation still treats x <= 0 as
+// "not expressed" (metrics.py:53), but the correlation-type scores use the raw values.  Pearson, its
+// sign and the cross-correlation do not change when a gene is shifted, so the value rows hold
+// rint((x - o_g) * 2^e_g) >= 0 with o_g = min(0, min_g x): the cells without a CSR entry (x = 0) all
+// hold q0_g = rint(-o_g * 2^e_g), written by a row fill before the stored entries are scattered.
+// edges[g][14] carries q0_g (cosine, which is not shift-invariant, subtracts it again) and
+// edges[g][15] the unit 2^-e_g.
+constexpr int EDGE_OFFSET_SLOT = 14;   // GV_EDGE_OFFSET_SLOT
+
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_val(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+struct SignedGene {            // per-gene scratch of the signed path
+  unsigned long long min_key, max_key;
+  double offset;               // o_g <= 0
+  long long q0;
+  unsigned long long acc1, acc2;   // Sum (q - q0), Sum (q^2 - q0^2) over stored entries (wrapping)
+  int shift, pad;
+};
+
+__global__ void k_signed_init(SignedGene* __restrict__ sg, int G) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+    sg[g].min_key = ~0ull; sg[g].max_key = 0ull; sg[g].acc1 = 0ull; sg[g].acc2 = 0ull;
+  }
+}
+
+template <typename T>
+__global__ void k_gene_minmax(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+                              int64_t nnz, SignedGene* __restrict__ sg) {
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const unsigned long long k = ordered_key(double(values[e]));
+    SignedGene* s = sg + col_idx[e];
+    if (k < *(volatile unsigned long long*)&s->min_key) atomicMin(&s->min_key, k);
+    if (k > *(volatile unsigned long long*)&s->max_key) atomicMax(&s->max_key, k);
+  }
+}
+
+__global__ void k_signed_params(SignedGene* __restrict__ sg, int G, int total_bits,
+                                double* __restrict__ edges_out) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+    SignedGene s = sg[g];
+    double lo = 0.0, hi = 0.0;
+    if (s.max_key != 0ull) { lo = ordered_val(s.min_key); hi = ordered_val(s.max_key); }
+    const double o = lo < 0.0 ? lo : 0.0;
+    const double top = (hi > 0.0 ? hi : 0.0) - o;      // largest shifted value (implicit zeros included)
+    int shift = 0; long long q0 = 0;
+    if (top > 0.0) {
+      int ex; frexp(top, &ex);
+      shift = total_bits - ex;
+      q0 = llrint(ldexp(-o, shift));
+      const long long cap = (1ll << total_bits) - 1ll;
+      q0 = q0 > cap ? cap : q0;
+    }
+    sg[g].offset = o; sg[g].shift = shift; sg[g].q0 = q0;
+    edges_out[int64_t(g) * 16 + EDGE_OFFSET_SLOT] = q0 ? double(q0) : DBL_MAX;
+    edges_out[int64_t(g) * 16 + EDGE_SCALE_SLOT] = ldexp(1.0, -shift);
+  }
+}
+
+// every cell of the gene's rows gets the digits of q0 (16 cells per thread); cells >= n_cells stay 0
+__global__ void k_signed_fill(const SignedGene* __restrict__ sg, int G, int64_t n_cells,
+                              int8_t* __restrict__ val_rows, int64_t val_pitch, int n_limbs,
+                              int limb_bits) {
+  const unsigned mask = (1u << limb_bits) - 1u;
+  for (int g = blockIdx.y; g < G; g += gridDim.y) {
+    const long long q0 = sg[g].q0;
+    if (q0 == 0) continue;
+    int8_t* base = val_rows + val_row0(g, n_limbs) * val_pitch;
+    for (int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 16; c < n_cells;
+         c += int64_t(gridDim.x) * blockDim.x * 16) {
+      for (int l = 0; l < n_limbs; ++l) {
+        const unsigned d = unsigned(q0 >> (l * limb_bits)) & mask;
+        int8_t* p = base + int64_t(l) * val_pitch + c;
+        if (c + 16 <= n_cells) {
+          const uint32_t w = d * 0x01010101u;
+          *reinterpret_cast<uint4*>(p) = make_uint4(w, w, w, w);
+        } else {
+          for (int64_t k = c; k < n_cells; ++k) p[k - c] = int8_t(d);
+        }
+      }
+    }
+  }
+}
+
+// one warp per CSR row: every stored entry (any sign, explicit zeros too) overwrites its cell
+template <typename T>
+__global__ void k_signed_scatter(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+                                 const int64_t* __restrict__ row_ptr, int64_t n_cells,
+                                 SignedGene* __restrict__ sg, int8_t* __restrict__ val_rows,
+                                 int64_t val_pitch, int n_limbs, int limb_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const long long cap = (1ll << (n_limbs * limb_bits)) - 1ll;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < n_cells; r += warps) {
+    const int64_t e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+      const int g = col_idx[e];
+      SignedGene* s = sg + g;
+      long long q = llrint(ldexp(__dsub_rn(double(values[e]), s->offset), s->shift));
+      q = q < 0 ? 0 : (q > cap ? cap : q);
+      write_digits(val_rows, val_pitch, g, r, (unsigned long long)q, n_limbs, limb_bits);
+      const long long q0 = s->q0;
+      atomicAdd(&s->acc1, (unsigned long long)(q - q0));
+      atomicAdd(&s->acc2, (unsigned long long)(q * q - q0 * q0));
+    }
+  }
+}
+
+__global__ void k_signed_finish(const SignedGene* __restrict__ sg, int G, int64_t n_cells,
+                                int64_t* __restrict__ gsum, int64_t* __restrict__ gsq) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+    const long long q0 = sg[g].q0;
+    gsum[g] = n_cells * q0 + (long long)sg[g].acc1;
+    gsq[g] = n_cells * q0 * q0 + (long long)sg[g].acc2;
+  }
+}
+
 // ================================================================ host-side launchers
 #define GV_LAUNCH_CHECK()                                     \
   do {                                                        \
@@ -993,9 +1118,10 @@ static int check_val_config(const DiscretizeArgs& a, const unsigned long long* h
   if (n_limbs < 1 || n_limbs > 4 || limb_bits < 1 || limb_bits > 7)
     return set_error(GV_ERR_ARG, "value rows: n_limbs must be in [1,4] and limb_bits in [1,7]");
   const int tb = n_limbs * limb_bits;
-  if (hflags[0] & 1ull)
+  if ((hflags[0] & 1ull) && a.val_mode != 2)
     return set_error(GV_ERR_UNSUPPORTED,
-                     "co-moment path needs non-negative values (negative values found)");
+                     "count / rank value rows need non-negative values (negative values found): "
+                     "use the fixed-point value rows (val_mode 2)");
   if (a.val_mode == 0) {
     if (hflags[0] & 2ull)
       return set_error(GV_ERR_UNSUPPORTED,
@@ -1135,11 +1261,37 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     if (rc != GV_OK) return rc;
     g_cell = s_cell; g_val = s_val;
   }
+  // negative values: the value rows come from the signed fixed-point kernels below instead
+  const bool signed_rows = val_rows != nullptr && a.val_mode == 2 && (hflags[0] & 1ull);
   k_gene_bins<T><<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, 0, st>>>(
       gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
-      int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
-      a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, a.n_cells);
+      int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq,
+      signed_rows ? nullptr : val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, a.n_cells);
   GV_LAUNCH_CHECK();
+  if (signed_rows) {
+    SignedGene* sg = static_cast<SignedGene*>(take(size_t(G) * sizeof(SignedGene)));
+    if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
+    const int gb = (G + 255) / 256;
+    k_signed_init<<<gb, 256, 0, st>>>(sg, G);
+    GV_LAUNCH_CHECK();
+    if (a.nnz > 0) {
+      k_gene_minmax<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, sg);
+      GV_LAUNCH_CHECK();
+    }
+    k_signed_params<<<gb, 256, 0, st>>>(sg, G, n_limbs * a.val_limb_bits, a.edges);
+    GV_LAUNCH_CHECK();
+    if (a.n_cells > 0) {
+      dim3 fgrid(unsigned((a.n_cells + 4095) / 4096 < 64 ? (a.n_cells + 4095) / 4096 : 64),
+                 unsigned(G < 65535 ? G : 65535));
+      k_signed_fill<<<fgrid, 256, 0, st>>>(sg, G, a.n_cells, val_rows, a.val_pitch, n_limbs, a.val_limb_bits);
+      GV_LAUNCH_CHECK();
+      k_signed_scatter<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, sg, val_rows,
+                                                    a.val_pitch, n_limbs, a.val_limb_bits);
+      GV_LAUNCH_CHECK();
+    }
+    k_signed_finish<<<gb, 256, 0, st>>>(sg, G, a.n_cells, a.gsum, a.gsq);
+    GV_LAUNCH_CHECK();
+  }
   if (a.path_used) *a.path_used = GV_PATH_GENERAL;
   return GV_OK;
 }
@@ -1269,7 +1421,7 @@ size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value
   const size_t counts = al256(size_t(G) * kcells) + al256(size_t(G) * VH * 4);
   const size_t entropy = al256(size_t(G) * VH * 4);
   size_t general = al256(size_t(G) * 4) + al256(size_t(G) * 8) + al256(size_t(G + 1) * 8) +
-                   al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs);
+                   al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs) + al256(size_t(G) * sizeof(SignedGene));
   if (sorted)
     general += al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs) + al256(segsort_temp_bytes(nnz, G, value_dtype));
   size_t m = counts > general ? counts : general;

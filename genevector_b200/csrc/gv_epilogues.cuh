@@ -239,6 +239,7 @@ struct MomentParams {
   const int64_t* gsum;   // [G] Sum_c x            (sign / pearson / cosine)
   const int64_t* gsq;    // [G] Sum_c x^2          (sign / pearson / cosine)
   const int32_t* marg;   // [G][MARG_STRIDE], [0] = #cells with x>0 (jaccard)
+  const double* edges;   // [G][16] or nullptr: slot 14 = value-row integer of a zero cell (cosine)
   int8_t* sgn;           // [G][ld_sgn]  (MOM_SIGN)
   int64_t ld_sgn;
   float* out;            // [G][ld_out]  (other kinds)
@@ -274,6 +275,7 @@ struct MomentEpi {
   struct Meta {
     int64_t csum[GENES_PER_TILE];
     int64_t csq[GENES_PER_TILE];
+    int64_t coff[GENES_PER_TILE];
   };
   static constexpr size_t SMEM_BYTES = sizeof(Meta) + 16;
   static constexpr int ACTIVE_ROWS = 32;
@@ -282,6 +284,12 @@ struct MomentEpi {
   Meta* meta;
   __device__ MomentEpi(const Params& p_, uint8_t* smem) : p(p_) {
     meta = reinterpret_cast<Meta*>(smem);
+  }
+  // value-row integer of the gene's zero cells (genes with negative values are stored shifted)
+  __device__ int64_t zero_offset(int g) const {
+    if (p.edges == nullptr) return 0;
+    const double o = p.edges[int64_t(g) * 16 + 14];
+    return o < 1e300 ? int64_t(o) : 0;
   }
   __device__ void prepare(const EpiTile& et) {
     epi_bar_sync();
@@ -294,6 +302,7 @@ struct MomentEpi {
       } else {
         meta->csum[c] = gj < p.G ? p.gsum[gj] : 0;
         meta->csq[c] = gj < p.G ? p.gsq[gj] : 0;
+        if constexpr (KIND == MOM_COSINE) meta->coff[c] = gj < p.G ? zero_offset(gj) : 0;
       }
     }
     epi_bar_sync();
@@ -314,6 +323,12 @@ struct MomentEpi {
     }
     const i128 n = i128(p.n_cells);
     const i128 var_i = n * sxx - i128(sx) * sx;
+    int64_t ox = 0;
+    i128 txx = 0;
+    if constexpr (KIND == MOM_COSINE) {
+      ox = row_ok ? zero_offset(gi) : 0;
+      txx = i128(sxx) - 2 * i128(ox) * sx + n * ox * ox;
+    }
     const int lb = p.limb_bits;
 #pragma unroll 1
     for (int cbi = 0; cbi < 4; ++cbi) {
@@ -357,9 +372,13 @@ struct MomentEpi {
               q = q > 1.0 ? 1.0 : (q < -1.0 ? -1.0 : q);
               r = float(q);
             } else if constexpr (KIND == MOM_COSINE) {
-              const int64_t syy = meta->csq[cg];
-              r = (sxx == 0 || syy == 0) ? 0.0f
-                                         : float(double(sxy) / sqrt(double(sxx) * double(syy)));
+              // cosine is not shift-invariant: undo the per-gene offsets (zero for non-negative data)
+              const int64_t oy = meta->coff[cg];
+              const i128 txy = i128(sxy) - i128(oy) * sx - i128(ox) * sy + n * ox * oy;
+              const i128 tyy = i128(meta->csq[cg]) - 2 * i128(oy) * sy + n * oy * oy;
+              r = (txx == 0 || tyy == 0)
+                      ? 0.0f
+                      : float(i128_to_double(txy) / sqrt(i128_to_double(txx) * i128_to_double(tyy)));
             } else {  // JACCARD: float32 division of exact integers, as metrics.py:443-447
               int64_t uni = sx + sy - sxy;
               if (uni == 0) uni = 1;

@@ -43,22 +43,26 @@ constexpr int GA_THREADS = 256;
 
 __global__ void __launch_bounds__(GA_THREADS)
 k_graph_aggregate(const int8_t* __restrict__ xrows, int64_t pitch, int lx, int limb_bits,
-                  const double* __restrict__ xscale, int64_t xscale_stride,
-                  const int64_t* __restrict__ w_ptr, const int32_t* __restrict__ w_col,
+                  const double* __restrict__ xscale, const double* __restrict__ xoffset,
+                  int64_t xscale_stride, const int64_t* __restrict__ w_ptr, const int32_t* __restrict__ w_col,
                   const double* __restrict__ w_val, const double* __restrict__ w_inv, int include_self,
                   int64_t n_cells, int G, int8_t* __restrict__ yrows, int ly,
                   int64_t* __restrict__ ysum, int64_t* __restrict__ ysq, double* __restrict__ yscale) {
-  __shared__ double red_d[GA_THREADS / 32];
+  __shared__ double red_d[GA_THREADS / 32][2];
+  __shared__ double s_off;
   __shared__ long long red_i[GA_THREADS / 32][2];
   __shared__ int s_shift;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned dmask = (1u << limb_bits) - 1u;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int8_t* xr = xrows + vrow0(g, lx) * pitch;
+    // genes with negative values are stored shifted by q0 (GV_EDGE_OFFSET_SLOT; DBL_MAX = none)
+    double q0x = 0.0;
+    if (xoffset != nullptr) { const double o = xoffset[int64_t(g) * xscale_stride]; q0x = o < 1e300 ? o : 0.0; }
     auto xval = [&](int64_t c) -> double {
       unsigned long long v = 0;
       for (int l = 0; l < lx; ++l) v |= (unsigned long long)(uint8_t(xr[int64_t(l) * pitch + c])) << (l * limb_bits);
-      return double(v);
+      return double(v) - q0x;
     };
     auto yval = [&](int64_t c) -> double {
       double acc = 0.0;
@@ -68,29 +72,41 @@ k_graph_aggregate(const int8_t* __restrict__ xrows, int64_t pitch, int lx, int l
       if (include_self) acc = __dadd_rn(__dmul_rn(0.5, xval(c)), __dmul_rn(0.5, acc));
       return acc;
     };
-    // ---- sweep 1: largest aggregated value of the gene
-    double mx = 0.0;
-    for (int64_t c = tid; c < n_cells; c += GA_THREADS) { const double y = yval(c); mx = y > mx ? y : mx; }
-    for (int d = 16; d >= 1; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, d); mx = o > mx ? o : mx; }
+    // ---- sweep 1: range of the aggregated values of the gene
+    double mx = 0.0, mn = 0.0;
+    for (int64_t c = tid; c < n_cells; c += GA_THREADS) {
+      const double y = yval(c);
+      mx = y > mx ? y : mx; mn = y < mn ? y : mn;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, mx, d); mx = o > mx ? o : mx;
+      const double u = __shfl_xor_sync(0xffffffffu, mn, d); mn = u < mn ? u : mn;
+    }
     __syncthreads();
-    if (lane == 0) red_d[warp] = mx;
+    if (lane == 0) { red_d[warp][0] = mx; red_d[warp][1] = mn; }
     __syncthreads();
     if (tid == 0) {
-      double m = 0.0;
-      for (int w = 0; w < GA_THREADS / 32; ++w) m = red_d[w] > m ? red_d[w] : m;
+      double m = 0.0, lo = 0.0;
+      for (int w = 0; w < GA_THREADS / 32; ++w) {
+        m = red_d[w][0] > m ? red_d[w][0] : m;
+        lo = red_d[w][1] < lo ? red_d[w][1] : lo;
+      }
       int ex = 0;
-      if (m > 0.0) frexp(m, &ex);
-      s_shift = m > 0.0 ? ly * limb_bits - ex : 0;
+      if (m - lo > 0.0) frexp(m - lo, &ex);
+      s_shift = (m - lo) > 0.0 ? ly * limb_bits - ex : 0;
+      s_off = lo;                                   // <= 0; the rows hold rint((y - lo) * 2^shift)
     }
     __syncthreads();
     const int shift = s_shift;
+    const double yoff = s_off;
     const unsigned long long cap = (1ull << (ly * limb_bits)) - 1ull;
     // ---- sweep 2: fixed-point digits, sums
     long long s1 = 0, s2 = 0;
     int8_t* yr = yrows + vrow0(g, ly) * pitch;
     for (int64_t c = tid; c < n_cells; c += GA_THREADS) {
       const double y = yval(c);
-      unsigned long long q = y > 0.0 ? (unsigned long long)llrint(ldexp(y, shift)) : 0ull;
+      const double ys = y - yoff;
+      unsigned long long q = ys > 0.0 ? (unsigned long long)llrint(ldexp(ys, shift)) : 0ull;
       q = q > cap ? cap : q;
       s1 += (long long)q; s2 += (long long)(q * q);
       for (int l = 0; l < ly; ++l) yr[int64_t(l) * pitch + c] = int8_t((q >> (l * limb_bits)) & dmask);
@@ -112,7 +128,8 @@ k_graph_aggregate(const int8_t* __restrict__ xrows, int64_t pitch, int lx, int l
 }
 
 int graph_aggregate_dispatch(const void* x_rows, int64_t kp, int x_limbs, int limb_bits,
-                             const double* x_scale, int64_t x_scale_stride, const int64_t* w_ptr,
+                             const double* x_scale, const double* x_offset, int64_t x_scale_stride,
+                             const int64_t* w_ptr,
                              const int32_t* w_col, const double* w_val, double* w_inv_ws,
                              int include_self, int64_t n_cells, int G, void* y_rows, int64_t y_rows_alloc,
                              int y_limbs, int64_t* ysum, int64_t* ysq, double* yscale, cudaStream_t st) {
@@ -124,7 +141,7 @@ int graph_aggregate_dispatch(const void* x_rows, int64_t kp, int x_limbs, int li
     GV_LAUNCH_CHECK_G();
   }
   k_graph_aggregate<<<G < sms * 8 ? G : sms * 8, GA_THREADS, 0, st>>>(
-      static_cast<const int8_t*>(x_rows), kp, x_limbs, limb_bits, x_scale, x_scale_stride, w_ptr, w_col,
+      static_cast<const int8_t*>(x_rows), kp, x_limbs, limb_bits, x_scale, x_offset, x_scale_stride, w_ptr, w_col,
       w_val, w_inv_ws, include_self, n_cells, G, static_cast<int8_t*>(y_rows), y_limbs, ysum, ysq, yscale);
   GV_LAUNCH_CHECK_G();
   return GV_OK;

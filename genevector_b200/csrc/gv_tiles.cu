@@ -185,11 +185,11 @@ static int moment_dispatch_l(int kind, int cta_group, const void* val_rows, int6
 
 int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                           const int64_t* gsum, const int64_t* gsq, const int32_t* marg,
-                          int64_t n_cells, int n_genes, int n_limbs, int limb_bits,
+                          const double* edges, int64_t n_cells, int n_genes, int n_limbs, int limb_bits,
                           const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
                           float* out, int64_t ld_out, int cta_group, void* sync_ws, cudaStream_t st) {
   MomentParams p;
-  p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
+  p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.edges = edges; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
   p.ld_out = ld_out; p.G = n_genes; p.n_cells = n_cells; p.limb_bits = limb_bits;
   if (kind == GV_MOM_SIGN && (!sgn || !gsum || !gsq)) return set_error(GV_ERR_ARG, "sign needs sgn, gsum, gsq");
   if ((kind == GV_MOM_PEARSON || kind == GV_MOM_COSINE) && (!out || !gsum || !gsq))

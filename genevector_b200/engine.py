@@ -318,10 +318,10 @@ class Engine:
                                self._stream())
                 except GvError as e:
                     negative, fractional = int(flags[0]) & 1, int(flags[0]) & 2
-                    if not (auto and mode == 0 and e.status == -4) or negative:
+                    if not (auto and mode == 0 and e.status == -4):
                         raise
                     need = -(-int(flags[1]).bit_length() // lb)      # digits the largest count needs
-                    if fractional or need > l_max:
+                    if fractional or negative or need > l_max:
                         if l_fixed < 1:
                             raise
                         mode, L = 2, l_fixed       # not counts (or too large): fixed-point rows
@@ -417,7 +417,8 @@ class Engine:
             else:
                 n = int(tiles.shape[0])
             self._call("gv_moment_tiles", _lib.GV_MOM_SIGN, blk.val_rows.data_ptr(), rows, blk.kp,
-                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
+                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.edges.data_ptr(),
+                       blk.n_cells, G,
                        blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0,
                        self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
             return sgn
@@ -433,7 +434,8 @@ class Engine:
             rows = value_rows(G, blk.n_limbs)
             tiles, n, _ = self.schedule(rows, rank=rank, world=world)
             self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), rows, blk.kp,
-                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.n_cells, G,
+                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.edges.data_ptr(),
+                       blk.n_cells, G,
                        blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, None, 0, out.data_ptr(),
                        out.stride(0), self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
             return out
@@ -542,8 +544,9 @@ class Engine:
             yscale = torch.empty(G, dtype=torch.float64, device=self.device)
             w_inv = torch.empty(max(N, 1), dtype=torch.float64, device=self.device)
             xscale_ptr = blk.edges.data_ptr() + 8 * _lib.GV_EDGE_SCALE_SLOT
+            xoff_ptr = blk.edges.data_ptr() + 8 * _lib.GV_EDGE_OFFSET_SLOT
             self._call("gv_graph_aggregate", blk.val_rows.data_ptr(), rows_x, kp, blk.n_limbs, lb, xscale_ptr,
-                       _lib.GV_EDGE_STRIDE, w_ptr.data_ptr(), w_col.data_ptr(), w_val.data_ptr(),
+                       xoff_ptr, _lib.GV_EDGE_STRIDE, w_ptr.data_ptr(), w_col.data_ptr(), w_val.data_ptr(),
                        w_inv.data_ptr(), 1 if include_self else 0, N, G, y_rows.data_ptr(), rows_y, ly,
                        ysum.data_ptr(), ysq.data_ptr(), yscale.data_ptr(), self._stream())
             tiles, n = self.rect_schedule(rows_x, rows_y)
@@ -579,6 +582,11 @@ class Engine:
             buf = blk_or_none.buf
         else:
             buf = torch.empty(total1, dtype=torch.uint8, device=self.device)
+        ev = None
+        if self.kernel_events is not None:
+            stream = torch.cuda.current_stream(self.device)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(stream)
         broadcast_block(buf, total1, group)
         o, _ = lay["header"]
         hdr = buf[o:o + 40].view(torch.int64).cpu()
@@ -593,6 +601,9 @@ class Engine:
                 buf = big
             src = dist.get_global_rank(group, 0) if group is not None else 0
             dist.broadcast(buf[total1:total_l], src=src, group=group)
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+            self.kernel_events.append(("broadcast", ev[0], ev[1], 0))
         return _views(buf, n_cells, n_genes, n_bins, mode, L, lb, flags)
 
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,

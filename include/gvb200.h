@@ -33,6 +33,8 @@ extern "C" {
 #define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
 #define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
 #define GV_EDGE_SCALE_SLOT 15 /* edges[g][15]: real value of one unit of the gene's value-row integer */
+#define GV_EDGE_OFFSET_SLOT 14 /* edges[g][14]: value-row integer of a zero cell (DBL_MAX = 0): only
+                                  genes with negative values are stored shifted (val_mode 2) */
 #define GV_QTABLE_DIM 16  /* q_table_host is [16][16] float64 */
 
 typedef enum gv_status {
@@ -100,9 +102,10 @@ int gv_device_check(void);
  *                            The integer is, by val_mode (gv_value_mode):
  *                              0 the count itself (integer data; exact co-moments);
  *                              1 1 where the gene is detected (one row per gene; Jaccard);
- *                              2 fixed point rint(x * 2^e_g), e_g per gene such that the gene's largest
- *                                value lands just below 2^(val_limbs*val_limb_bits) (any non-negative
- *                                float data; Pearson / cosine / the sign do not depend on e_g);
+ *                              2 fixed point rint((x - o_g) * 2^e_g), o_g = min(0, min x) (0 unless the
+ *                                gene has negative values), e_g per gene such that the largest shifted
+ *                                value lands just below 2^(val_limbs*val_limb_bits) (any float data;
+ *                                Pearson, its sign and xcorr depend on neither, cosine undoes o_g);
  *                              3 doubled average rank minus (n_zero + 1) (Spearman; needs
  *                                2*n_cells < 2^(val_limbs*val_limb_bits)).
  *                            gsum / gsq are then the sums of that integer and of its square.
@@ -195,20 +198,24 @@ int gv_mma_peak(int operand_format, int cta_group, int iters, double* tops_out_h
  * GV_MOM_SIGN writes int8 `sgn` (both triangles, 0 on the diagonal); the other kinds write float32
  * `out` like gv_mi_tiles.  GV_MOM_PEARSON on rank rows (val_mode 3) is the Spearman correlation
  * (metrics.py:423-431).  The co-moments are exact integers (128-bit covariance arithmetic): requires
- * n_cells * (2^limb_bits - 1)^2 < 2^32, n_limbs in 1..4 and n_cells * 4^(n_limbs*limb_bits) < 2^63. */
+ * n_cells * (2^limb_bits - 1)^2 < 2^32, n_limbs in 1..4 and n_cells * 4^(n_limbs*limb_bits) < 2^63.
+ * edges: the `edges` array of gv_discretize_csr or NULL; GV_MOM_COSINE reads GV_EDGE_OFFSET_SLOT
+ * from it (genes with negative values are stored shifted; cosine is not shift-invariant). */
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
-                    const int64_t* gsum, const int64_t* gsq, const int32_t* marg, int64_t n_cells,
+                    const int64_t* gsum, const int64_t* gsq, const int32_t* marg, const double* edges,
+                    int64_t n_cells,
                     int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
                     int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
                     void* sync_ws, void* stream);
 
 /* ---------------------------------------------------------------- graph cross-correlation target
  * Replaces target_graph_xcorr (genevector/_graph_targets.py:10-55) with the built-in "mean"
- * aggregation (genevector/_aggregation.py:48-109) for non-negative data.
+ * aggregation (genevector/_aggregation.py:48-109); graph weights must be non-negative.
  *
  * gv_graph_aggregate: X_agg = (D^-1 W) X (0.5 X + 0.5 that with include_self) on the gene-major value
  *   rows: x_rows / x_limbs / limb_bits / x_scale as produced by gv_discretize_csr (x_scale = the
- *   `edges` array + GV_EDGE_SCALE_SLOT with x_scale_stride 16, or NULL for unit scale); W is the
+ *   `edges` array + GV_EDGE_SCALE_SLOT, x_offset = `edges` + GV_EDGE_OFFSET_SLOT, both with
+ *   x_scale_stride 16, or NULL for unit scale / no offset); W is the
  *   adjacency in CSR (w_row_ptr int64 [n_cells+1], w_col int32, w_val float64, any non-negative
  *   weights); w_inv_ws: n_cells doubles of scratch.  Out: y_rows (fixed point, y_limbs digits per
  *   gene, op_rows_y >= gv_value_rows(n_genes, y_limbs)), ysum / ysq int64 [n_genes], yscale float64
@@ -220,7 +227,8 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
 int64_t gv_tile_schedule_rect(int64_t rows_a, int64_t rows_b, int tile_m, int32_t* out_pairs_host,
                               int64_t capacity);
 int gv_graph_aggregate(const void* x_rows, int64_t op_rows_x, int64_t kp, int x_limbs, int limb_bits,
-                       const double* x_scale, int64_t x_scale_stride, const int64_t* w_row_ptr,
+                       const double* x_scale, const double* x_offset, int64_t x_scale_stride,
+                       const int64_t* w_row_ptr,
                        const int32_t* w_col, const double* w_val, double* w_inv_ws, int include_self,
                        int64_t n_cells, int n_genes, void* y_rows, int64_t op_rows_y, int y_limbs,
                        int64_t* ysum, int64_t* ysq, double* yscale, void* stream);

@@ -281,18 +281,22 @@ def rank_rows_np(X):
 
 def fixed_point_rows_np(X, total_bits):
     """What the B200 path contracts for Pearson / cosine / the sign of non-count data (checker for
-    the value rows): per gene rint(x * 2^e), e = total_bits - exponent(max) with max = f * 2^exponent,
-    f in [0.5, 1); capped at 2^total_bits - 1.  [n_genes][n_cells] int64."""
+    the value rows): per gene rint((x - o) * 2^e) with o = min(0, min x) (0 for non-negative genes),
+    e = total_bits - exponent(top), top = max(max x, 0) - o = f * 2^exponent, f in [0.5, 1); capped at
+    2^total_bits - 1.  For data without negative values only x > 0 contributes.  [n_genes][n_cells]
+    int64; also returns nothing else: use fixed_point_offsets_np for the per-gene zero-cell value."""
     Xd = _dense(X).astype(np.float64)
+    has_neg = bool((Xd < 0).any())
     out = np.zeros(Xd.T.shape, dtype=np.int64)
     for g in range(Xd.shape[1]):
-        col = np.where(Xd[:, g] > 0, Xd[:, g], 0.0)
-        mx = col.max()
-        if mx <= 0:
+        col = Xd[:, g] if has_neg else np.where(Xd[:, g] > 0, Xd[:, g], 0.0)
+        o = min(0.0, float(col.min())) if col.size else 0.0
+        top = max(float(col.max()), 0.0) - o if col.size else 0.0
+        if top <= 0:
             continue
-        _, ex = np.frexp(mx)
-        out[g] = np.minimum(np.rint(np.ldexp(col, int(total_bits - ex))).astype(np.int64),
-                            (1 << total_bits) - 1)
+        _, ex = np.frexp(top)
+        out[g] = np.clip(np.rint(np.ldexp(col - o, int(total_bits - ex))).astype(np.int64), 0,
+                         (1 << total_bits) - 1)
     return out
 
 

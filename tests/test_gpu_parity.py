@@ -343,9 +343,13 @@ def test_count_path_falls_back_and_refuses(engine):
     blk3 = engine.discretize(engine.upload_csr(Xbig), 10, val_mode=0)
     assert blk3.n_limbs == 3 and blk3.val_mode == 0
     assert np.array_equal(blk3.gene_values(), np.asarray(Xbig.todense()).astype(np.int64).T)
-    with pytest.raises(GvError, match="non-negative"):
-        Xn = X.copy(); Xn.data[0] = -2.0
-        engine.mi_from_csr(engine.upload_csr(Xn), 300, 20, signed=True)
+    # a negative value: "not expressed" for the bins (metrics.py:53), the raw value for the sign
+    Xn = X.copy(); Xn.data[0] = -2.0
+    xdn, nbn = orc.discretize_genes_np(Xn, 10)
+    sgn_n = np.sign(orc.pearson_sign_np(Xn)).astype(np.int8); np.fill_diagonal(sgn_n, 0)
+    want_n, _ = orc.mi_pairs_c(xdn, nbn, corr=sgn_n.astype(np.float64), sign_mode=1)
+    out_n = engine.mi_from_csr(engine.upload_csr(Xn), 300, 20, signed=True).cpu().numpy()
+    assert np.abs(out_n - want_n).max() <= MI_TOL
 
 
 @pytest.mark.parametrize("n_cells,n_genes,seed", [(900, 300, 31), (1300, 150, 32)])

@@ -257,3 +257,75 @@ def test_graph_xcorr_several_tiles(engine, cg):
     finally:
         engine.cta_group = old
     assert np.abs(s.matrix.astype(np.float64) - orc.graph_xcorr_np(X, W)).max() <= F32_TOL
+
+
+# ------------------------------------------------------------------ data with negative values
+def _signed_sparse(n_cells, n_genes, seed, dtype=np.float32):
+    """Sparse matrix with normal-distributed stored values (negative, positive, explicit zeros)."""
+    rng = np.random.default_rng(seed)
+    dense = rng.standard_normal((n_cells, n_genes)) * (rng.random((n_cells, n_genes)) < 0.3)
+    dense[:, 3] = np.abs(dense[:, 3])           # a gene without negative values
+    dense[:, 4] = -np.abs(dense[:, 4])          # a gene without positive values
+    dense[:, 5] = 0.0                           # an empty gene
+    X = sp.csr_matrix(dense.astype(dtype))
+    X.data[7] = 0.0                             # an explicit stored zero
+    return X
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_negative_values_signed_fixed_point(engine, dtype):
+    """Centred / scaled data: bins treat x <= 0 as not expressed (metrics.py:53) while Pearson, its
+    sign, cosine and signed MI use the raw values (shifted fixed-point rows, offsets undone for
+    cosine)."""
+    from genevector_b200 import _lib
+    from genevector_b200.engine import GvError
+    from genevector_b200.metrics import target_pearson, target_cosine, target_spearman, compute_mi_b200
+    from genevector_b200.data import get_gene_entropy
+    from oracle import oracle as orc
+    X = _signed_sparse(900, 120, seed=3, dtype=dtype)
+    G = X.shape[1]
+    genes = [f"g{i}" for i in range(G)]
+    csr = engine.upload_csr(X)
+    blk = engine.discretize(csr, 10, val_mode=0)
+    assert (blk.val_mode, blk.n_limbs) == (2, 3) and blk.data_flags[0] & 1
+    xd, nb = orc.discretize_genes_np(X, 10)
+    assert np.array_equal(blk.x_disc(), xd) and np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+    V = orc.fixed_point_rows_np(X, 21)
+    assert np.array_equal(blk.gene_values(), V)
+    assert np.array_equal(blk.gsum.cpu().numpy(), V.sum(axis=1))
+    assert np.array_equal(blk.gsq.cpu().numpy(), (V * V).sum(axis=1))
+    sgn = engine.sign_matrix(blk).cpu().numpy()[:, :G]
+    assert np.array_equal(sgn, orc.int_sign_exact(V))
+    ref_sign = np.sign(orc.pearson_sign_np(X)).astype(np.int8); np.fill_diagonal(ref_sign, 0)
+    assert np.array_equal(sgn, ref_sign)
+    p = target_pearson(X, genes).matrix.astype(np.float64)
+    want = orc.pearson_np(X); np.fill_diagonal(want, 0.0)
+    ok = ~np.isnan(want)
+    assert np.abs(p[ok] - want[ok]).max() <= F32_TOL and np.array_equal(np.isnan(p), np.isnan(want))
+    c = target_cosine(X, genes).matrix.astype(np.float64)
+    assert np.abs(c - orc.cosine_np(X)).max() <= F32_TOL
+    want_mi, _ = orc.mi_pairs_c(xd, nb, corr=ref_sign.astype(np.float64), sign_mode=1)
+    got_mi = compute_mi_b200(X, genes, signed=True).matrix.astype(np.float64)
+    assert np.abs(got_mi - want_mi).max() <= MI_TOL
+    # ranks and unique-value entropies of data with negative values are refused loudly
+    with pytest.raises(GvError, match="non-negative"):
+        target_spearman(X, genes)
+    with pytest.raises(GvError, match="non-negative"):
+        get_gene_entropy(X, genes)
+
+
+def test_graph_xcorr_standard_normal_like_the_reference_tests(engine):
+    """tests/test_graph_targets.py:52-77 of the reference draws X from a standard normal."""
+    from genevector_b200.metrics import target_graph_xcorr
+    from oracle import oracle as orc
+    rng = np.random.default_rng(42)
+    for n, d in ((50, 10), (300, 90)):
+        X = rng.standard_normal((n, d))
+        adj = sp.csr_matrix(rng.integers(0, 2, size=(n, n)).astype(np.float64))
+        genes = [f"g{i}" for i in range(d)]
+        s = target_graph_xcorr(X, genes, graph=adj)
+        assert np.abs(s.matrix).max() <= 1.0 + 1e-6
+        assert np.array_equal(s.matrix, s.matrix.T)
+        assert np.abs(s.matrix.astype(np.float64) - orc.graph_xcorr_np(X, adj)).max() <= F32_TOL
+        s2 = target_graph_xcorr(X, genes, graph=adj, aggr_params={"include_self": True})
+        assert np.abs(s2.matrix.astype(np.float64) - orc.graph_xcorr_np(X, adj, True)).max() <= F32_TOL
