@@ -28,8 +28,23 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0's stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class StdoutGuard:
+    """Rank 0's stdout carries exactly one JSON line: while the bench runs, file descriptor 1 points
+    at stderr (NCCL prints its version banner straight to fd 1), and emit() restores it for the line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
 
 N_BINS = 10
 L2_BYTES = 126 * 1024 * 1024
@@ -137,6 +152,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    guard = StdoutGuard()
     wl, G, N = parse_workload(args.workload)
     r = cpu_reference(N, G, args.steps, args.warmup)
     line = {"metric": "gene-pairs/s", "value": r["value"], "unit": "gene-pairs/s", "impl": "reference",
@@ -148,7 +164,7 @@ def run_reference_arm(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "gene-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    guard.emit(json.dumps(line))
     return 0
 
 
@@ -156,6 +172,7 @@ def run_reference_arm(args):
 def run_matrix_target(args):
     """BASELINE configs[4]: pearson / cosine / jaccard (and spearman) on the shared contraction
     skeleton.  Same contract as the MI line; not the default line."""
+    guard = StdoutGuard()
     import torch
     import torch.distributed as dist
     from genevector_b200 import _lib
@@ -264,7 +281,7 @@ def run_matrix_target(args):
         "clocks": clocks,
     }
     if rank == 0:
-        print(json.dumps(line))
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -291,6 +308,7 @@ def main():
     if args.target != "mi":
         return run_matrix_target(args)
 
+    guard = StdoutGuard()
     import torch
     import torch.distributed as dist
     from genevector_b200.engine import Engine, CsrDevice
@@ -470,7 +488,7 @@ def main():
         r = cpu_reference(N, G, steps=1, warmup=0, target_s=10.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
-        print(json.dumps(line))
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
