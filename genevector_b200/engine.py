@@ -198,6 +198,8 @@ class Engine:
         self._sync_ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
         # bench.py sets this to a list to collect (entry point, start event, end event, kernels)
         self.kernel_events = None
+        # pinned host matrix a callable `out_host` produced during the last mi_scores call
+        self.last_host_result = None
 
     # kernels launched by each entry point (memsets / copies not counted)
     _LAUNCHES = {"gv_discretize_csr": 2, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
@@ -248,8 +250,34 @@ class Engine:
         ptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64))
         if pinned:
             vals, cols, ptr = vals.pin_memory(), cols.pin_memory(), ptr.pin_memory()
-        return CsrDevice(vals.to(self.device, non_blocking=pinned), cols.to(self.device, non_blocking=pinned),
-                         ptr.to(self.device, non_blocking=pinned), n_cells, n_genes)
+            dv, dc, dp = (t.to(self.device, non_blocking=True) for t in (vals, cols, ptr))
+        else:
+            dv, dc, dp = self._staged_to_device(vals), self._staged_to_device(cols), self._staged_to_device(ptr)
+        return CsrDevice(dv, dc, dp, n_cells, n_genes)
+
+    _STAGE_BYTES = 64 << 20
+
+    def _staged_to_device(self, host: torch.Tensor) -> torch.Tensor:
+        """Pageable host tensor -> device through two pinned staging buffers: the CPU copy into one
+        buffer overlaps the DMA out of the other (a plain pageable cudaMemcpy runs at a few GB/s)."""
+        nbytes = host.numel() * host.element_size()
+        if nbytes < 2 * self._STAGE_BYTES:
+            return host.to(self.device)
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty(self._STAGE_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        src = host.contiguous().view(-1).view(torch.uint8)
+        dst = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        stream = torch.cuda.current_stream(self.device)
+        for i, off in enumerate(range(0, nbytes, self._STAGE_BYTES)):
+            n = min(self._STAGE_BYTES, nbytes - off)
+            b = i & 1
+            if i >= 2:
+                self._stage_ev[b].synchronize()          # the DMA that last read this buffer is done
+            self._stage[b][:n].copy_(src[off:off + n])
+            dst[off:off + n].copy_(self._stage[b][:n], non_blocking=True)
+            self._stage_ev[b].record(stream)
+        return dst.view(host.dtype).view(host.shape)
 
     def schedule(self, op_rows: int, cta_group: Optional[int] = None, rank: int = 0, world: int = 1):
         """Device tile list (int32 [n,2]) for this rank: a contiguous slice of the band-ordered
@@ -446,8 +474,8 @@ class Engine:
                   host_chunks: int = 6) -> torch.Tensor:
         """float32 [G][G] MI (times the Pearson sign when `sgn` is given).
 
-        out_host (pinned float32 [G][G], single rank): the result is streamed to the host while it
-        is computed.  The tile schedule walks the triangle band by band, and a tile of band b only
+        out_host (pinned float32 [G][G], or a callable returning one; single rank): the result is
+        streamed to the host while it is computed.  The tile schedule walks the triangle band by band, and a tile of band b only
         writes rows of bands >= b, so once the tiles of a band have run its rows are final: the
         schedule is launched in `host_chunks` pieces cut at band boundaries and every finished piece
         is copied on a second stream under the next one."""
@@ -469,6 +497,9 @@ class Engine:
             if out_host is None or world > 1 or n == 0:
                 launch(0, n)
                 if out_host is not None:
+                    if callable(out_host):
+                        out_host = out_host()
+                        self.last_host_result = out_host
                     out_host.copy_(out, non_blocking=True)
                 return out
             # cut points: first tiles of bands, nearest to equal shares of the schedule
@@ -487,16 +518,23 @@ class Engine:
             if not hasattr(self, "_copy_stream"):
                 self._copy_stream = torch.cuda.Stream(device=self.device)
             main = torch.cuda.current_stream(self.device)
-            t0, g0 = 0, 0
+            # all pieces are enqueued first (an event after each), then the copies: a host buffer that
+            # is only allocated now (callable out_host) is paid for while the GPU is already computing
+            pieces, t0, g0 = [], 0, 0
             for t1, g1 in zip(cuts, gene_ends):
                 launch(t0, t1)
-                if g1 > g0:
-                    ev = torch.cuda.Event()
-                    ev.record(main)
-                    self._copy_stream.wait_event(ev)
-                    with torch.cuda.stream(self._copy_stream):
-                        out_host[g0:g1].copy_(out[g0:g1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                pieces.append((ev, g0, g1))
                 t0, g0 = t1, g1
+            if callable(out_host):
+                out_host = out_host()
+                self.last_host_result = out_host
+            with torch.cuda.stream(self._copy_stream):
+                for ev, g0, g1 in pieces:
+                    if g1 > g0:
+                        self._copy_stream.wait_event(ev)
+                        out_host[g0:g1].copy_(out[g0:g1], non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._copy_stream)
             main.wait_event(done)

@@ -81,8 +81,15 @@ def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=
     if len(gene_names) != n_genes:
         raise ValueError("gene_names must have one entry per column of X")
     csr = eng.upload_csr(X) if rank == 0 else None
+    if world == 1:
+        # the pinned result matrix is allocated while the GPU computes and filled band by band
+        eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed,
+                        out_host=lambda: torch.empty((n_genes, n_genes), dtype=torch.float32, pin_memory=True))
+        torch.cuda.synchronize(eng.device)
+        host, eng.last_host_result = eng.last_host_result, None
+        return ScoreMatrix(host.numpy(), gene_names)
     out = eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world)
-    if world > 1 and gather:
+    if gather:
         import torch.distributed as dist
         dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize(eng.device)
