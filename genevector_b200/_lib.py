@@ -62,7 +62,7 @@ SIGNATURES = {
     "gv_xcorr_tiles": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                               _i64, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_symmetrize": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
-    "gv_mma_peak": (_i32, [_i32, _i32, _i32, _vp, _vp]),
+    "gv_mma_peak": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp]),
     "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),

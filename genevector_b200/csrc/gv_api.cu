@@ -54,7 +54,7 @@ int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, co
                           const int32_t*, const double*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
                           int64_t, float*, int64_t, int, void*, cudaStream_t);
 
-int mma_peak_dispatch(int, int, int, double*, cudaStream_t);
+int mma_peak_dispatch(int, int, int, int, double*, cudaStream_t);
 int xcorr_tiles_dispatch(const void*, int64_t, int, const void*, int64_t, int, int64_t, int, const int64_t*,
                          const int64_t*, const double*, int64_t, const int64_t*, const int64_t*,
                          const double*, int64_t, int, const int32_t*, int64_t, float*, int64_t, int, void*,
@@ -211,7 +211,7 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t kp, const int32_t
                  int operand_format, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
-  if (!operand || !tiles || !out || ld_out < op_rows) return set_error(GV_ERR_ARG, "gv_gram_dump: bad argument");
+  if (!operand || !tiles || (out && ld_out < op_rows)) return set_error(GV_ERR_ARG, "gv_gram_dump: bad argument");
   return gram_dump_dispatch(operand, op_rows, kp, tiles, n_tiles, out, ld_out, cta_group, active_rows,
                             operand_format, static_cast<cudaStream_t>(stream));
 }
@@ -295,10 +295,10 @@ int gv_symmetrize(const float* t, int64_t ld_t, int n_genes, float* out, int64_t
   return symmetrize_dispatch(t, ld_t, n_genes, out, ld_out, static_cast<cudaStream_t>(stream));
 }
 
-int gv_mma_peak(int operand_format, int cta_group, int iters, double* tops_out_host, void* stream) {
+int gv_mma_peak(int operand_format, int cta_group, int iters, int mode, double* tops_out_host, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
-  return mma_peak_dispatch(operand_format, cta_group, iters, tops_out_host, static_cast<cudaStream_t>(stream));
+  return mma_peak_dispatch(operand_format, cta_group, iters, mode, tops_out_host, static_cast<cudaStream_t>(stream));
 }
 
 int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_genes, float c,

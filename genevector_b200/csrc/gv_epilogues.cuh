@@ -46,6 +46,7 @@ struct DumpEpi {
   __device__ DumpEpi(const Params& p_, uint8_t*) : p(p_) {}
   __device__ void prepare(const EpiTile&) {}
   __device__ void run(const EpiTile& et) {
+    if (p.out == nullptr) return;      // discard mode: the main loop alone (tools/probe/l2_probe.py)
     const int row = et.row0 + et.quarter * 32 + et.lane;
 #pragma unroll 1
     for (int cbi = 0; cbi < 4; ++cbi) {

@@ -59,7 +59,11 @@ struct GramCfg {
   static constexpr int BAR_BYTES = 256;                   // barriers + tmem pointer
   // as many pipeline stages as fit next to the epilogue's scratch (1024 = alignment slack)
   static constexpr int STAGES_FIT = (GRAM_SMEM_MAX - 1024 - BAR_BYTES - EPI_SMEM_BYTES) / STAGE_BYTES;
+#ifdef GV_PROBE_STAGES      // probe build only (tools/probe): pipeline-depth sweep
+  static constexpr int STAGES = GV_PROBE_STAGES < STAGES_FIT ? GV_PROBE_STAGES : STAGES_FIT;
+#else
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+#endif
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage operand pipeline");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier block too small");
   static constexpr uint32_t IDESC = FP4 ? idesc_mxf4(TILE_M, N_COLS) : idesc_i8(TILE_M, N_COLS, true, true);

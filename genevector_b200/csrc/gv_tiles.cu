@@ -248,19 +248,25 @@ int xcorr_tiles_dispatch(const void* x_rows, int64_t op_rows_x, int x_limbs, con
 // rate the tensor pipe sustains when nothing else is in the way, i.e. the live roofline denominator
 // bench.py divides by.  Diagnostic only; not on the product path.
 template <int CG, bool FP4>
-__global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters) {
+__global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, int mode) {
   using Cfg = GramCfg<CG, 0, 30, FP4>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar = smem_base + Cfg::STAGE_BYTES;
+  constexpr int PK_STAGES = 6;            // mode 5 walks through as many stage buffers as the main loop
+  const uint32_t bar = smem_base + PK_STAGES * Cfg::STAGE_BYTES;
   const uint32_t tmem_slot = bar + 8;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGE_BYTES + 8);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + PK_STAGES * Cfg::STAGE_BYTES + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool leader = (CG == 2) ? cluster_ctarank() == 0 : true;
-  for (int i = threadIdx.x; i < Cfg::STAGE_BYTES / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < PK_STAGES * Cfg::STAGE_BYTES / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1); mbar_init(bar + 16, 1); mbar_init(bar + 32, 1);
+    fence_mbar_init();
+    mbar_arrive_local(bar + 32);          // phase 0 of this one is complete from the start
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
   tc_fence_before();
@@ -276,10 +282,15 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters) {
     tc_fence_after();
   }
   if (warp == 1 && lane == 0 && leader) {
-    const uint64_t adesc = smem_desc_k128(smem_base);
-    const uint64_t bdesc = smem_desc_k128(smem_base + Cfg::A_BYTES);
+    int stage = 0;
     for (int it = 0; it < iters; ++it) {
-      const uint32_t d_tmem = tmem_base + uint32_t(it & 1) * GRAM_TILE_N;
+      // mode 5: a different stage buffer every 4 MMAs (operands streamed, never re-read back to back)
+      const uint32_t sa = smem_base + (mode == 5 ? stage : 0) * Cfg::STAGE_BYTES;
+      if (++stage == PK_STAGES) stage = 0;
+      const uint64_t adesc = smem_desc_k128(sa);
+      const uint64_t bdesc = smem_desc_k128(sa + Cfg::A_BYTES);
+      // mode 4: one accumulator throughout (every MMA depends on the previous one, as inside a tile)
+      const uint32_t d_tmem = tmem_base + (mode == 4 ? 0u : uint32_t(it & 1) * GRAM_TILE_N);
 #pragma unroll
       for (int k = 0; k < GRAM_BK / 32; ++k) {
         if constexpr (FP4)
@@ -288,6 +299,13 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters) {
         else
           mma_i8<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, 1u);
       }
+      // mode 1: a commit after every 4 MMAs like the real main loop (to a barrier nobody waits on);
+      // mode 2: plus the fence the real loop executes after its full-barrier wait
+      if (mode >= 1 && mode <= 3) mma_commit<CG>(bar + 16);
+      if (mode >= 2 && mode <= 3) tc_fence_after();
+      // mode 3: plus a wait on an already completed barrier phase (the shared-memory round trip of
+      // the main loop's full-barrier wait)
+      if (mode == 3) mbar_wait(bar + 32, 0);
     }
     mma_commit<CG>(bar);
     mbar_wait(bar, 0);
@@ -299,10 +317,10 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters) {
 }
 
 template <int CG, bool FP4>
-static int mma_peak_launch(int iters, double* tops_out, cudaStream_t st) {
+static int mma_peak_launch(int iters, int mode, double* tops_out, cudaStream_t st) {
   using Cfg = GramCfg<CG, 0, 30, FP4>;
   auto kern = mma_peak_kernel<CG, FP4>;
-  const size_t smem = 1024 + Cfg::STAGE_BYTES + 64;
+  const size_t smem = 1024 + 6 * Cfg::STAGE_BYTES + 64;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
   const int sms = device_sm_count();
@@ -324,7 +342,7 @@ static int mma_peak_launch(int iters, double* tops_out, cudaStream_t st) {
   float best = 1e30f;
   for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {       // first launch is the warm-up
     cudaEventRecord(e0, st);
-    e = cudaLaunchKernelEx(&cfg, kern, iters);
+    e = cudaLaunchKernelEx(&cfg, kern, iters, mode);
     cudaEventRecord(e1, st);
     if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -340,12 +358,15 @@ static int mma_peak_launch(int iters, double* tops_out, cudaStream_t st) {
   return GV_OK;
 }
 
-int mma_peak_dispatch(int operand_format, int cta_group, int iters, double* tops_out, cudaStream_t st) {
+int mma_peak_dispatch(int operand_format, int cta_group, int iters, int mode, double* tops_out,
+                      cudaStream_t st) {
   if (!tops_out || iters < 1) return set_error(GV_ERR_ARG, "gv_mma_peak: bad argument");
   const bool fp4 = operand_format == GV_OPERAND_FP4;
   if (!fp4 && operand_format != GV_OPERAND_INT8) return set_error(GV_ERR_ARG, "unknown operand format");
-  if (cta_group == 2) return fp4 ? mma_peak_launch<2, true>(iters, tops_out, st) : mma_peak_launch<2, false>(iters, tops_out, st);
-  if (cta_group == 1) return fp4 ? mma_peak_launch<1, true>(iters, tops_out, st) : mma_peak_launch<1, false>(iters, tops_out, st);
+  if (cta_group == 2)
+    return fp4 ? mma_peak_launch<2, true>(iters, mode, tops_out, st) : mma_peak_launch<2, false>(iters, mode, tops_out, st);
+  if (cta_group == 1)
+    return fp4 ? mma_peak_launch<1, true>(iters, mode, tops_out, st) : mma_peak_launch<1, false>(iters, mode, tops_out, st);
   return set_error(GV_ERR_ARG, "cta_group must be 1 or 2");
 }
 

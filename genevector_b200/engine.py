@@ -599,12 +599,12 @@ class Engine:
                        self._stream())
             return out
 
-    def mma_peak(self, operand: str = "fp4", iters: int = 60000) -> float:
+    def mma_peak(self, operand: str = "fp4", iters: int = 60000, mode: int = 0) -> float:
         """Diagnostic: TOP/s the tensor pipe sustains on the MI contraction's own MMA instruction
         issued back to back (gv_mma_peak); bench.py's live roofline denominator."""
         with torch.cuda.device(self.device):
             out = np.zeros(1, dtype=np.float64)
-            _lib.call("gv_mma_peak", self._fmt(operand), self.cta_group, iters, out.ctypes.data,
+            _lib.call("gv_mma_peak", self._fmt(operand), self.cta_group, iters, mode, out.ctypes.data,
                       self._stream())
             return float(out[0])
 

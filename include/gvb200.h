@@ -181,7 +181,8 @@ int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t row_bytes, int rows
 /* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles.
  * active_rows = 32: every operand row is a column of the tile (N = 256); 30: the B side stages only
  * the first 30 rows of every 32-row block (N = 240, what gv_mi_tiles does for 10 or 5 rows per
- * gene) and columns of the other two rows are left untouched. */
+ * gene) and columns of the other two rows are left untouched.  out == NULL discards the accumulators
+ * (the main loop alone, for probing). */
 int gv_gram_dump(const void* operand, int64_t op_rows, int64_t row_bytes, const int32_t* tiles,
                  int64_t n_tiles, int32_t* out, int64_t ld_out, int cta_group, int active_rows,
                  int operand_format, void* stream);
@@ -189,8 +190,12 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t row_bytes, const 
 /* Diagnostic: the rate (TOP/s, whole device) at which the tensor pipe executes the MI contraction's
  * own tcgen05.mma instruction (M = 256 per CTA pair, N = 240, operands resident in shared memory)
  * when issued back to back with no loads: the live roofline denominator of bench.py.  Synchronous
- * (times `iters` x 4 MMAs per CTA pair with CUDA events on `stream`, best of 3). */
-int gv_mma_peak(int operand_format, int cta_group, int iters, double* tops_out_host, void* stream);
+ * (times `iters` x 4 MMAs per CTA pair with CUDA events on `stream`, best of 3).  mode 0: MMAs only
+ * (the peak); 1: a tcgen05.commit after every 4 MMAs, as the main loop issues; 2: plus its fence;
+ * 3: plus a wait on a completed mbarrier phase; 4: MMAs only, all into one accumulator; 5: MMAs only,
+ * operands taken from six stage buffers in turn as the main loop does. */
+int gv_mma_peak(int operand_format, int cta_group, int iters, int mode, double* tops_out_host,
+                void* stream);
 
 /* ---------------------------------------------------------------- co-moment targets
  * val_rows from gv_discretize_csr: n_limbs INT8 rows per gene (layout there; one 0/1 row for

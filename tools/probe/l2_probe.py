@@ -38,4 +38,15 @@ for operand in ("fp4", "int8"):
         ms = e0.elapsed_time(e1)
         issued = n_use * 2.0 * 256 * 240 * (blk.kp)
         print(f"{operand:5s} {name:28s}: {ms:8.2f} ms for {n_use} tiles -> issued {issued/ms/1e9:8.1f} TOP/s")
+    # main loop alone: accumulators discarded (no epilogue work, no TMEM reads)
+    for name, tl in variants.items():
+        for rep in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("gv_gram_dump", onehot.data_ptr(), rows, row_bytes, tl.data_ptr(), n_use, None, rows, 2, 30, fmt,
+                      torch.cuda.current_stream().cuda_stream)
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        issued = n_use * 2.0 * 256 * 240 * (blk.kp)
+        print(f"{operand:5s} no epilogue, no lockstep, {name:24s}: {ms:8.2f} ms -> issued {issued/ms/1e9:8.1f} TOP/s")
     del onehot
