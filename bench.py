@@ -121,13 +121,20 @@ def cpu_reference(n_cells, n_genes_workload, steps, warmup, target_s=8.0, seed=0
     from genevector_b200.synth import synth_counts
     cores = orc.num_threads()
 
+    phases = {"discretize_genes": [], "corrcoef_sign": [], "mi_pairs": []}
+
     def one_step(Xd):
         t0 = time.perf_counter()
         xd, nb = orc.discretize_genes_c(Xd, N_BINS)
+        t1 = time.perf_counter()
         with np.errstate(invalid="ignore", divide="ignore"):
             corr = np.nan_to_num(np.corrcoef(Xd.T), nan=0.0)
+        t2 = time.perf_counter()
         _, npairs = orc.mi_pairs_c(xd, nb, corr=corr, sign_mode=1)
-        return time.perf_counter() - t0
+        t3 = time.perf_counter()
+        for k, v in zip(phases, (t1 - t0, t2 - t1, t3 - t2)):
+            phases[k].append(v * 1e3)
+        return t3 - t0
 
     # calibrate on 48 genes, then size the sample for ~target_s per step
     S0 = min(48, n_genes_workload)
@@ -139,10 +146,13 @@ def cpu_reference(n_cells, n_genes_workload, steps, warmup, target_s=8.0, seed=0
     X = synth_counts(n_cells, S, seed=seed).toarray() if S != S0 else X0
     for _ in range(max(warmup, 0)):
         one_step(X)
+    for v in phases.values():
+        v.clear()
     times = [one_step(X) for _ in range(max(steps, 1))]
     pairs = S * (S - 1) / 2
     t = float(np.mean(times))
     return {"value": pairs / t, "unit": "gene-pairs/s", "cores": cores, "kind": "port",
+            "phases_ms": {k: float(np.mean(v)) for k, v in phases.items()},
             "sample": f"{S} genes x {n_cells} cells ({int(pairs)} pairs) of the workload's generator, "
                       f"discretize + corrcoef sign + all-pairs MI per step, mean of {len(times)} steps",
             "ms_per_step": t * 1e3}
@@ -161,7 +171,7 @@ def run_reference_arm(args):
             "data": "synthetic",
             "config": {"workload": f"{wl}: all-pairs signed MI, {G} genes x {N} cells, n_bins={N_BINS}",
                        "note": "CPU path timed on a gene sample; pairs/s is per-pair throughput at this cell count"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_ms")},
             "e2e": {"value": r["value"], "unit": "gene-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     guard.emit(json.dumps(line))
@@ -486,7 +496,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(N, G, steps=1, warmup=0, target_s=10.0)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_ms")}
     if rank == 0:
         guard.emit(json.dumps(line))
     if world > 1:
