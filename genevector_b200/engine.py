@@ -16,6 +16,7 @@ the upper-triangular tile schedule; no other collective.
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Optional
 
 import numpy as np
@@ -95,6 +96,7 @@ class BinBlock:
     limb_bits: int
     data_flags: tuple            # (flag bits, max value)
     path_used: int = 0           # gv_disc_path the discretisation took (1 counts, 2 general)
+    pending: object = None       # handle of a value-row broadcast still in flight (Engine._replicate)
 
     def gene_values(self) -> np.ndarray:
         """The integers behind the value rows, int64 [n_genes][n_cells] (tests)."""
@@ -198,6 +200,8 @@ class Engine:
         self._sync_ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
         # bench.py sets this to a list to collect (entry point, start event, end event, kernels)
         self.kernel_events = None
+        # multi-rank: send the value rows asynchronously and expand the one-hot operand meanwhile
+        self.defer_values = os.environ.get("GV_DEFER_VALUES", "1") != "0"
         # pinned host matrix a callable `out_host` produced during the last mi_scores call
         self.last_host_result = None
 
@@ -609,11 +613,14 @@ class Engine:
             return float(out[0])
 
     # ------------------------------------------------------------------ whole paths
-    def _replicate(self, blk_or_none, n_cells, n_genes, n_bins, val_mode, group) -> BinBlock:
+    def _replicate(self, blk_or_none, n_cells, n_genes, n_bins, val_mode, group,
+                   defer_values: bool = False) -> BinBlock:
         """The single collective of the path: broadcast the bin block from rank 0.  The header at
         the front of the block says how many digits per gene the value rows have; only when there is
         more than one (counts > 2^limb_bits - 1, or data that are not counts) is the extra tail sent
-        by a second broadcast."""
+        by a further call.  defer_values: the value rows (the last section of the block) are sent by
+        an asynchronous call whose handle is left in blk.pending, so that the caller can expand the
+        one-hot operand (which needs the bins only) while they are still on the wire."""
         import torch.distributed as dist
         _, _, lay, total1 = block_layout(n_cells, n_genes, val_mode, 1)
         if blk_or_none is not None:
@@ -625,24 +632,36 @@ class Engine:
             stream = torch.cuda.current_stream(self.device)
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(stream)
-        broadcast_block(buf, total1, group)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        val_off, val_bytes = lay["val"]
+        pending = None
+        if defer_values and val_bytes > 0:
+            broadcast_block(buf, val_off, group)                       # header, bins, per-gene arrays
+        else:
+            broadcast_block(buf, total1, group)
         o, _ = lay["header"]
         hdr = buf[o:o + 40].view(torch.int64).cpu()
         L, lb, flags, mode = int(hdr[0]), int(hdr[1]), (int(hdr[2]), int(hdr[3])), int(hdr[4])
         if val_mode < 0:
             mode = val_mode
+        if defer_values and val_bytes > 0:
+            if L == 1:
+                pending = dist.broadcast(buf[val_off:total1], src=src, group=group, async_op=True)
+            else:
+                dist.broadcast(buf[val_off:total1], src=src, group=group)
         if L > 1:
             _, _, _, total_l = block_layout(n_cells, n_genes, val_mode, L)
             if blk_or_none is None:
                 big = torch.empty(total_l, dtype=torch.uint8, device=self.device)
                 big[:total1].copy_(buf)
                 buf = big
-            src = dist.get_global_rank(group, 0) if group is not None else 0
             dist.broadcast(buf[total1:total_l], src=src, group=group)
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(self.device))
             self.kernel_events.append(("broadcast", ev[0], ev[1], 0))
-        return _views(buf, n_cells, n_genes, n_bins, mode, L, lb, flags)
+        blk = _views(buf, n_cells, n_genes, n_bins, mode, L, lb, flags)
+        blk.pending = pending
+        return blk
 
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
                     signed: bool = False, rank: int = 0, world: int = 1, group=None,
@@ -657,9 +676,14 @@ class Engine:
         # process (tests): each "rank" then discretises for itself
         blk = self.discretize(csr, n_bins, val_mode) if (rank == 0 or not distributed) else None
         if distributed:
-            blk = self._replicate(blk, n_cells, n_genes, n_bins, val_mode, group)
+            blk = self._replicate(blk, n_cells, n_genes, n_bins, val_mode, group,
+                                  defer_values=signed and self.defer_values)
         sgn = None
         B = _lib.call("gv_rows_per_gene", n_bins)
+        onehot, B = self.expand_onehot(blk)        # needs the bins only: runs under the value-row transfer
+        if getattr(blk, "pending", None) is not None:
+            blk.pending.wait()                     # the current stream now waits for the value rows
+            blk.pending = None
         if signed:
             # each rank computes only the part of the sign map its own MI tiles read (1 % of the
             # work, sharded like the MI tiles); no second collective
@@ -672,7 +696,6 @@ class Engine:
                     self._sched_cache[key] = self.sign_tiles_for(mine, B, blk.n_limbs)
                 st = self._sched_cache[key]
             sgn = self.sign_matrix(blk, tiles=st)
-        onehot, B = self.expand_onehot(blk)
         return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, out_host=out_host)
 
     def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,
