@@ -136,6 +136,33 @@ def test_c4_sampled(engine):
     torch.cuda.empty_cache()
 
 
+def test_wide_matrix_beyond_2g_result_elements(engine):
+    """48,000 genes x 20,000 cells (a whole-transcriptome gene axis): 2.3e9 result elements, i.e. every
+    64-bit index of the result / sign-map / tile arithmetic beyond 2^31, checked on genes sampled from
+    the far end of the gene axis as well as at random, plus the streamed host copy."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs ~40 GB of free HBM")
+    G, N = 48000, 20000
+    csr = _make(engine, N, G, seed=8)
+    blk = engine.discretize(csr, 10, val_mode=0)
+    out = engine.mi_from_csr(csr, N, G, n_bins=10, signed=True)
+    assert out.numel() > 2 ** 31
+    _structural(out, signed=True)
+    _check_sampled(engine, csr, out, blk, n_gene_sample=40, n_pair_sample=300, signed=True, seed=1)
+    # the last genes of the axis (largest row / column offsets)
+    from oracle import oracle as orc
+    genes = np.arange(G - 24, G)
+    D = _dense_columns(csr, genes)
+    xd, nb = orc.discretize_genes_c(D, 10)
+    want, _ = orc.mi_pairs_c(xd, nb, corr=orc.sign_int_c(D).astype(np.float64), sign_mode=1)
+    gi = torch.as_tensor(genes, device=out.device)
+    got = out[gi][:, gi].cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= MI_TOL
+    del out, blk, csr
+    torch.cuda.empty_cache()
+
+
 def test_c5_matrix_targets_sampled(engine):
     """configs[4]: 10,000 genes x 100,000 cells, pearson / cosine / jaccard on the shared skeleton."""
     from genevector_b200 import _lib
