@@ -163,6 +163,22 @@ def test_wide_matrix_beyond_2g_result_elements(engine):
     torch.cuda.empty_cache()
 
 
+def test_atlas_scale_cell_axis(engine):
+    """1,048,593 cells x 1,200 genes: a cell axis beyond 2^20 (6-bit digits for the exact co-moments,
+    8,193 cell blocks in the transposition, K extent not a multiple of anything)."""
+    from genevector_b200.engine import limb_bits_for
+    G, N = 1200, (1 << 20) + 17
+    assert limb_bits_for(N) == 6
+    csr = _make(engine, N, G, seed=9)
+    blk = engine.discretize(csr, 10, val_mode=0)
+    assert blk.limb_bits == 6 and blk.val_mode == 0
+    out = engine.mi_from_csr(csr, N, G, n_bins=10, signed=True)
+    _structural(out, signed=True)
+    _check_sampled(engine, csr, out, blk, n_gene_sample=16, n_pair_sample=60, signed=True, seed=2)
+    del out, blk, csr
+    torch.cuda.empty_cache()
+
+
 def test_c5_matrix_targets_sampled(engine):
     """configs[4]: 10,000 genes x 100,000 cells, pearson / cosine / jaccard on the shared skeleton."""
     from genevector_b200 import _lib
