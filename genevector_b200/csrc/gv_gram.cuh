@@ -62,7 +62,11 @@ struct GramCfg {
 #ifdef GV_PROBE_STAGES      // probe build only (tools/probe): pipeline-depth sweep
   static constexpr int STAGES = GV_PROBE_STAGES < STAGES_FIT ? GV_PROBE_STAGES : STAGES_FIT;
 #else
+#ifdef GV_PROBE_STAGES      // probe build only (tools/probe): pipeline-depth sweep
+  static constexpr int STAGES = GV_PROBE_STAGES < STAGES_FIT ? GV_PROBE_STAGES : STAGES_FIT;
+#else
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+#endif
 #endif
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage operand pipeline");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier block too small");

@@ -260,8 +260,30 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, int mode) {
       reinterpret_cast<volatile uint32_t*>(smem_gen + PK_STAGES * Cfg::STAGE_BYTES + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool leader = (CG == 2) ? cluster_ctarank() == 0 : true;
-  for (int i = threadIdx.x; i < PK_STAGES * Cfg::STAGE_BYTES / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
+  // operand bytes: zeros (modes 0-5), pseudo-random (mode 6: every bit toggles, worst-case switching
+  // power) or one-hot-like (mode 7: one E2M1 1.0 / INT8 1 in ~10 % of the elements, like the MI operand)
+  for (int i = threadIdx.x; i < PK_STAGES * Cfg::STAGE_BYTES / 16; i += blockDim.x) {
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (mode >= 6) {
+      uint32_t h[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t x = (uint32_t(i) * 4u + q) * 2654435761u + blockIdx.x * 40503u + 12345u;
+        x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+        if (mode == 6) {
+          h[q] = FP4 ? (x & 0x77777777u) : (x & 0x7F7F7F7Fu);          // finite, non-negative values
+        } else {
+          // keep an element with probability ~1/10: value 1.0 (E2M1 0x2) or 1 (INT8)
+          uint32_t o = 0;
+          if (FP4) { for (int n = 0; n < 8; ++n) if (((x >> (4 * n)) & 0xF) == 0 || (((x >> (4 * n)) & 0xF) == 1 && (n & 1))) o |= 0x2u << (4 * n); }
+          else     { for (int n = 0; n < 4; ++n) if (((x >> (8 * n)) & 0xFF) < 26) o |= 0x1u << (8 * n); }
+          h[q] = o;
+        }
+      }
+      w = make_uint4(h[0], h[1], h[2], h[3]);
+    }
+    reinterpret_cast<uint4*>(smem_gen)[i] = w;
+  }
   if (threadIdx.x == 0) {
     mbar_init(bar, 1); mbar_init(bar + 16, 1); mbar_init(bar + 32, 1);
     fence_mbar_init();
@@ -285,7 +307,7 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, int mode) {
     int stage = 0;
     for (int it = 0; it < iters; ++it) {
       // mode 5: a different stage buffer every 4 MMAs (operands streamed, never re-read back to back)
-      const uint32_t sa = smem_base + (mode == 5 ? stage : 0) * Cfg::STAGE_BYTES;
+      const uint32_t sa = smem_base + (mode >= 5 ? stage : 0) * Cfg::STAGE_BYTES;
       if (++stage == PK_STAGES) stage = 0;
       const uint64_t adesc = smem_desc_k128(sa);
       const uint64_t bdesc = smem_desc_k128(sa + Cfg::A_BYTES);

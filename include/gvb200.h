@@ -193,7 +193,8 @@ int gv_gram_dump(const void* operand, int64_t op_rows, int64_t row_bytes, const 
  * (times `iters` x 4 MMAs per CTA pair with CUDA events on `stream`, best of 3).  mode 0: MMAs only
  * (the peak); 1: a tcgen05.commit after every 4 MMAs, as the main loop issues; 2: plus its fence;
  * 3: plus a wait on a completed mbarrier phase; 4: MMAs only, all into one accumulator; 5: MMAs only,
- * operands taken from six stage buffers in turn as the main loop does. */
+ * operands taken from six stage buffers in turn as the main loop does; 6: like 5 with pseudo-random
+ * operand bytes instead of zeros (switching power); 7: like 5 with one-hot-like operands (~10 % ones). */
 int gv_mma_peak(int operand_format, int cta_group, int iters, int mode, double* tops_out_host,
                 void* stream);
 
