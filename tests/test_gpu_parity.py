@@ -456,3 +456,49 @@ def test_streamed_host_result_equals_device_result(engine):
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
     assert torch.equal(host, ref.cpu())
+
+
+def test_input_formats_match_the_reference_semantics(engine):
+    """The reference takes whatever `adata.X` is (metrics.py:45, data.py:171): dense arrays, CSC, integer
+    or bool dtypes, CSR with unsorted indices or duplicate entries (which scipy's todense sums).  All
+    must give the result of the canonical float32 CSR."""
+    from genevector_b200.metrics import compute_mi_b200, discretize_genes
+    from genevector_b200.synth import synth_counts, gene_names
+    from oracle import oracle as orc
+    X = synth_counts(600, 60, seed=11)
+    genes = gene_names(60)
+    ref = compute_mi_b200(X, genes, signed=True).matrix
+    want, _ = orc.mi_pairs_c(*orc.discretize_genes_np(X, 10), corr=orc.sign_int_c(X).astype(np.float64), sign_mode=1)
+    assert np.abs(ref.astype(np.float64) - want).max() <= MI_TOL
+    dense = np.asarray(X.todense())
+    variants = {
+        "dense float32": dense, "dense float64": dense.astype(np.float64), "csc": sp.csc_matrix(X),
+        "coo": sp.coo_matrix(X), "int32": sp.csr_matrix(dense.astype(np.int32)),
+        "int64 dense": dense.astype(np.int64), "uint8": sp.csr_matrix(dense.astype(np.uint8)),
+    }
+    # unsorted column indices within rows
+    U = X.copy()
+    for r in range(U.shape[0]):
+        a, b = U.indptr[r], U.indptr[r + 1]
+        U.indices[a:b] = U.indices[a:b][::-1].copy()
+        U.data[a:b] = U.data[a:b][::-1].copy()
+    U.has_sorted_indices = False
+    variants["unsorted csr"] = U
+    # duplicate entries: every value split into two stored entries that sum to it
+    half = np.floor(X.data / 2)
+    data2 = np.empty(2 * X.nnz, dtype=X.data.dtype)
+    data2[0::2], data2[1::2] = half, X.data - half
+    D = sp.csr_matrix((data2, np.repeat(X.indices, 2), X.indptr * 2), shape=X.shape)
+    assert D.nnz == 2 * X.nnz and not D.has_canonical_format
+    variants["duplicates"] = D
+    for name, V in variants.items():
+        got = compute_mi_b200(V, genes, signed=True).matrix
+        assert np.array_equal(got, ref), name
+    xd, nb = discretize_genes(dense, n_bins=10)
+    xr, nr = orc.discretize_genes_np(X, 10)
+    assert np.array_equal(xd, xr) and np.array_equal(nb, nr)
+    # bool input: every expressed gene has one unique value -> one non-zero bin (metrics.py:60-62)
+    B = sp.csr_matrix(dense > 0)
+    xb, nbb = discretize_genes(B, n_bins=10)
+    xbr, nbr = orc.discretize_genes_np(B.astype(np.float32), 10)
+    assert np.array_equal(xb, xbr) and np.array_equal(nbb, nbr)
