@@ -182,7 +182,11 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int2 tc = ga.tiles[t];
         const int arow = tc.x + int(rank) * Cfg::A_ROWS;
         const int brow = tc.y + int(rank) * (GRAM_TILE_N / CG);   // first operand row of my B blocks
-        for (int kb = 0; kb < ga.k_blocks; ++kb) {
+        // odd waves walk K backwards: the K slices a wave touched last are still in L2 when the next
+        // wave (same band: same A panels) starts with them; the exact sums do not depend on the order
+        const bool backwards = (wave & 1u) != 0u;
+        for (int kq = 0; kq < ga.k_blocks; ++kq) {
+          const int kb = backwards ? ga.k_blocks - 1 - kq : kq;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include "gv_internal.h"
 #include "gv_epilogues.cuh"
@@ -103,13 +104,15 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // the wave barrier spins on all clusters of the grid: ask for a cooperative launch so that the
-  // grid is only started when every CTA can be resident at once (a launch error instead of a hang
-  // if something else holds SMs)
+  // The wave barrier spins on all clusters of the grid, so every CTA must be resident at once: the
+  // grid is one CTA per SM and nothing else runs on the stream's device meanwhile.  GV_COOPERATIVE=1
+  // additionally asks for a cooperative launch (a launch error instead of a spin if something else
+  // holds SMs); it is off by default because Nsight Compute cannot replay cooperative cluster launches.
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = sync_ws != nullptr ? 2 : 1;
+  static const bool coop = getenv("GV_COOPERATIVE") != nullptr && getenv("GV_COOPERATIVE")[0] == '1';
+  cfg.numAttrs = (sync_ws != nullptr && coop) ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, map, map_b, ga, ep);
   if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
   return GV_OK;
