@@ -232,3 +232,24 @@ def test_graph_xcorr_argument_errors_match_the_reference():
         target_graph_xcorr(X, ["a", "b"], graph=sp.identity(2, format="csr"), aggr="nonexistent")
     with pytest.raises(ValueError, match="callable"):
         target_graph_xcorr(X, ["a", "b"], graph=sp.identity(2, format="csr"), aggr=lambda X, G, **kw: X)
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference (the CPU arm: runs without a GPU): exactly one line on stdout, a JSON
+    object with the keys of the bench contract."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                        "300x2000", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "gene-pairs/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
