@@ -253,3 +253,27 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_install_into_reference_uses_the_registry_hook():
+    """INTEGRATION.md route A: the B200 targets are re-registered through the reference's own
+    register_target decorator (metrics.py:347-352), replacing the entries of its TARGETS table."""
+    import types
+    from genevector_b200 import metrics as ours
+    ref = types.ModuleType("genevector.metrics")
+    ref.TARGETS = {"mi": object(), "pearson": object(), "custom_user_target": object()}
+
+    def register_target(name):
+        def wrapper(fn):
+            ref.TARGETS[name] = fn
+            return fn
+        return wrapper
+    ref.register_target = register_target
+    keep = ref.TARGETS["custom_user_target"]
+    assert ours.install_into_reference(ref) is ref
+    for name in ("mi", "pearson", "spearman", "cosine", "jaccard", "graph_xcorr"):
+        assert ref.TARGETS[name] is ours.TARGETS[name]
+    assert ref.TARGETS["custom_user_target"] is keep
+    # the call GeneVectorDataset._compute_target_scores makes (data.py:319-326): unknown backends raise
+    with pytest.raises(ValueError, match="Unknown MI backend"):
+        ref.TARGETS["mi"](None, [], signed=True, backend="numba", device="cpu")
