@@ -277,3 +277,61 @@ def test_install_into_reference_uses_the_registry_hook():
     # the call GeneVectorDataset._compute_target_scores makes (data.py:319-326): unknown backends raise
     with pytest.raises(ValueError, match="Unknown MI backend"):
         ref.TARGETS["mi"](None, [], signed=True, backend="numba", device="cpu")
+
+
+REF_DIR = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DIR, "genevector")),
+                    reason="reference sources only exist in the build container")
+def test_reference_consumers_accept_the_score_matrix(tmp_path, monkeypatch):
+    """Drop-in check against the reference's own consumer code (build container only): its
+    GeneVectorDataset._build_training_tensors (data.py:377-411), cache.save_scores / load_scores
+    (cache.py:64-110) and compute_cache_key run unmodified on a ScoreMatrix and give what they give on
+    the nested dict the reference's tiers return."""
+    import collections
+    import importlib
+    import sys
+    import types
+    from genevector_b200 import cache as our_cache
+    from genevector_b200.scores import ScoreMatrix
+    pkg = types.ModuleType("genevector")
+    pkg.__path__ = [os.path.join(REF_DIR, "genevector")]
+    monkeypatch.setitem(sys.modules, "genevector", pkg)
+    for sub in ("genevector.data", "genevector.cache", "genevector.metrics", "genevector._aggregation",
+                "genevector._graph_targets"):
+        monkeypatch.delitem(sys.modules, sub, raising=False)
+    refd = importlib.import_module("genevector.data")
+    refc = importlib.import_module("genevector.cache")
+    monkeypatch.setattr(refc, "CACHE_DIR", str(tmp_path))
+    z = load_golden("ref_poisson_500x20_b5")
+    genes = [f"GENE{i}" for i in range(20)]
+    M = z["mi_signed_round5"]
+    ours = ScoreMatrix(M.astype(np.float32), genes)
+    theirs = collections.defaultdict(lambda: collections.defaultdict(float))
+    for i, g1 in enumerate(genes):
+        for j, g2 in enumerate(genes):
+            if i != j and M[i, j] != 0:
+                theirs[g1][g2] = float(M[i, j])
+
+    def build(scores, signed):
+        ds = object.__new__(refd.GeneVectorDataset)
+        ds.data = types.SimpleNamespace(genes=genes)
+        ds.mi_scores, ds.signed_mi, ds.device = scores, signed, "cpu"
+        ds._build_training_tensors(100.0)
+        return ds._i_idx.numpy(), ds._j_idx.numpy(), ds._xij.numpy()
+
+    for signed in (True, False):
+        a, b = build(ours, signed), build(theirs, signed)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.abs(a[2] - b[2]).max() <= 100.0 ** 2 * 1e-6        # float32 storage of the 5-dp values
+    # the reference's cache writer / reader on our Mapping, and key compatibility
+    key = refc.compute_cache_key(z["X"], genes, "mi", {}, True)
+    assert key == our_cache.compute_cache_key(z["X"], genes, "mi", {}, True)
+    refc.save_scores(key, ours, genes)
+    refc.save_scores(key + "t", theirs, genes)
+    m1 = np.load(refc.get_cache_path(key))["scores"]
+    m2 = np.load(refc.get_cache_path(key + "t"))["scores"]
+    assert np.abs(m1 - m2).max() <= 1e-6
+    back, g2 = refc.load_scores(key)
+    assert g2 == genes and abs(back[genes[0]][genes[1]] - M[0, 1]) <= 1.1e-5
