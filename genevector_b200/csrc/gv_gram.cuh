@@ -53,7 +53,11 @@ struct GramCfg {
   static constexpr int B_BLOCKS = 8 / CG;                 // 32-row operand blocks behind them
   static constexpr int A_BYTES = A_ROWS * GRAM_BK;
   static constexpr int B_BYTES = B_ROWS * GRAM_BK;
+#ifdef GV_PROBE_7STAGES      // probe build only: stages packed tightly (B slot = its 120 data rows)
+  static constexpr int B_SLOT_BYTES = B_BYTES;
+#else
   static constexpr int B_SLOT_BYTES = (GRAM_TILE_N / CG) * GRAM_BK;   // smem reserved for B
+#endif
   static constexpr int STAGE_BYTES = A_BYTES + B_SLOT_BYTES;
   static constexpr int TX_BYTES = A_BYTES + B_BYTES;      // bytes TMA delivers per CTA per stage
   static constexpr int BAR_BYTES = 256;                   // barriers + tmem pointer
