@@ -106,11 +106,7 @@ struct MiEpi {
   // warp-private transpose scratch: 32 rows x ACTIVE columns, odd row stride (no bank conflicts)
   static constexpr int SCR_STRIDE = (ACTIVE % 2 == 0) ? ACTIVE + 1 : ACTIVE;
   static constexpr size_t SCR_INTS = 32 * SCR_STRIDE;
-#ifdef GV_PROBE_7STAGES      // probe build only: ONE scratch shared by all warps (wrong results, timing only)
-  static constexpr size_t SMEM_BYTES = sizeof(Meta) + SCR_INTS * 4 + 16;
-#else
   static constexpr size_t SMEM_BYTES = sizeof(Meta) + GRAM_EPI_WARPS * SCR_INTS * 4 + 16;
-#endif
 
   const Params& p;
   Meta* meta;
@@ -156,11 +152,7 @@ struct MiEpi {
       if (1 + pos < MARG_STRIDE) m_ia = p.marg[int64_t(gi) * MARG_STRIDE + 1 + pos];
     }
     const float inv_rx = m_ia > 0 ? 1.0f / float(m_ia) : 0.0f;
-#ifdef GV_PROBE_7STAGES
-    int* scr = scr_all;
-#else
     int* scr = scr_all + ((et.quarter + 4 * et.half) * SCR_INTS);
-#endif
 
 #pragma unroll 1
     for (int cbi = 0; cbi < 4; ++cbi) {

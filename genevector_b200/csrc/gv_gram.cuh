@@ -53,25 +53,13 @@ struct GramCfg {
   static constexpr int B_BLOCKS = 8 / CG;                 // 32-row operand blocks behind them
   static constexpr int A_BYTES = A_ROWS * GRAM_BK;
   static constexpr int B_BYTES = B_ROWS * GRAM_BK;
-#ifdef GV_PROBE_7STAGES      // probe build only: stages packed tightly (B slot = its 120 data rows)
-  static constexpr int B_SLOT_BYTES = B_BYTES;
-#else
   static constexpr int B_SLOT_BYTES = (GRAM_TILE_N / CG) * GRAM_BK;   // smem reserved for B
-#endif
   static constexpr int STAGE_BYTES = A_BYTES + B_SLOT_BYTES;
   static constexpr int TX_BYTES = A_BYTES + B_BYTES;      // bytes TMA delivers per CTA per stage
   static constexpr int BAR_BYTES = 256;                   // barriers + tmem pointer
   // as many pipeline stages as fit next to the epilogue's scratch (1024 = alignment slack)
   static constexpr int STAGES_FIT = (GRAM_SMEM_MAX - 1024 - BAR_BYTES - EPI_SMEM_BYTES) / STAGE_BYTES;
-#ifdef GV_PROBE_STAGES      // probe build only (tools/probe): pipeline-depth sweep
-  static constexpr int STAGES = GV_PROBE_STAGES < STAGES_FIT ? GV_PROBE_STAGES : STAGES_FIT;
-#else
-#ifdef GV_PROBE_STAGES      // probe build only (tools/probe): pipeline-depth sweep
-  static constexpr int STAGES = GV_PROBE_STAGES < STAGES_FIT ? GV_PROBE_STAGES : STAGES_FIT;
-#else
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
-#endif
-#endif
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage operand pipeline");
   static_assert(8 * (2 * STAGES + 5) <= BAR_BYTES, "barrier block too small");
   static constexpr uint32_t IDESC = FP4 ? idesc_mxf4(TILE_M, N_COLS) : idesc_i8(TILE_M, N_COLS, true, true);
