@@ -435,9 +435,14 @@ class Engine:
         st = st[st[:, 0] <= st[:, 1] + 255]          # tiles holding some (row <= col)
         return torch.from_numpy(np.ascontiguousarray(st.astype(np.int32))).to(self.device)
 
-    def sign_matrix(self, blk: BinBlock, tiles: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def sign_matrix(self, blk: BinBlock, tiles: Optional[torch.Tensor] = None,
+                    rule: str = "numpy") -> torch.Tensor:
         """int8 [G][ld] Pearson sign from the INT8 value rows (exact integer co-moments).
-        `tiles`: optional subset of sign tiles (see sign_tiles_for); default the whole triangle."""
+        `tiles`: optional subset of sign tiles (see sign_tiles_for); default the whole triangle.
+        rule "numpy": np.sign of the correlation, 0 where it is 0 or undefined (metrics.py:111,134, the
+        NumPy / Numba / torch tiers); rule "rust": +1 unless the correlation is negative (lib.rs:91-94)."""
+        if rule not in ("numpy", "rust"):
+            raise ValueError(f"unknown sign rule {rule!r} (numpy or rust)")
         assert blk.val_rows is not None and blk.val_mode in (0, 2)
         with torch.cuda.device(self.device):
             G = blk.n_genes
@@ -453,6 +458,8 @@ class Engine:
                        blk.n_cells, G,
                        blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0,
                        self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
+            if rule == "rust":
+                sgn.masked_fill_(sgn == 0, 1)
             return sgn
 
     def moment_scores(self, blk: BinBlock, kind: int, out: Optional[torch.Tensor] = None,
@@ -666,7 +673,7 @@ class Engine:
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
                     signed: bool = False, rank: int = 0, world: int = 1, group=None,
                     out: Optional[torch.Tensor] = None,
-                    out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out_host: Optional[torch.Tensor] = None, sign_rule: str = "numpy") -> torch.Tensor:
         """All-pairs (signed) MI.  With world > 1 only rank 0 needs `csr`; each rank returns a
         [G][G] matrix in which the entries of its own tiles are filled."""
         import torch.distributed as dist
@@ -695,7 +702,7 @@ class Engine:
                     mine, _ = tile_slice(rows, self.cta_group, self.band, rank, world)
                     self._sched_cache[key] = self.sign_tiles_for(mine, B, blk.n_limbs)
                 st = self._sched_cache[key]
-            sgn = self.sign_matrix(blk, tiles=st)
+            sgn = self.sign_matrix(blk, tiles=st, rule=sign_rule)
         return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, out_host=out_host)
 
     def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,

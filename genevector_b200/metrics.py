@@ -66,14 +66,19 @@ def _dist_info():
     return 0, 1
 
 
-def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=True):
+def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=True, sign_rule="numpy"):
     """All-pairs (signed) mutual information on B200; returns a ScoreMatrix (Mapping view with
     the reference's dict semantics, see scores.py).
 
     Under torch.distributed (one process per GPU) the tile space is split over the ranks after a
     single broadcast of the bin block; with gather=True the disjoint per-rank tiles are then
     summed onto rank 0 (result assembly, outside the hot path) and the other ranks return their
-    partial matrices."""
+    partial matrices.
+
+    sign_rule: "numpy" (default) signs with np.sign of the Pearson correlation like the reference's
+    NumPy / Numba / torch tiers and its documentation (metrics.py:134, 227, 302): a zero or undefined
+    correlation zeroes the score; "rust" reproduces the Rust tier (src/lib.rs:91-94): +1 unless the
+    correlation is negative."""
     import torch
     eng = get_engine(_device_of(device))
     rank, world = _dist_info()
@@ -83,12 +88,13 @@ def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=
     csr = eng.upload_csr(X) if rank == 0 else None
     if world == 1:
         # the pinned result matrix is allocated while the GPU computes and filled band by band
-        eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed,
+        eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, sign_rule=sign_rule,
                         out_host=lambda: torch.empty((n_genes, n_genes), dtype=torch.float32, pin_memory=True))
         torch.cuda.synchronize(eng.device)
         host, eng.last_host_result = eng.last_host_result, None
         return ScoreMatrix(host.numpy(), gene_names)
-    out = eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world)
+    out = eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world,
+                          sign_rule=sign_rule)
     if gather:
         import torch.distributed as dist
         dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
@@ -98,9 +104,11 @@ def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=
 
 @register_target("mi")
 def target_mi(X, gene_names, signed=False, backend="b200", device="cuda", n_bins=10, **kwargs):
-    """Mutual information, optionally signed by the Pearson correlation (metrics.py:381-411)."""
+    """Mutual information, optionally signed by the Pearson correlation (metrics.py:381-411).
+    target_kwargs={"sign_rule": "rust"} selects the Rust tier's sign convention."""
     if backend in ("b200", "auto"):
-        return compute_mi_b200(X, gene_names, n_bins=n_bins, signed=signed, device=device)
+        return compute_mi_b200(X, gene_names, n_bins=n_bins, signed=signed, device=device,
+                               sign_rule=kwargs.get("sign_rule", "numpy"))
     raise ValueError(f"Unknown MI backend: {backend}")
 
 

@@ -502,3 +502,27 @@ def test_input_formats_match_the_reference_semantics(engine):
     xb, nbb = discretize_genes(B, n_bins=10)
     xbr, nbr = orc.discretize_genes_np(B.astype(np.float32), 10)
     assert np.array_equal(xb, xbr) and np.array_equal(nbb, nbr)
+
+
+def test_rust_sign_rule(engine):
+    """sign_rule="rust" (src/lib.rs:91-94: +1 unless the correlation is negative) against the C port of
+    the Rust tier; where the covariance is exactly zero the Rust tier signs with float64 rounding
+    noise, the exact integer covariance here gives +1."""
+    from genevector_b200.metrics import compute_mi_b200, target_mi
+    from oracle import oracle as orc
+    z = load_golden("synth_counts_700x96_b10")        # has constant and all-zero genes
+    genes = [f"GENE{i}" for i in range(96)]
+    corr = orc.pearson_sign_np(z["X"])                # nan_to_num(corrcoef) as compute_mi_rust passes it
+    want, _ = orc.mi_pairs_c(z["x_disc"].astype(np.int32), z["n_bins_per_gene"], corr=corr, sign_mode=2)
+    got = compute_mi_b200(z["X"], genes, signed=True, sign_rule="rust").matrix.astype(np.float64)
+    exact0 = z["int_sign"] == 0
+    assert np.abs(got - want)[~exact0].max() <= MI_TOL
+    assert np.abs(got - np.abs(want))[exact0].max() <= MI_TOL         # +1 there
+    assert (got[exact0 & (z["mi_raw"] > 0)] > 0).any()
+    # default rule zeroes those pairs; the kwarg travels through the target function
+    dflt = compute_mi_b200(z["X"], genes, signed=True).matrix
+    assert not dflt[exact0].any()
+    via = target_mi(z["X"], genes, signed=True, backend="b200", sign_rule="rust").matrix
+    assert np.array_equal(via, got.astype(np.float32))
+    with pytest.raises(ValueError, match="sign rule"):
+        compute_mi_b200(z["X"], genes, signed=True, sign_rule="julia")
