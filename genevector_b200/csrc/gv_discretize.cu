@@ -65,7 +65,8 @@ __device__ __forceinline__ void write_digits(int8_t* __restrict__ val_rows, int6
 // ---------------------------------------------------------------- k_count_positive
 // flags[0] |= 1 if a value is negative, |= 2 if a positive value is not an integer;
 // flags[1] = max over ceil(values) (as uint64).
-template <typename T>
+// ALL: count every stored entry (the signed rank / entropy regroup), not only x > 0.
+template <typename T, bool ALL = false>
 __global__ void k_count_positive(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
                                  int64_t nnz, uint32_t* __restrict__ cnt,
                                  unsigned long long* __restrict__ flags) {
@@ -74,6 +75,7 @@ __global__ void k_count_positive(const T* __restrict__ values, const int32_t* __
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz;
        e += int64_t(gridDim.x) * blockDim.x) {
     const T v = values[e];
+    if (ALL && !(v > T(0))) atomicAdd(&cnt[col_idx[e]], 1u);
     if (v > T(0)) {
       atomicAdd(&cnt[col_idx[e]], 1u);
       const T c = ceil(v);
@@ -135,7 +137,7 @@ __global__ void k_scan_counts(const uint32_t* __restrict__ cnt, int64_t* __restr
 
 // ---------------------------------------------------------------- k_scatter
 // One warp per CSR row (cell): coalesced reads, scattered 4/8-byte writes into gene segments.
-template <typename T>
+template <typename T, bool ALL = false>
 __global__ void k_scatter(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
                           const int64_t* __restrict__ row_ptr, int64_t n_cells,
                           unsigned long long* __restrict__ cursor, int32_t* __restrict__ g_cell,
@@ -146,7 +148,7 @@ __global__ void k_scatter(const T* __restrict__ values, const int32_t* __restric
     const int64_t e0 = row_ptr[r], e1 = row_ptr[r + 1];
     for (int64_t e = e0 + lane; e < e1; e += 32) {
       const T v = values[e];
-      if (v > T(0)) {
+      if (ALL || v > T(0)) {
         const unsigned long long pos = atomicAdd(&cursor[col_idx[e]], 1ull);
         g_cell[pos] = int32_t(r);
         g_val[pos] = v;
@@ -1098,6 +1100,91 @@ __global__ void k_signed_finish(const SignedGene* __restrict__ sg, int G, int64_
   }
 }
 
+// ---------------------------------------------------------------- signed rank rows
+// Rank rows (val_mode 3) for data with negative values, on per-gene segments that hold EVERY stored
+// entry sorted by value (negatives, explicit zeros, positives).  With n_neg negatives and n_zero zero
+// cells (implicit + explicit), the doubled average rank minus one of a cell is #{y < x} + #{y <= x}:
+//   negatives: their tie range inside the sorted negatives;  zero cells: 2 n_neg + n_zero;
+//   positives: 2 (n_neg + n_zero) + their tie range inside the sorted positives.
+// Pearson of the ranks is shift-invariant: genes without negatives keep the usual shift by n_zero
+// (zero cells hold 0, no fill); the others are stored unshifted and their rows are first filled with
+// the zero cells' value (k_signed_fill), then the stored entries are written.
+template <typename T>
+__global__ void k_rank_params(const int64_t* __restrict__ gene_ptr, const T* __restrict__ s_val, int G,
+                              int64_t n_cells, SignedGene* __restrict__ sg) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+    const int64_t e0 = gene_ptr[g], e1 = gene_ptr[g + 1];
+    int64_t lo = e0, hi = e1;                       // first index with value >= 0
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (s_val[mid] < T(0)) lo = mid + 1; else hi = mid; }
+    const int64_t lbz = lo;
+    hi = e1;                                        // first index with value > 0
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (s_val[mid] <= T(0)) lo = mid + 1; else hi = mid; }
+    const int64_t ubz = lo;
+    const long long n_neg = lbz - e0;
+    const long long n_zero = n_cells - (e1 - e0) + (ubz - lbz);
+    SignedGene s;
+    s.min_key = (unsigned long long)lbz;            // reused: index of the first stored zero
+    s.max_key = (unsigned long long)ubz;            // reused: index of the first positive
+    s.offset = double(n_neg);
+    s.q0 = n_neg > 0 ? 2 * n_neg + n_zero : 0;      // value of the zero cells
+    s.acc1 = 0ull; s.acc2 = 0ull;
+    s.shift = int(n_neg > 0 ? 0 : 1);               // 1: shifted by n_zero (no negatives)
+    s.pad = 0;
+    sg[g] = s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_rank_scatter(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ s_cell,
+               const T* __restrict__ s_val, int G, int64_t n_cells, const SignedGene* __restrict__ sg,
+               int8_t* __restrict__ val_rows, int64_t val_pitch, int n_limbs, int limb_bits,
+               int64_t* __restrict__ gsum, int64_t* __restrict__ gsq) {
+  __shared__ long long red[8][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const int64_t e0 = gene_ptr[g], e1 = gene_ptr[g + 1];
+    const SignedGene s = sg[g];
+    const int64_t lbz = int64_t(s.min_key), ubz = int64_t(s.max_key);
+    const long long n_neg = lbz - e0;
+    const long long n_zero = n_cells - (e1 - e0) + (ubz - lbz);
+    const long long shift = s.shift ? n_zero : 0;
+    const long long q0 = s.q0;
+    long long s1 = 0, s2 = 0;
+    for (int64_t e = e0 + tid; e < e1; e += 256) {
+      const T v = s_val[e];
+      long long q;
+      if (v == T(0)) {
+        q = 2 * n_neg + n_zero - shift;
+      } else {
+        int64_t lo = v < T(0) ? e0 : ubz, hi = e;             // first index holding v
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (s_val[mid] < v) lo = mid + 1; else hi = mid; }
+        const int64_t first = lo;
+        lo = e; hi = (v < T(0) ? lbz : e1) - 1;               // last index holding v
+        while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if (s_val[mid] > v) hi = mid - 1; else lo = mid; }
+        const int64_t last = lo;
+        if (v < T(0)) q = (first - e0) + (last - e0 + 1);
+        else q = 2 * (n_neg + n_zero) + (first - ubz) + (last - ubz + 1) - shift;
+      }
+      write_digits(val_rows, val_pitch, g, s_cell[e], (unsigned long long)q, n_limbs, limb_bits);
+      s1 += q - q0; s2 += q * q - q0 * q0;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    __syncthreads();
+    if (lane == 0) { red[warp][0] = s1; red[warp][1] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+      long long a = 0, b = 0;
+      for (int w = 0; w < 8; ++w) { a += red[w][0]; b += red[w][1]; }
+      gsum[g] = n_cells * q0 + a;
+      gsq[g] = n_cells * q0 * q0 + b;
+    }
+  }
+}
+
 // ================================================================ host-side launchers
 #define GV_LAUNCH_CHECK()                                     \
   do {                                                        \
@@ -1118,9 +1205,9 @@ static int check_val_config(const DiscretizeArgs& a, const unsigned long long* h
   if (n_limbs < 1 || n_limbs > 4 || limb_bits < 1 || limb_bits > 7)
     return set_error(GV_ERR_ARG, "value rows: n_limbs must be in [1,4] and limb_bits in [1,7]");
   const int tb = n_limbs * limb_bits;
-  if ((hflags[0] & 1ull) && a.val_mode != 2)
+  if ((hflags[0] & 1ull) && a.val_mode != 2 && a.val_mode != 3)
     return set_error(GV_ERR_UNSUPPORTED,
-                     "count / rank value rows need non-negative values (negative values found): "
+                     "count value rows need non-negative values (negative values found): "
                      "use the fixed-point value rows (val_mode 2)");
   if (a.val_mode == 0) {
     if (hflags[0] & 2ull)
@@ -1185,7 +1272,9 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     GV_LAUNCH_CHECK();
     GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
     GV_CUDA_TRY(cudaStreamSynchronize(st));
-    const bool eligible = (hflags[0] & 6ull) == 0 && hflags[1] < (unsigned long long)VH;
+    // (rank rows of data with negative values need every stored entry: general path)
+    const bool eligible = (hflags[0] & 6ull) == 0 && hflags[1] < (unsigned long long)VH &&
+                          !(ranks && (hflags[0] & 1ull));
     if (eligible) {
       if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
       int rc = check_val_config(a, hflags);
@@ -1254,20 +1343,46 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     k_scatter<T><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, cursor, g_cell, g_val);
     GV_LAUNCH_CHECK();
   }
-  if (ranks) {
+  // negative values: the value rows come from the signed kernels below instead
+  const bool signed_rows = val_rows != nullptr && a.val_mode == 2 && (hflags[0] & 1ull);
+  const bool signed_ranks = ranks && (hflags[0] & 1ull);
+  int32_t* u_cell = g_cell; T* u_val = g_val;        // the unsorted regroup buffers
+  if (ranks && !signed_ranks) {
     // explicit zeros / negatives are dropped by k_scatter, so the segments hold positives only
     rc = segsort_pairs(sort_tmp, sort_bytes, g_val, s_val, g_cell, s_cell, a.nnz, G, gene_ptr,
                        a.value_dtype, st);
     if (rc != GV_OK) return rc;
     g_cell = s_cell; g_val = s_val;
   }
-  // negative values: the value rows come from the signed fixed-point kernels below instead
-  const bool signed_rows = val_rows != nullptr && a.val_mode == 2 && (hflags[0] & 1ull);
   k_gene_bins<T><<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, 0, st>>>(
       gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
       int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq,
-      signed_rows ? nullptr : val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, a.n_cells);
+      (signed_rows || signed_ranks) ? nullptr : val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs,
+      a.n_cells);
   GV_LAUNCH_CHECK();
+  if (signed_ranks) {
+    // second regroup with every stored entry (the buffers of the first one are free again), sorted
+    SignedGene* sg = static_cast<SignedGene*>(take(size_t(G) * sizeof(SignedGene)));
+    if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
+    GV_CUDA_TRY(cudaMemsetAsync(cnt, 0, size_t(G) * 4, st));
+    k_count_positive<T, true><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.nnz, cnt, flags);
+    GV_LAUNCH_CHECK();
+    k_scan_counts<<<1, 1024, 0, st>>>(cnt, gene_ptr, cursor, G);
+    GV_LAUNCH_CHECK();
+    k_scatter<T, true><<<sms * 8, 256, 0, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, cursor, u_cell, u_val);
+    GV_LAUNCH_CHECK();
+    rc = segsort_pairs(sort_tmp, sort_bytes, u_val, s_val, u_cell, s_cell, a.nnz, G, gene_ptr, a.value_dtype, st);
+    if (rc != GV_OK) return rc;
+    k_rank_params<T><<<(G + 255) / 256, 256, 0, st>>>(gene_ptr, s_val, G, a.n_cells, sg);
+    GV_LAUNCH_CHECK();
+    dim3 fgrid(unsigned((a.n_cells + 4095) / 4096 < 64 ? (a.n_cells + 4095) / 4096 : 64),
+               unsigned(G < 65535 ? G : 65535));
+    k_signed_fill<<<fgrid, 256, 0, st>>>(sg, G, a.n_cells, val_rows, a.val_pitch, n_limbs, a.val_limb_bits);
+    GV_LAUNCH_CHECK();
+    k_rank_scatter<T><<<G < sms * 8 ? G : sms * 8, 256, 0, st>>>(gene_ptr, s_cell, s_val, G, a.n_cells, sg, val_rows,
+                                                             a.val_pitch, n_limbs, a.val_limb_bits, a.gsum, a.gsq);
+    GV_LAUNCH_CHECK();
+  }
   if (signed_rows) {
     SignedGene* sg = static_cast<SignedGene*>(take(size_t(G) * sizeof(SignedGene)));
     if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
@@ -1297,42 +1412,66 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- gene entropy, general data
-// Sorted gene segments (positives only): runs of equal values are the unique values, their lengths
-// the counts; the zero count is n_cells - m and is the one np.unique lists first (data.py:201-202
-// drops it); a gene without zeros loses its smallest positive value's count instead.
+// Per-gene segments holding every stored entry sorted by value: runs of equal values are the unique
+// values of np.unique (data.py:198), the zero run also takes the cells without an entry; the count of
+// the smallest value is dropped (data.py:201-202: the zeros, unless the gene has negative values or
+// no zero at all) and scipy.stats.entropy (natural log) is taken of the rest.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_gene_entropy_sorted(const int64_t* __restrict__ gene_ptr, const T* __restrict__ s_val, int G,
                       int64_t n_cells, double* __restrict__ ent) {
   __shared__ double red[8];
+  __shared__ int64_t s_lbz, s_ubz;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int64_t e0 = gene_ptr[g], e1 = gene_ptr[g + 1];
     const int64_t m = e1 - e0;
+    __syncthreads();
+    if (tid == 0) {
+      int64_t lo = e0, hi = e1;                     // first index with value >= 0
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (s_val[mid] < T(0)) lo = mid + 1; else hi = mid; }
+      s_lbz = lo;
+      hi = e1;                                      // first index with value > 0
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (s_val[mid] <= T(0)) lo = mid + 1; else hi = mid; }
+      s_ubz = lo;
+    }
+    __syncthreads();
+    const int64_t lbz = s_lbz, ubz = s_ubz;
+    const int64_t n_zero = n_cells - m + (ubz - lbz);
     auto run_end = [&](int64_t e) {          // last index holding s_val[e]
       const T v = s_val[e];
       int64_t lo = e, hi = e1 - 1;
       while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if (s_val[mid] > v) hi = mid - 1; else lo = mid; }
       return lo;
     };
-    int64_t first_kept = e0;                 // a gene without zeros drops its first run
-    if (m > 0 && m == n_cells) first_kept = run_end(e0) + 1;
-    const double kept = double(e1 - first_kept);
+    // the dropped first value: the smallest negative run, else the zeros, else the smallest positive run
+    int64_t first_stored = e0;               // stored runs start here after the drop
+    bool zeros_kept = n_zero > 0;
+    int64_t dropped;
+    if (lbz > e0) { const int64_t r = run_end(e0); dropped = r - e0 + 1; first_stored = r + 1; }
+    else if (n_zero > 0) { dropped = n_zero; zeros_kept = false; }
+    else if (m > 0) { const int64_t r = run_end(e0); dropped = r - e0 + 1; first_stored = r + 1; }
+    else dropped = 0;
+    const double kept = double(n_cells - dropped);
     double h = 0.0;
-    for (int64_t e = first_kept + tid; e < e1; e += 256) {
-      if (e == first_kept || s_val[e - 1] != s_val[e]) {
+    for (int64_t e = first_stored + tid; e < e1; e += 256) {
+      if (e >= lbz && e < ubz) continue;     // stored zeros belong to the zero run below
+      if (e == first_stored || e == ubz || s_val[e - 1] != s_val[e]) {
         const double pk = double(run_end(e) - e + 1) / kept;
         h -= pk * log(pk);
       }
     }
+    if (tid == 0 && zeros_kept && kept > 0.0) {
+      const double pk = double(n_zero) / kept;
+      h -= pk * log(pk);
+    }
     for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
-    __syncthreads();
     if (lane == 0) red[warp] = h;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
       for (int w = 0; w < 8; ++w) t += red[w];
-      ent[g] = t;
+      ent[g] = kept > 0.0 ? t : 0.0;
     }
   }
 }
@@ -1358,9 +1497,7 @@ static int gene_entropy_impl(const void* values_v, const int32_t* col_idx, const
   unsigned long long hflags[2] = {0, 0};
   GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
   GV_CUDA_TRY(cudaStreamSynchronize(st));
-  if (hflags[0] & 1ull)
-    return set_error(GV_ERR_UNSUPPORTED, "gene entropy needs non-negative values");
-  if ((hflags[0] & 2ull) == 0 && hflags[1] < (unsigned long long)VH) {
+  if ((hflags[0] & 3ull) == 0 && hflags[1] < (unsigned long long)VH) {
     k_gene_entropy<<<(G + 7) / 8, 256, 0, st>>>(hist, G, n_cells, ent);
     GV_LAUNCH_CHECK();
     return GV_OK;
@@ -1380,11 +1517,12 @@ static int gene_entropy_impl(const void* values_v, const int32_t* col_idx, const
   void* sort_tmp = take(sort_bytes);
   if (off > ws_bytes) return set_error(GV_ERR_ARG, "gene entropy: workspace too small");
   GV_CUDA_TRY(cudaMemsetAsync(cnt, 0, size_t(G) * 4, st));
-  k_count_positive<T><<<sms * 8, 256, 0, st>>>(values, col_idx, nnz, cnt, flags);
+  // every stored entry (negatives and explicit zeros too) goes into the per-gene segments
+  k_count_positive<T, true><<<sms * 8, 256, 0, st>>>(values, col_idx, nnz, cnt, flags);
   GV_LAUNCH_CHECK();
   k_scan_counts<<<1, 1024, 0, st>>>(cnt, gene_ptr, cursor, G);
   GV_LAUNCH_CHECK();
-  k_scatter<T><<<sms * 8, 256, 0, st>>>(values, col_idx, row_ptr, n_cells, cursor, g_cell, g_val);
+  k_scatter<T, true><<<sms * 8, 256, 0, st>>>(values, col_idx, row_ptr, n_cells, cursor, g_cell, g_val);
   GV_LAUNCH_CHECK();
   int rc = segsort_pairs(sort_tmp, sort_bytes, g_val, s_val, g_cell, s_cell, nnz, G, gene_ptr, dt, st);
   if (rc != GV_OK) return rc;

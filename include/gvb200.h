@@ -106,8 +106,9 @@ int gv_device_check(void);
  *                                gene has negative values), e_g per gene such that the largest shifted
  *                                value lands just below 2^(val_limbs*val_limb_bits) (any float data;
  *                                Pearson, its sign and xcorr depend on neither, cosine undoes o_g);
- *                              3 doubled average rank minus (n_zero + 1) (Spearman; needs
- *                                2*n_cells < 2^(val_limbs*val_limb_bits)).
+ *                              3 doubled average rank minus one, #{y < x} + #{y <= x} over all cells
+ *                                (minus n_zero for genes without negative values, whose zero cells
+ *                                then hold 0) (Spearman; needs 2*n_cells < 2^(val_limbs*val_limb_bits)).
  *                            gsum / gsq are then the sums of that integer and of its square.
  *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen;
  *                            [1] = max ceil(value)
@@ -129,8 +130,8 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
 /* ---------------------------------------------------------------- gene entropy
  * Replaces GeneVectorDataset.get_gene_entropy (data.py:186-203), which runs before every score
  * computation (data.py:349): per gene the entropy (nats) of the counts of its unique values after
- * dropping the first.  Non-negative data: integer counts <= 255 take a value-histogram path, anything
- * else a per-gene sort (needs row_ptr and nnz < 2^31).  entropy_out float64 [n_genes];
+ * dropping the first.  Non-negative integer counts <= 255 take a value-histogram path, anything else
+ * (floats, negative values) a per-gene sort of every stored entry (needs row_ptr and nnz < 2^31).  entropy_out float64 [n_genes];
  * workspace >= gv_discretize_workspace_bytes(nnz, n_cells, n_genes, value_dtype, 1) bytes. */
 int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
                     const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int n_genes,

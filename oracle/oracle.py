@@ -266,16 +266,19 @@ def spearman_np(X):
 
 def rank_rows_np(X):
     """What the B200 path contracts for Spearman (checker for the value rows, not reference code):
-    per gene, 2 * average rank - (n_zero + 1) as integers [n_genes][n_cells]; zero cells map to 0."""
+    per gene #{y < x} + #{y <= x} = 2 * average rank - 1 as integers [n_genes][n_cells]; genes without
+    negative values are shifted by their number of zero cells, so that those cells hold 0."""
     from scipy.stats import rankdata
     Xd = _dense(X)
-    n_cells = Xd.shape[0]
     out = np.zeros(Xd.T.shape, dtype=np.int64)
     for g in range(Xd.shape[1]):
         col = Xd[:, g]
-        n_zero = int((col <= 0).sum())
-        r2 = np.rint(2 * rankdata(col, method="average")).astype(np.int64) - (n_zero + 1)
-        out[g] = np.where(col > 0, r2, 0)
+        r2m1 = np.rint(2 * rankdata(col, method="average")).astype(np.int64) - 1
+        if (col < 0).any():
+            out[g] = r2m1
+        else:
+            n_zero = int((col == 0).sum())
+            out[g] = np.where(col > 0, r2m1 - n_zero, 0)
     return out
 
 

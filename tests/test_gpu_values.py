@@ -307,11 +307,23 @@ def test_negative_values_signed_fixed_point(engine, dtype):
     want_mi, _ = orc.mi_pairs_c(xd, nb, corr=ref_sign.astype(np.float64), sign_mode=1)
     got_mi = compute_mi_b200(X, genes, signed=True).matrix.astype(np.float64)
     assert np.abs(got_mi - want_mi).max() <= MI_TOL
-    # ranks and unique-value entropies of data with negative values are refused loudly
+    # ranks over every stored entry (negatives, explicit zeros, positives) and the zero cells
+    blk3 = engine.discretize(csr, 10, val_mode=3)
+    R = orc.rank_rows_np(X)
+    assert blk3.val_mode == 3 and np.array_equal(blk3.gene_values(), R)
+    assert np.array_equal(blk3.gsum.cpu().numpy(), R.sum(axis=1))
+    assert np.array_equal(blk3.gsq.cpu().numpy(), (R * R).sum(axis=1))
+    assert np.array_equal(blk3.x_disc(), xd)
+    sp_got = target_spearman(X, genes).matrix.astype(np.float64)
+    sp_want = orc.spearman_np(X); np.fill_diagonal(sp_want, 0.0)
+    oks = ~np.isnan(sp_want)
+    assert np.abs(sp_got[oks] - sp_want[oks]).max() <= 1e-7 and np.array_equal(np.isnan(sp_got), np.isnan(sp_want))
+    # unique-value entropy (data.py:186-203): the dropped first value is now the smallest negative one
+    ent = get_gene_entropy(X, genes)
+    assert np.abs(np.array([ent[g] for g in genes]) - orc.gene_entropy_np(X)).max() < 1e-12
+    # count digits cannot hold negative values
     with pytest.raises(GvError, match="non-negative"):
-        target_spearman(X, genes)
-    with pytest.raises(GvError, match="non-negative"):
-        get_gene_entropy(X, genes)
+        engine.discretize(csr, 10, val_mode=0, n_limbs=1)
 
 
 def test_graph_xcorr_standard_normal_like_the_reference_tests(engine):
