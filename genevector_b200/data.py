@@ -4,6 +4,8 @@ Mirrors the two methods of the reference's dataset that sit on the co-expression
 
     compute_target_scores(...)   = GeneVectorDataset._compute_target_scores     data.py:292-334
     build_training_tensors(...)  = GeneVectorDataset._build_training_tensors    data.py:377-411
+    save_target_scores / load_target_scores                                      data.py:235-251
+    get_gene_entropy(...)        = GeneVectorDataset.get_gene_entropy            data.py:186-203
 
 The first dispatches to the B200 targets (with the reference's cache protocol); the second turns a
 ScoreMatrix into the (i_idx, j_idx, xij) training tensors with one CUDA kernel
@@ -75,6 +77,26 @@ def build_training_tensors(scores, genes, c=100.0, signed_mi=True, device="cuda"
                   0 if signed_mi else 1, 1, i_idx.data_ptr(), j_idx.data_ptr(), xij.data_ptr(),
                   torch.cuda.current_stream(eng.device).cuda_stream)
     return i_idx, j_idx, xij
+
+
+def save_target_scores(scores, genes, filepath):
+    """GeneVectorDataset.save_target_scores (data.py:235-239) on the matrix path.  The reference derives
+    a cache key from the path and writes into the cache directory (its defect 9 in SURVEY Appendix D is
+    kept: same file, same schema), so a file written here is found by the reference and vice versa."""
+    from .cache import save_scores
+    key = filepath.replace(".npz", "").replace("/", "_")
+    return save_scores(key, scores, list(genes))
+
+
+def load_target_scores(filepath):
+    """GeneVectorDataset.load_target_scores (data.py:241-251) without the G^2 Python loop: the .npz
+    schema of the cache (`scores` float32 [G][G], `genes`) straight into a ScoreMatrix.  Exact zeros
+    read 0.0 through the mapping, which is what the reference's defaultdict yields for the pairs it
+    drops (data.py:250)."""
+    data = np.load(filepath, allow_pickle=False)
+    matrix = np.array(data["scores"], dtype=np.float32)
+    np.fill_diagonal(matrix, 0.0)
+    return ScoreMatrix(matrix, [str(g) for g in data["genes"]])
 
 
 def get_gene_entropy(X, gene_names, device="cuda"):

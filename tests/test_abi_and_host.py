@@ -335,3 +335,15 @@ def test_reference_consumers_accept_the_score_matrix(tmp_path, monkeypatch):
     assert np.abs(m1 - m2).max() <= 1e-6
     back, g2 = refc.load_scores(key)
     assert g2 == genes and abs(back[genes[0]][genes[1]] - M[0, 1]) <= 1.1e-5
+    # save_target_scores / load_target_scores (data.py:235-251): files are interchangeable
+    from genevector_b200 import data as our_data
+    monkeypatch.setattr(our_cache, "CACHE_DIR", str(tmp_path))
+    ds = object.__new__(refd.GeneVectorDataset)
+    ds.data, ds.mi_scores = types.SimpleNamespace(genes=genes), theirs
+    ds.save_target_scores("run1/scores.npz")
+    path_ours = our_data.save_target_scores(ours, genes, "run2/scores.npz")
+    assert os.path.basename(path_ours) == "scores_run2_scores.npz"
+    got = our_data.load_target_scores(refc.get_cache_path("run1_scores"))
+    assert got.genes == genes and np.abs(got.rounded() - M).max() <= 1.1e-5
+    ds.load_target_scores(path_ours)
+    assert abs(ds.mi_scores[genes[0]][genes[1]] - M[0, 1]) <= 1.1e-5 and genes[0] not in ds.mi_scores[genes[0]]
