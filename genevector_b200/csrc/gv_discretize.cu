@@ -85,6 +85,7 @@ __global__ void k_count_positive(const T* __restrict__ values, const int32_t* __
     } else if (v < T(0)) {
       f |= 1u;
     }
+    if (!(v - v == T(0))) f |= 8u;           // NaN or infinity
   }
   f = __reduce_or_sync(0xffffffffu, f);
   for (int d = 16; d >= 1; d >>= 1) {
@@ -584,6 +585,7 @@ __global__ void k_hist2d(const T* __restrict__ values, const int32_t* __restrict
     } else if (v < T(0)) {
       f |= 1u;
     }
+    if (!(v - v == T(0))) f |= 8u;           // NaN or infinity
   }
   f = __reduce_or_sync(0xffffffffu, f);
   for (int d = 16; d >= 1; d >>= 1) {
@@ -713,7 +715,7 @@ __device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bin
 
 // ---------------------------------------------------------------- k_transpose_counts
 // flags[0] |= 1 negative value, |= 2 fractional value, |= 4 column indices of a row not ascending
-// (the walk below needs canonical CSR; the caller then takes the general path);
+// (the walk below needs canonical CSR; the caller then takes the general path), |= 8 NaN / infinity;
 // flags[1] = max over ceil(values).
 constexpr int TP_CB = 128;                 // cells per CTA block = bytes per output line
 constexpr int TP_STRIDE = TP_CB + 4;       // tile row stride: 33 words, conflict-free both ways
@@ -797,6 +799,7 @@ k_transpose_counts(const T* __restrict__ values, const int32_t* __restrict__ col
               } else if (v < T(0)) {
                 f |= 1u;
               }
+              if (!(v - v == T(0))) f |= 8u;   // NaN or infinity
             }
             const int cnt = __popc(__ballot_sync(0xffffffffu, in));
             cur[k] += cnt;
@@ -1205,6 +1208,10 @@ static int check_val_config(const DiscretizeArgs& a, const unsigned long long* h
   if (n_limbs < 1 || n_limbs > 4 || limb_bits < 1 || limb_bits > 7)
     return set_error(GV_ERR_ARG, "value rows: n_limbs must be in [1,4] and limb_bits in [1,7]");
   const int tb = n_limbs * limb_bits;
+  if (hflags[0] & 8ull)
+    return set_error(GV_ERR_UNSUPPORTED,
+                     "NaN or infinite values: the correlation-type scores are undefined for such genes "
+                     "(the discretisation alone treats NaN as not expressed, like the reference)");
   if ((hflags[0] & 1ull) && a.val_mode != 2 && a.val_mode != 3)
     return set_error(GV_ERR_UNSUPPORTED,
                      "count value rows need non-negative values (negative values found): "
@@ -1273,7 +1280,7 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
     GV_CUDA_TRY(cudaStreamSynchronize(st));
     // (rank rows of data with negative values need every stored entry: general path)
-    const bool eligible = (hflags[0] & 6ull) == 0 && hflags[1] < (unsigned long long)VH &&
+    const bool eligible = (hflags[0] & 14ull) == 0 && hflags[1] < (unsigned long long)VH &&
                           !(ranks && (hflags[0] & 1ull));
     if (eligible) {
       if (a.data_flags_out) { a.data_flags_out[0] = hflags[0]; a.data_flags_out[1] = hflags[1]; }
@@ -1497,6 +1504,7 @@ static int gene_entropy_impl(const void* values_v, const int32_t* col_idx, const
   unsigned long long hflags[2] = {0, 0};
   GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
   GV_CUDA_TRY(cudaStreamSynchronize(st));
+  if (hflags[0] & 8ull) return set_error(GV_ERR_UNSUPPORTED, "gene entropy: NaN or infinite values");
   if ((hflags[0] & 3ull) == 0 && hflags[1] < (unsigned long long)VH) {
     k_gene_entropy<<<(G + 7) / 8, 256, 0, st>>>(hist, G, n_cells, ent);
     GV_LAUNCH_CHECK();

@@ -110,8 +110,8 @@ int gv_device_check(void);
  *                                (minus n_zero for genes without negative values, whose zero cells
  *                                then hold 0) (Spearman; needs 2*n_cells < 2^(val_limbs*val_limb_bits)).
  *                            gsum / gsq are then the sums of that integer and of its square.
- *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen;
- *                            [1] = max ceil(value)
+ *   data_flags_out_host[2] : [0] bit0 = negative value seen, bit1 = fractional value seen, bit3 = NaN or
+ *                            infinity seen (value rows are then refused); [1] = max ceil(value)
  *   workspace              : >= gv_discretize_workspace_bytes(nnz, n_cells, n_genes, value_dtype, sorted) bytes,
  *                            sorted = 1 when val_mode is 3 (the rank rows of non-count data need a
  *                            per-gene sort: twice the regroup scratch)

@@ -341,3 +341,27 @@ def test_graph_xcorr_standard_normal_like_the_reference_tests(engine):
         assert np.abs(s.matrix.astype(np.float64) - orc.graph_xcorr_np(X, adj)).max() <= F32_TOL
         s2 = target_graph_xcorr(X, genes, graph=adj, aggr_params={"include_self": True})
         assert np.abs(s2.matrix.astype(np.float64) - orc.graph_xcorr_np(X, adj, True)).max() <= F32_TOL
+
+
+def test_nan_values_are_not_silently_turned_into_zeros(engine):
+    """NaN > 0 is False, so the reference bins NaN as "not expressed" (metrics.py:53) -- reproduced --
+    while its np.corrcoef turns the whole gene into NaN; the co-moment paths refuse such input loudly
+    instead of treating NaN as 0."""
+    from genevector_b200.engine import GvError
+    from genevector_b200.metrics import compute_mi_b200, target_pearson
+    from genevector_b200.synth import synth_counts, gene_names
+    from oracle import oracle as orc
+    X = synth_counts(400, 30, seed=4)
+    X.data[11] = np.nan
+    genes = gene_names(30)
+    csr = engine.upload_csr(X)
+    blk = engine.discretize(csr, 10)
+    with np.errstate(invalid="ignore"):
+        xd, nb = orc.discretize_genes_np(X, 10)
+    assert np.array_equal(blk.x_disc(), xd) and np.array_equal(blk.n_bins_per_gene.cpu().numpy(), nb)
+    assert blk.data_flags[0] & 8
+    got = compute_mi_b200(X, genes, signed=False).matrix.astype(np.float64)
+    assert np.abs(got - orc.mi_pairs_c(xd, nb)[0]).max() <= MI_TOL
+    for fn in (lambda: compute_mi_b200(X, genes, signed=True), lambda: target_pearson(X, genes)):
+        with pytest.raises(GvError, match="NaN"):
+            fn()
