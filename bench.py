@@ -221,12 +221,18 @@ def run_matrix_target(args):
         flush.fill_(1)
         eng.target_from_csr(csr, kind, ranks=ranks, n_cells=N, n_genes=G, rank=rank, world=world, out=out)
 
+    h2d_events = []
+
     def step_e2e():
         flush.fill_(1)
         c = None
         if rank == 0:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             c = CsrDevice(host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
                           host[2].to(dev, non_blocking=True), N, G)
+            e1.record()
+            h2d_events.append((e0, e1))
         eng.target_from_csr(c, kind, ranks=ranks, n_cells=N, n_genes=G, rank=rank, world=world, out=out)
         res_host.copy_(out, non_blocking=True)
 
@@ -279,7 +285,7 @@ def run_matrix_target(args):
         "e2e": {"value": pairs / (ms_e2e / args.steps * 1e-3), "unit": "gene-pairs/s",
                 "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) if host else 0,
-                "d2h_bytes_per_step": int(G * G * 4)},
+                "d2h_bytes_per_step": int(G * G * 4), "h2d_ms": h2d_ms},
         "gpu_launches": int(sum(k for (_, _, _, k) in kev)),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": None, "kernel_ms": mom_ms,
