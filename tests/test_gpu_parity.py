@@ -526,3 +526,30 @@ def test_rust_sign_rule(engine):
     assert np.array_equal(via, got.astype(np.float32))
     with pytest.raises(ValueError, match="sign rule"):
         compute_mi_b200(z["X"], genes, signed=True, sign_rule="julia")
+
+
+@pytest.mark.parametrize("extra", [[], ["--operand", "int8"], ["--unsigned"], ["--target", "pearson"],
+                                   ["--target", "spearman"], ["--target", "jaccard"]])
+def test_bench_lines_carry_the_contract_keys(extra):
+    """bench.py on a small workload: one JSON line on stdout with every key of the bench contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "C2", "--steps", "2",
+                        "--warmup", "1", "--no-cpu-baseline"] + extra, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert key in d, key
+    assert d["metric"] == "gene-pairs/s" and d["value"] > 0 and d["gpu_launches"] > 0
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in d["e2e"], key
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in d["roofline"], key
+    assert 0 < d["roofline"]["frac"] < 1.05 and "workload" in d["config"]
