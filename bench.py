@@ -278,7 +278,7 @@ def run_matrix_target(args):
         "metric": "gene-pairs/s", "value": pairs / (ms_dev / args.steps * 1e-3), "unit": "gene-pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
+        "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"{wl}: all-pairs {args.target}, {G} genes x {N} cells", "pairs": pairs,
                    "cta_group": args.cta_group, "l2": "L2 flushed between steps",
                    "parallelism": f"tile-sharded x{world}, 1 broadcast" if world > 1 else "single GPU"},
@@ -468,7 +468,9 @@ def main():
     line = {
         "metric": "gene-pairs/s", "value": pairs / (ms_dev / args.steps * 1e-3), "unit": "gene-pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        # arithmetic type of the contraction: one-hot operands in E2M1 (fp4) or INT8, exact integer counts
+        "dtype": "fp4" if fp4 else "int8",
         "data": "synthetic",
         "config": {"workload": f"{wl}: all-pairs {'signed ' if signed else ''}MI, {G} genes x {N} cells, "
                                f"n_bins={N_BINS}, nnz={nnz}",
