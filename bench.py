@@ -4,12 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C3|C2|GxN] [--impl reference]
 
 One step = one full pass of the hot path over the synthetic count matrix of the workload:
-discretise (rank 0) -> one NCCL broadcast of the bin block (N > 1) -> one-hot expansion ->
-Pearson-sign tiles -> INT8 tcgen05 contraction with the fused MI epilogue over this rank's slice
-of the upper-triangular tile schedule.  `value` times it with the CSR already in HBM; `e2e` times
-the same through host buffers (pinned CSR -> device, result rows -> pinned host) inside the timed
-region.  Prints ONE JSON line (rank 0).  The default workload is BASELINE.json's headline
-configuration, 20,000 genes x 200,000 cells (C4), which fits one B200.
+discretise -> (N > 1: replicate the discretised matrix) -> one-hot expansion -> Pearson-sign tiles ->
+tcgen05 contraction with the fused MI epilogue over this rank's slice of the upper-triangular tile
+schedule.  `value` times it with the CSR already in HBM; `e2e` times the reference-facing plugin call
+itself, genevector_b200.metrics.target_mi(scipy CSR on the host, gene names, signed=True,
+backend="b200") (what data.py:319-326 calls), from pageable host arrays to the full ScoreMatrix on
+rank 0 -- host -> device copies, result assembly and device -> host copies inside the timed region.
+Prints ONE JSON line (rank 0).  The default workload is BASELINE.json's headline configuration,
+20,000 genes x 200,000 cells (C4), which fits one B200.
 
 --impl reference times the reference's CPU implementation of the path instead: the C/OpenMP port
 of src/lib.rs + discretize_genes + np.corrcoef (oracle/, the Rust original cannot be built here),
@@ -48,6 +50,11 @@ class StdoutGuard:
 
 N_BINS = 10
 L2_BYTES = 126 * 1024 * 1024
+
+
+def workload_name(wl, G, N, signed=True):
+    """The one workload string both arms print (the gene subsample of the CPU arm is in `sample`)."""
+    return f"{wl}: all-pairs {'signed ' if signed else ''}MI, {G} genes x {N} cells, n_bins={N_BINS}"
 
 
 def parse_workload(name):
@@ -119,7 +126,15 @@ def cpu_reference(n_cells, n_genes_workload, steps, warmup, target_s=8.0, seed=0
     Per step: discretize_genes + np.corrcoef sign + all-pairs MI (lib.rs:30-98) on S genes x all cells."""
     from oracle import oracle as orc
     from genevector_b200.synth import synth_counts
-    cores = orc.num_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its own thread count
+    # (all host cores) for the C port and for numpy's BLAS
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = orc.set_num_threads(ncpu)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncpu)
+    except Exception:
+        pass
 
     phases = {"discretize_genes": [], "corrcoef_sign": [], "mi_pairs": []}
 
@@ -154,7 +169,10 @@ def cpu_reference(n_cells, n_genes_workload, steps, warmup, target_s=8.0, seed=0
     return {"value": pairs / t, "unit": "gene-pairs/s", "cores": cores, "kind": "port",
             "phases_ms": {k: float(np.mean(v)) for k, v in phases.items()},
             "sample": f"{S} genes x {n_cells} cells ({int(pairs)} pairs) of the workload's generator, "
-                      f"discretize + corrcoef sign + all-pairs MI per step, mean of {len(times)} steps",
+                      f"discretize + corrcoef sign + all-pairs MI per step, mean of {len(times)} steps; "
+                      "C/OpenMP port of src/lib.rs (oracle/gv_oracle.c): the Rust tier cannot be built here and "
+                      "the reference's Numba tier (BASELINE.md 4(i)) is not on the GPU box -- its builder-run "
+                      "timing beside this port is in profiles/r02_cpu_numba_vs_port.txt",
             "ms_per_step": t * 1e3}
 
 
@@ -169,13 +187,77 @@ def run_reference_arm(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{wl}: all-pairs signed MI, {G} genes x {N} cells, n_bins={N_BINS}",
+            "config": {"workload": workload_name(wl, G, N, True),
                        "note": "CPU path timed on a gene sample; pairs/s is per-pair throughput at this cell count"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_ms")},
             "e2e": {"value": r["value"], "unit": "gene-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     guard.emit(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------ shared pieces
+def setup_dist():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev
+
+
+def synthetic_input(N, G, dev, keep_device):
+    """The workload's matrix as every caller of the reference holds it: a scipy CSR in pageable host
+    memory (drawn on this rank's GPU, same seed on every rank).  keep_device: also return it resident
+    on the device for the device-timed leg."""
+    import scipy.sparse as sp
+    import torch
+    from genevector_b200.engine import CsrDevice
+    from genevector_b200.synth import synth_counts_torch
+    vals, cols, ptr = synth_counts_torch(N, G, seed=0, device=dev)
+    X = sp.csr_matrix((vals.cpu().numpy(), cols.cpu().numpy(), ptr.cpu().numpy().astype(np.int32)
+                       if int(ptr[-1]) < 2 ** 31 else ptr.cpu().numpy()), shape=(N, G))
+    csr = CsrDevice(vals, cols, ptr, N, G) if keep_device else None
+    torch.cuda.synchronize()
+    return X, csr
+
+
+def make_timed(world, dev):
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps between barriers; CUDA events on the launching stream and the host clock around
+        them (a step that ends in host work is not over when its last kernel is), max over ranks."""
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms = torch.tensor([max(ev0.elapsed_time(ev1), 0.0), (t1 - t0) * 1e3], dtype=torch.float64, device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0].item()), float(ms[1].item())
+
+    return barrier, timed
+
+
+def csr_bytes(X):
+    return int(X.data.nbytes + X.indices.nbytes + (X.shape[0] + 1) * 8)
 
 
 # ------------------------------------------------------------------------------ matrix targets
@@ -186,69 +268,35 @@ def run_matrix_target(args):
     import torch
     import torch.distributed as dist
     from genevector_b200 import _lib
-    from genevector_b200.engine import Engine, CsrDevice, value_rows
-    from genevector_b200.synth import synth_counts_torch
+    from genevector_b200 import metrics as gm
+    from genevector_b200.engine import get_engine
+    from genevector_b200.synth import gene_names
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local, dev = setup_dist()
     wl, G, N = parse_workload(args.workload if args.workload != "C4" else "C5")
     pairs = G * (G - 1) // 2
     kind = {"pearson": _lib.GV_MOM_PEARSON, "spearman": _lib.GV_MOM_PEARSON, "cosine": _lib.GV_MOM_COSINE,
             "jaccard": _lib.GV_MOM_JACCARD}[args.target]
     ranks = args.target == "spearman"
-    eng = Engine(dev, cta_group=args.cta_group)
-    csr = host = None
-    if rank == 0:
-        vals, cols, ptr = synth_counts_torch(N, G, seed=0, device=dev)
-        csr = CsrDevice(vals, cols, ptr, N, G)
-        host = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (vals, cols, ptr))
-        torch.cuda.synchronize()
+    eng = get_engine(dev)
+    eng.cta_group = args.cta_group
+    X, csr = synthetic_input(N, G, dev, keep_device=(rank == 0))
+    genes = gene_names(G)
     out = torch.zeros((G, G), dtype=torch.float32, device=dev)
-    res_host = torch.empty((G, G), dtype=torch.float32, pin_memory=True) if rank == 0 or world > 1 else None
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier, timed = make_timed(world, dev)
+    public = {"pearson": gm.target_pearson, "spearman": gm.target_spearman, "cosine": gm.target_cosine,
+              "jaccard": gm.target_jaccard}[args.target]
 
     def step_device():
         flush.fill_(1)
         eng.target_from_csr(csr, kind, ranks=ranks, n_cells=N, n_genes=G, rank=rank, world=world, out=out)
 
-    h2d_events = []
+    last = [None]
 
     def step_e2e():
         flush.fill_(1)
-        c = None
-        if rank == 0:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            c = CsrDevice(host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
-                          host[2].to(dev, non_blocking=True), N, G)
-            e1.record()
-            h2d_events.append((e0, e1))
-        eng.target_from_csr(c, kind, ranks=ranks, n_cells=N, n_genes=G, rank=rank, world=world, out=out)
-        res_host.copy_(out, non_blocking=True)
-
-    def timed(fn, steps):
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(steps):
-            fn()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        barrier()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        last[0] = public(X, genes, device=dev)
 
     for _ in range(args.warmup):
         step_device()
@@ -257,18 +305,17 @@ def run_matrix_target(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, args.steps)
+    ms_dev, _ = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     kev = eng.kernel_events
     eng.kernel_events = None
     phase_ms = {}
     for name, a, b, _ in kev:
         phase_ms.setdefault(name, []).append(a.elapsed_time(b))
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(3, args.warmup)):
         step_e2e()
-    h2d_events.clear()
-    ms_e2e = timed(step_e2e, args.steps)
-    h2d_ms = float(np.mean([a.elapsed_time(b) for a, b in h2d_events])) if h2d_events else 0.0
+    ms_e2e_ev, ms_e2e_wall = timed(step_e2e, args.steps)
+    ms_e2e = max(ms_e2e_ev, ms_e2e_wall)
 
     mom_ms = float(np.mean(phase_ms["gv_moment_tiles"]))
     alg_ops = pairs / world * 2.0 * N                      # 2*N ops per pair
@@ -284,8 +331,9 @@ def run_matrix_target(args):
                    "parallelism": f"tile-sharded x{world}, 1 broadcast" if world > 1 else "single GPU"},
         "e2e": {"value": pairs / (ms_e2e / args.steps * 1e-3), "unit": "gene-pairs/s",
                 "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) if host else 0,
-                "d2h_bytes_per_step": int(G * G * 4), "h2d_ms": h2d_ms},
+                "h2d_bytes_per_step": csr_bytes(X), "d2h_bytes_per_step": int(G * G * 4),
+                "note": f"genevector_b200.metrics.target_{args.target}(scipy CSR on the host, gene names) -> full "
+                        "ScoreMatrix on rank 0 (pageable host arrays in, shared page-locked host matrix out)"},
         "gpu_launches": int(sum(k for (_, _, _, k) in kev)),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": None, "kernel_ms": mom_ms,
@@ -298,12 +346,59 @@ def run_matrix_target(args):
     }
     if rank == 0:
         guard.emit(json.dumps(line))
+    last[0] = None
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
 # ------------------------------------------------------------------------------ B200 arm
+def parity_check(eng, csr, sm, G, N, signed, rank, world, n_sample=12, seed=0):
+    """Rank 0 recomputes, single rank, a seeded sample of tiles that OTHER ranks own and compares them
+    bit for bit with the matrix the ranks assembled in the shared host matrix."""
+    import torch
+    from genevector_b200 import _lib
+    from genevector_b200.engine import schedule_host, rank_bounds
+    B = eng.lib.gv_rows_per_gene(N_BINS)
+    gpb = 32 // B
+    op_rows = eng.lib.gv_onehot_rows(G, B)
+    th, tile_m = schedule_host(op_rows, eng.cta_group, eng.band)
+    b = rank_bounds(th, tile_m, eng.band, world)
+    rng = np.random.default_rng(seed)
+    pick = []
+    for r in range(1, world):
+        if b[r + 1] > b[r]:
+            pick += list(rng.integers(b[r], b[r + 1], size=max(1, n_sample // (world - 1))))
+    pick = np.array(sorted(set(int(t) for t in pick)), dtype=np.int64)
+    tiles_h = np.ascontiguousarray(th[pick])
+    blk = eng.discretize(csr, N_BINS, 0 if signed else -1)
+    onehot, B = eng.expand_onehot(blk)
+    sgn = eng.sign_matrix(blk, tiles=eng.sign_tiles_for(tiles_h, B, blk.n_limbs)) if signed else None
+    out = torch.zeros((G, G), dtype=torch.float32, device=eng.device)
+    tiles_d = torch.from_numpy(tiles_h).to(eng.device)
+    fmt = _lib.GV_OPERAND_FP4 if onehot.dtype == torch.uint8 else _lib.GV_OPERAND_INT8
+    _lib.call("gv_mi_tiles", onehot.data_ptr(), onehot.shape[0], onehot.shape[1], B, blk.marg.data_ptr(),
+              sgn.data_ptr() if sgn is not None else None, sgn.stride(0) if sgn is not None else 0, G,
+              tiles_d.data_ptr(), len(tiles_h), out.data_ptr(), out.stride(0), eng.cta_group, fmt, None,
+              torch.cuda.current_stream(eng.device).cuda_stream)
+    torch.cuda.synchronize()
+    identical, entries = True, 0
+    for r0, c0 in tiles_h:
+        g0, g1 = r0 // 32 * gpb, min(G, (r0 + tile_m) // 32 * gpb)
+        h0, h1 = c0 // 32 * gpb, min(G, (c0 + 256) // 32 * gpb)
+        want = out[g0:g1, h0:h1].cpu().numpy()
+        got = sm.matrix[g0:g1, h0:h1]
+        upper = np.arange(g0, g1)[:, None] < np.arange(h0, h1)[None, :]
+        identical &= bool(np.array_equal(want[upper].view(np.uint32), np.asarray(got)[upper].view(np.uint32)))
+        mirror = sm.matrix[h0:h1, g0:g1].T
+        identical &= bool(np.array_equal(want[upper].view(np.uint32), np.asarray(mirror)[upper].view(np.uint32)))
+        entries += int(upper.sum())
+    return {"tiles": int(len(tiles_h)), "entries": entries, "identical": bool(identical),
+            "note": "tiles owned by ranks 1..N-1, recomputed single-rank on rank 0, compared bitwise (both "
+                    "triangles) with the assembled host matrix"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -313,9 +408,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--unsigned", action="store_true", help="plain MI (no Pearson sign pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-int8-pass", action="store_true", help="skip the short INT8-operand pass (roofline_int8)")
     ap.add_argument("--cta-group", type=int, default=2)
     ap.add_argument("--operand", default="fp4", choices=["int8", "fp4"],
                     help="storage of the one-hot operand (fp4: tcgen05 kind::mxf4, exact counts)")
+    ap.add_argument("--front", default="auto", choices=["auto", "broadcast", "sharded"],
+                    help="N > 1: how the discretised matrix reaches every rank (DESIGN.md section 5)")
     ap.add_argument("--target", default="mi", choices=["mi", "pearson", "spearman", "cosine", "jaccard"],
                     help="mi (default, the headline) or one of the matrix targets of BASELINE configs[4]")
     args = ap.parse_args()
@@ -327,92 +425,55 @@ def main():
     guard = StdoutGuard()
     import torch
     import torch.distributed as dist
-    from genevector_b200.engine import Engine, CsrDevice
-    from genevector_b200.synth import synth_counts_torch
+    from genevector_b200 import metrics as gm
+    from genevector_b200.engine import get_engine
+    from genevector_b200.synth import gene_names
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local, dev = setup_dist()
     signed = not args.unsigned
     wl, G, N = parse_workload(args.workload)
     pairs = G * (G - 1) // 2
-    eng = Engine(dev, cta_group=args.cta_group)
+    eng = get_engine(dev)
+    eng.cta_group = args.cta_group
     eng.operand = args.operand
 
-    # ---- synthetic input: generated on rank 0's device, staged to pinned host for the e2e leg
-    csr = None
-    host = None
-    if rank == 0:
-        vals, cols, ptr = synth_counts_torch(N, G, seed=0, device=dev)
-        csr = CsrDevice(vals, cols, ptr, N, G)
-        host = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (vals, cols, ptr))
-        torch.cuda.synchronize()
-    nnz = int(csr.nnz) if csr is not None else 0
-
-    # rows of the result this rank owns (gene range spanned by its tile slice) for the D2H leg
+    # ---- synthetic input: a scipy CSR in pageable host memory on every rank (what the reference's
+    # callers hold); the device-timed leg keeps a resident copy
+    X, csr = synthetic_input(N, G, dev, keep_device=True)
+    nnz = int(X.nnz)
+    genes = gene_names(G)
     B = eng.lib.gv_rows_per_gene(N_BINS)
     op_rows = eng.lib.gv_onehot_rows(G, B)
-    tiles, n_my_tiles, n_all_tiles = eng.schedule(op_rows, rank=rank, world=world)
-    th = tiles.cpu().numpy()
-    gpb = 32 // B
-    g_lo = int(th[:, 0].min()) // 32 * gpb if n_my_tiles else 0
-    g_hi = min(G, (int(th[:, 0].max()) + eng.lib.gv_tile_m(args.cta_group)) // 32 * gpb) if n_my_tiles else 0
+    _, n_my_tiles, n_all_tiles = eng.schedule(op_rows, rank=rank, world=world)
     out = torch.zeros((G, G), dtype=torch.float32, device=dev)
-    res_host = torch.empty((max(g_hi - g_lo, 1), G), dtype=torch.float32, pin_memory=True)
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
     operand_bytes = op_rows * ((N + 255) // 256 * 256) // (2 if args.operand == "fp4" else 1)
     flush_needed = operand_bytes <= 2 * L2_BYTES
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    eng.kernel_events = []
+    barrier, timed = make_timed(world, dev)
+    front = eng.resolve_front(args.front, world)
 
     def step_device():
         if flush_needed:
             flush.fill_(1)
-        eng.mi_from_csr(csr, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out)
+        eng.mi_device_step(csr, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out, front=front)
 
-    h2d_events = []
+    last = [None]
 
     def step_e2e():
         if flush_needed:
             flush.fill_(1)
-        c = None
-        if rank == 0:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            c = CsrDevice(host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
-                          host[2].to(dev, non_blocking=True), N, G)
-            e1.record()
-            h2d_events.append((e0, e1))
-        if world == 1:
-            # single rank: the result rows stream to the pinned host matrix under the computation
-            eng.mi_from_csr(c, N, G, n_bins=N_BINS, signed=signed, out=out, out_host=res_host)
-        else:
-            eng.mi_from_csr(c, N, G, n_bins=N_BINS, signed=signed, rank=rank, world=world, out=out)
-            if g_hi > g_lo:
-                res_host[:g_hi - g_lo].copy_(out[g_lo:g_hi], non_blocking=True)
+        # the reference-facing plugin call: data.py:319-326 -> TARGETS["mi"](X, gene_names, signed=, backend=, device=)
+        last[0] = gm.target_mi(X, genes, signed=signed, backend="b200", device=dev, n_bins=N_BINS, front=front)
 
-    def timed(fn, steps):
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(steps):
-            fn()
-        ev1.record()
+    def device_leg(steps, warmup):
+        for _ in range(warmup):
+            step_device()
         torch.cuda.synchronize()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        barrier()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        eng.kernel_events = []
+        ms, _ = timed(step_device, steps)
+        kev = eng.kernel_events
+        eng.kernel_events = None
+        return ms, kev
 
     for _ in range(args.warmup):
         step_device()
@@ -421,50 +482,86 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, args.steps)
+    ms_dev, _ = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     kev = eng.kernel_events
     eng.kernel_events = None
     mi_ms = [a.elapsed_time(b) for (name, a, b, _) in kev if name == "gv_mi_tiles"]
+    n_mi_launches = max(1, len(mi_ms) // max(args.steps, 1))
     phase_ms = {}
     for name, a, b, _ in kev:
         phase_ms.setdefault(name, []).append(a.elapsed_time(b))
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    # ---- end to end through the public call (first calls allocate the page-locked buffers)
+    for _ in range(max(3, args.warmup)):
         step_e2e()
-    h2d_events.clear()
-    ms_e2e = timed(step_e2e, args.steps)
-    h2d_ms = float(np.mean([a.elapsed_time(b) for a, b in h2d_events])) if h2d_events else 0.0
+    eng.host_timings = {}
+    ms_e2e_ev, ms_e2e_wall = timed(step_e2e, args.steps)
+    ms_e2e = max(ms_e2e_ev, ms_e2e_wall)
+    host_ms = {k: float(np.mean(v)) for k, v in (eng.host_timings or {}).items()}
+    eng.host_timings = None
+    sm = last[0]
 
-    # correctness guard inside the bench: the result is symmetric, finite, bounded by log2(11)
-    if rank == 0 and world == 1:
-        sub = out[:512, :512]
-        assert torch.isfinite(sub).all() and float(sub.abs().max()) <= 3.46 + 1e-3
-        assert torch.equal(sub, sub.T)
+    # correctness guards inside the bench: symmetric, finite, bounded by log2(11); with several ranks a
+    # sample of tiles of the other ranks is recomputed on rank 0 and compared bitwise
+    parity = None
+    if rank == 0:
+        sub = np.asarray(sm.matrix[:512, :512])
+        assert np.isfinite(sub).all() and float(np.abs(sub).max()) <= 3.46 + 1e-3
+        assert np.array_equal(sub, sub.T)
+        if world > 1:
+            parity = parity_check(eng, csr, sm, G, N, signed, rank, world)
+    if world > 1:
+        dist.barrier()
 
     # ---- roofline of the dominant kernel (contraction + fused MI epilogue), this rank's share
     peaks = load_peaks()
+
+    def roofline(operand, mi_list, step_ms):
+        fp4 = operand == "fp4"
+        my_frac = n_my_tiles / max(n_all_tiles, 1)
+        alg_ops = pairs * my_frac * 2.0 * N_BINS * N_BINS * N        # 2*B^2*N per pair
+        per_step = float(np.sum(mi_list)) / max(args.steps if mi_list is mi_ms else 1, 1) if mi_list else float("nan")
+        achieved = alg_ops / (per_step * 1e-3) / 1e12 if mi_list else None
+        long_step = step_ms > 500.0
+        rate = 4.0 if fp4 else 2.0
+        nominal = 9000.0 if fp4 else 4500.0
+        bf16_scaled = rate * (peaks["bf16_sustained"] if long_step else peaks["bf16_burst"])
+        peak = eng.mma_peak(operand)
+        opb = op_rows * ((N + 255) // 256 * 256) // (2 if fp4 else 1)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            ent = json.load(open(tpath)).get(f"{wl}:{world}:{operand}")
+            if ent and signed and args.cta_group == 2:
+                traffic = ent["traffic_bytes"]
+        return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "algorithmic_operand_bytes": int(opb),
+                "kernel": f"gram_tiles_kernel<{args.cta_group}, MiEpi<10{', fp4' if fp4 else ''}>> (gv_mi_tiles)",
+                "kernel_ms": per_step, "launches_per_step": n_mi_launches if mi_list is mi_ms else None,
+                "peak_note": f"peak = tcgen05 {'kind::mxf4' if fp4 else 'kind::i8'} M256 N240 issued back to back from "
+                             "resident shared memory, measured live in this run (gv_mma_peak); "
+                             f"{rate:.0f} x {peaks['src']} cuBLAS bf16 ({'sustained' if long_step else 'burst'}) "
+                             f"would be {bf16_scaled:.0f} TOP/s, nominal dense {'FP4 9000' if fp4 else 'INT8 4500'} TOP/s; "
+                             "achieved counts algorithmic work only (issued work is 128/120 of it)",
+                "peak_bf16_scaled": bf16_scaled,
+                "frac_of_nominal": (achieved / nominal) if achieved else None,
+                "frac_of_nominal_int8": (achieved / 4500.0) if achieved else None}
+
+    roof = roofline(args.operand, mi_ms, ms_dev / args.steps)
+    roof_int8 = None
+    if args.operand != "int8" and not args.no_int8_pass:
+        # the metric's own dtype ("% INT8 TC peak"): a short pass with the INT8 one-hot operand
+        eng.operand = "int8"
+        ms8, kev8 = device_leg(1, 1)
+        mi8 = [a.elapsed_time(b) for (name, a, b, _) in kev8 if name == "gv_mi_tiles"]
+        roof_int8 = roofline("int8", mi8, ms8)
+        roof_int8["ms_per_step"] = ms8
+        roof_int8["value"] = pairs / (ms8 * 1e-3)
+        eng.operand = args.operand
+
     fp4 = args.operand == "fp4"
-    my_pairs_frac = n_my_tiles / max(n_all_tiles, 1)
-    alg_ops = pairs * my_pairs_frac * 2.0 * N_BINS * N_BINS * N        # 2*B^2*N per pair
-    mi_avg_ms = float(np.mean(mi_ms)) if mi_ms else float("nan")
-    achieved_tops = alg_ops / (mi_avg_ms * 1e-3) / 1e12 if mi_ms else None
-    long_step = (ms_dev / args.steps) > 500.0
-    # roofline denominator: the rate of the kernel's own tcgen05.mma (same shape, operands resident in
-    # shared memory, no loads), measured live on this GPU; MEASURED_PEAKS.json holds bf16 only, whose
-    # kind::i8 / kind::mxf4 equivalents (2x / 4x the issue rate) are reported beside it
-    rate = 4.0 if fp4 else 2.0
-    nominal = 9000.0 if fp4 else 4500.0
-    bf16_scaled = rate * (peaks["bf16_sustained"] if long_step else peaks["bf16_burst"])
-    peak_tops = eng.mma_peak(args.operand)
-
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        ent = json.load(open(tpath)).get(f"{wl}:{world}:{args.operand}")
-        if ent and signed and args.cta_group == 2:
-            traffic = ent["traffic_bytes"]
-
     line = {
         "metric": "gene-pairs/s", "value": pairs / (ms_dev / args.steps * 1e-3), "unit": "gene-pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -472,42 +569,36 @@ def main():
         # arithmetic type of the contraction: one-hot operands in E2M1 (fp4) or INT8, exact integer counts
         "dtype": "fp4" if fp4 else "int8",
         "data": "synthetic",
-        "config": {"workload": f"{wl}: all-pairs {'signed ' if signed else ''}MI, {G} genes x {N} cells, "
-                               f"n_bins={N_BINS}, nnz={nnz}",
+        "config": {"workload": workload_name(wl, G, N, signed), "nnz": nnz,
                    "pairs": pairs, "cta_group": args.cta_group, "operand": args.operand,
-                   "parallelism": f"tile-sharded x{world}, 1 broadcast" if world > 1 else "single GPU",
+                   "parallelism": (f"tile-sharded x{world}, front={front}" if world > 1 else "single GPU"),
                    "l2": "operand larger than L2" if not flush_needed else "L2 flushed between steps"},
         "e2e": {"value": pairs / (ms_e2e / args.steps * 1e-3), "unit": "gene-pairs/s",
                 "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) if host else 0,
-                "d2h_bytes_per_step": int(max(g_hi - g_lo, 0) * G * 4),
-                "h2d_ms": h2d_ms,
-                "d2h_exposed_ms": max(0.0, (ms_e2e - ms_dev) / args.steps - h2d_ms),
-                "note": "pinned host CSR -> device on rank 0; result rows -> pinned host "
-                        + ("streamed under the computation" if world == 1 else "after the computation")},
+                "ms_per_step_events": ms_e2e_ev / args.steps, "ms_per_step_wall": ms_e2e_wall / args.steps,
+                "h2d_bytes_per_step": csr_bytes(X),
+                "d2h_bytes_per_step": int(G) * int(G) * 4,
+                "host_phases_ms": host_ms,
+                "note": "genevector_b200.metrics.target_mi(scipy CSR in pageable host memory, gene names, signed=True, "
+                        "backend='b200') -> full ScoreMatrix on rank 0; all ranks' host->device and device->host "
+                        "copies are inside the timed region (bytes are totals over the ranks)"},
         "gpu_launches": int(sum(k for (_, _, _, k) in kev)),
-        "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s",
-                     "frac": (achieved_tops / peak_tops) if achieved_tops else None, "traffic": traffic,
-                     "algorithmic_operand_bytes": int(operand_bytes),
-                     "kernel": f"gram_tiles_kernel<{args.cta_group}, MiEpi<10{', fp4' if args.operand == 'fp4' else ''}>> (gv_mi_tiles)",
-                     "kernel_ms": mi_avg_ms,
-                     "peak_note": f"peak = tcgen05 {'kind::mxf4' if fp4 else 'kind::i8'} M256 N240 issued back to back from "
-                                  "resident shared memory, measured live in this run (gv_mma_peak); "
-                                  f"{rate:.0f} x {peaks['src']} cuBLAS bf16 ({'sustained' if long_step else 'burst'}) "
-                                  f"would be {bf16_scaled:.0f} TOP/s, nominal dense {'FP4 9000' if fp4 else 'INT8 4500'} TOP/s; "
-                                  "achieved counts algorithmic work only (issued work is 128/120 of it)",
-                     "peak_bf16_scaled": bf16_scaled,
-                     "frac_of_nominal": (achieved_tops / nominal) if achieved_tops else None,
-                     "frac_of_nominal_int8": (achieved_tops / 4500.0) if achieved_tops else None},
-        "phases_ms": {k: float(np.mean(v)) for k, v in phase_ms.items()},
+        "roofline": roof,
+        "phases_ms": {k: float(np.sum(v)) / args.steps for k, v in phase_ms.items()},
         "clocks": clocks,
     }
+    if roof_int8 is not None:
+        line["roofline_int8"] = roof_int8
+    if parity is not None:
+        line["parity_check"] = parity
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(N, G, steps=1, warmup=0, target_s=10.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_ms")}
     if rank == 0:
         guard.emit(json.dumps(line))
+    last[0] = sm = None
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

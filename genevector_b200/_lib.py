@@ -23,8 +23,9 @@ GV_EDGE_STRIDE = 16
 GV_EDGE_SCALE_SLOT = 15
 GV_EDGE_OFFSET_SLOT = 14
 GV_QTABLE_DIM = 16
-GV_ABI_VERSION = 4
+GV_ABI_VERSION = 5
 GV_OPERAND_INT8, GV_OPERAND_FP4 = 0, 1
+GV_ERR_TIMEOUT = -5
 
 
 class GvError(RuntimeError):
@@ -46,6 +47,7 @@ SIGNATURES = {
     "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _i32, _vp, _vp]),
+    "gv_csr_check": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "gv_gene_entropy": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "gv_rows_per_gene": (_i32, [_i32]),
     "gv_onehot_rows": (_i64, [_i32, _i32]),
@@ -64,8 +66,20 @@ SIGNATURES = {
     "gv_symmetrize": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "gv_mma_peak": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp]),
     "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
-                               _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
+                               _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "gv_upload_pageable": (_i32, [_vp, _vp, _sz, _i32, _vp]),
+    "gv_runtime_shutdown": (_i32, []),
+    "gv_shm_open": (_i32, [C.c_char_p, _sz, _i32, _i32, C.POINTER(_vp)]),
+    "gv_shm_close": (_i32, [_vp, _sz, _i32, C.c_char_p]),
+    "gv_flag_store": (_i32, [_vp, C.c_uint64]),
+    "gv_flag_load": (C.c_uint64, [_vp]),
+    "gv_flag_wait_ge": (_i32, [_vp, C.c_uint64, _i32]),
+    "gv_copy_rect_d2h": (_i32, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "gv_ipc_alloc": (_i32, [_sz, C.POINTER(_vp), _vp]),
+    "gv_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "gv_ipc_close": (_i32, [_vp]),
+    "gv_ipc_free": (_i32, [_vp]),
 }
 
 _lib = None

@@ -66,7 +66,11 @@ def save_scores(cache_key, mi_scores, gene_names):
                 if j is not None:
                     matrix[i, j] = val
     path = get_cache_path(cache_key)
-    np.savez_compressed(path, scores=matrix, genes=np.array(gene_names))
+    # written under a private name and moved into place: a concurrent reader (another rank, another
+    # process) never sees a partial file
+    tmp = f"{path[:-4]}.tmp{os.getpid()}.npz"
+    np.savez_compressed(tmp, scores=matrix, genes=np.array(gene_names))
+    os.replace(tmp, path)
     return path
 
 

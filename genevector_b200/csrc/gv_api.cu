@@ -52,7 +52,7 @@ int gram_dump_dispatch(const void*, int64_t, int64_t, const int32_t*, int64_t, i
                        int, int, cudaStream_t);
 int moment_tiles_dispatch(int, const void*, int64_t, int64_t, const int64_t*, const int64_t*,
                           const int32_t*, const double*, int64_t, int, int, int, const int32_t*, int64_t, int8_t*,
-                          int64_t, float*, int64_t, int, void*, cudaStream_t);
+                          int64_t, float*, int64_t, int, void*, int, cudaStream_t);
 
 int mma_peak_dispatch(int, int, int, int, double*, cudaStream_t);
 int xcorr_tiles_dispatch(const void*, int64_t, int, const void*, int64_t, int, int64_t, int, const int64_t*,
@@ -115,6 +115,17 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
     return set_error(GV_ERR_ARG, "unknown discretisation path");
   a.path = path; a.path_used = path_used_host;
   return discretize_dispatch(a, static_cast<cudaStream_t>(stream));
+}
+
+int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int n_genes,
+                 int* scratch_dev, int* result_host, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!row_ptr || !scratch_dev || !result_host || n_cells < 0 || n_genes <= 0)
+    return set_error(GV_ERR_ARG, "gv_csr_check: bad argument");
+  *result_host = 0;
+  return csr_check_dispatch(col_idx, row_ptr, n_cells, n_genes, scratch_dev, result_host,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
@@ -221,9 +232,10 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     int64_t n_cells,
                     int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
                     int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
-                    void* sync_ws, void* stream) {
+                    void* sync_ws, int sign_zero, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
+  if (sign_zero != 0 && sign_zero != 1) return set_error(GV_ERR_ARG, "gv_moment_tiles: sign_zero must be 0 or 1");
   if (!val_rows || !tiles || n_genes <= 0 || n_limbs < 1 || n_limbs > 4 ||
       op_rows < gv_value_rows(n_genes, n_limbs))
     return set_error(GV_ERR_ARG, "gv_moment_tiles: bad argument");
@@ -231,7 +243,7 @@ int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
     return set_error(GV_ERR_ARG, "gv_moment_tiles: leading dimension < n_genes");
   return moment_tiles_dispatch(kind, val_rows, op_rows, kp, gsum, gsq, marg, edges, n_cells, n_genes, n_limbs,
                                limb_bits, tiles, n_tiles, sgn, ld_sgn, out, ld_out, cta_group, sync_ws,
-                               static_cast<cudaStream_t>(stream));
+                               sign_zero, static_cast<cudaStream_t>(stream));
 }
 
 int64_t gv_tile_schedule_rect(int64_t rows_a, int64_t rows_b, int tile_m, int32_t* out_pairs_host,

@@ -1549,6 +1549,41 @@ int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* co
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
+// ---------------------------------------------------------------- canonical-CSR check
+// One warp per row: every column index must lie in [0, G) and exceed its predecessor in the row
+// (sorted, no duplicate entries) -- what scipy calls canonical format and what the discretisation
+// kernels assume.  result: 0 canonical, 1 unsorted or duplicate entries, 2 an index out of range.
+__global__ void k_csr_check(const int32_t* __restrict__ col_idx, const int64_t* __restrict__ row_ptr,
+                            int64_t n_cells, int G, int* __restrict__ result) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  int bad = 0;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < n_cells; r += warps) {
+    const int64_t e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    if (e1 < e0) bad = 2;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+      const int32_t c = col_idx[e];
+      if (c < 0 || c >= G) bad = 2;
+      else if (e > e0 && col_idx[e - 1] >= c && bad < 1) bad = 1;
+    }
+  }
+  bad = __reduce_max_sync(0xffffffffu, bad);
+  if (lane == 0 && bad) atomicMax(result, bad);
+}
+
+int csr_check_dispatch(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int G,
+                       int* scratch_dev, int* result_host, cudaStream_t st) {
+  GV_CUDA_TRY(cudaMemsetAsync(scratch_dev, 0, sizeof(int), st));
+  if (n_cells > 0) {
+    const int sms = device_sm_count();
+    k_csr_check<<<sms * 8, 256, 0, st>>>(col_idx, row_ptr, n_cells, G, scratch_dev);
+    GV_LAUNCH_CHECK();
+  }
+  GV_CUDA_TRY(cudaMemcpyAsync(result_host, scratch_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GV_CUDA_TRY(cudaStreamSynchronize(st));
+  return GV_OK;
+}
+
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
   if (a.n_bins < 1 || a.n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
   if (a.bins_pitch_bytes % 16 != 0 || int64_t(a.bins_pitch_bytes) * 2 < a.n_cells)

@@ -248,6 +248,8 @@ struct MomentParams {
   int G;
   int64_t n_cells;
   int limb_bits;         // digit width of the value rows (two-digit operands)
+  int sign_zero;         // MOM_SIGN: value written where the correlation is 0 or undefined: 0 follows
+                         // np.sign (metrics.py:111,134), +1 the Rust tier (src/lib.rs:91-94)
 };
 
 // 128-bit integers keep n*Sum(xy) - Sum(x)*Sum(y) exact for 21-bit fixed-point values over 2^18 cells.
@@ -357,7 +359,8 @@ struct MomentEpi {
             const int64_t syy = meta->csq[cg];
             const i128 var_j = n * syy - i128(sy) * sy;
             const i128 cov = n * sxy - i128(sx) * sy;
-            s = (var_i == 0 || var_j == 0) ? 0 : (cov > 0 ? 1 : (cov < 0 ? -1 : 0));
+            const int8_t z = int8_t(p.sign_zero);
+            s = (var_i == 0 || var_j == 0) ? z : (cov > 0 ? int8_t(1) : (cov < 0 ? int8_t(-1) : z));
           }
           p.sgn[int64_t(gi) * p.ld_sgn + gj] = s;
           p.sgn[int64_t(gj) * p.ld_sgn + gi] = s;

@@ -161,13 +161,19 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const int n_waves = (ga.n_tiles + n_clusters - 1) / n_clusters;
       for (int t = cluster_id; int(wave) < n_waves; t += n_clusters, ++wave) {
         if (ga.wave_sync != nullptr && leader) {
-          // the peer's loads only fill its own stages; MMA cannot start before the leader's arrive
+          // the peer's loads only fill its own stages; MMA cannot start before the leader's arrive.
+          // wave_sync[0] counts arrivals; wave_sync[1] != 0 means the lockstep was given up: a cluster
+          // that waited a full second for the others (they are not co-resident: something else holds
+          // SMs) sets it and every cluster runs on unsynchronised -- slower, never a hang or a trap
+          volatile unsigned int* ws = reinterpret_cast<volatile unsigned int*>(ga.wave_sync);
           atomicAdd(ga.wave_sync, 1u);
           const unsigned int target = unsigned(n_clusters) * (wave + 1u);
-          const uint64_t t0 = global_timer_ns();
-          while (*reinterpret_cast<volatile unsigned int*>(ga.wave_sync) < target) {
-            __nanosleep(128);
-            if (global_timer_ns() - t0 > 20000000000ull) __trap();
+          if (ws[1] == 0u && ws[0] < target) {
+            const uint64_t t0 = global_timer_ns();
+            while (ws[0] < target && ws[1] == 0u) {
+              __nanosleep(128);
+              if (global_timer_ns() - t0 > 1000000000ull) ws[1] = 1u;
+            }
           }
         }
         if (t >= ga.n_tiles) break;

@@ -1,0 +1,270 @@
+// gv_host.cu -- host-side runtime of libgvb200.so: the pieces around the kernels that move data
+// between the caller's host buffers and the device without a collective.
+//
+//   gv_upload_pageable   pageable host array -> device through a ring of pinned staging buffers that
+//                        worker threads fill in parallel (the reference hands over scipy CSR arrays,
+//                        data.py:171; a plain cudaMemcpy of pageable memory runs at a few GB/s)
+//   gv_shm_*             one POSIX shared-memory segment, page-locked for CUDA in every process of
+//                        the box: the G x G result matrix every rank DMAs its own tiles into
+//                        (north_star: "each rank writes its own result tiles", no reduction)
+//   gv_flag_*            release / acquire flags in such a segment (completion hand-shake, no NCCL)
+//   gv_copy_rect_d2h     one rectangle of the device result matrix -> the host matrix
+//   gv_ipc_*             device allocations mapped into the peer processes of the box (NVLink /
+//                        NVSwitch peer stores of the sharded discretisation front)
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "gv_internal.h"
+
+namespace gv {
+
+#define GV_HOST_TRY(expr)                                                 \
+  do {                                                                    \
+    cudaError_t e_ = (expr);                                              \
+    if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------- staged upload
+constexpr size_t UP_CHUNK = size_t(8) << 20;   // bytes per staging slot
+constexpr int UP_SLOTS_PER_THREAD = 2;
+constexpr int UP_MAX_THREADS = 16;
+
+struct UploadRing {
+  std::mutex mu;                  // one upload at a time per process
+  int device = -1;
+  int n_slots = 0;
+  uint8_t* slot[UP_MAX_THREADS * UP_SLOTS_PER_THREAD] = {};
+  cudaEvent_t ev[UP_MAX_THREADS * UP_SLOTS_PER_THREAD] = {};
+};
+static UploadRing g_ring;
+
+static int ring_release_locked() {
+  for (int i = 0; i < g_ring.n_slots; ++i) {
+    if (g_ring.ev[i]) { cudaEventSynchronize(g_ring.ev[i]); cudaEventDestroy(g_ring.ev[i]); g_ring.ev[i] = nullptr; }
+    if (g_ring.slot[i]) { cudaFreeHost(g_ring.slot[i]); g_ring.slot[i] = nullptr; }
+  }
+  g_ring.n_slots = 0;
+  g_ring.device = -1;
+  return GV_OK;
+}
+
+static int ring_prepare_locked(int device, int n_slots) {
+  if (g_ring.device == device && g_ring.n_slots >= n_slots) return GV_OK;
+  if (g_ring.device != device) ring_release_locked();
+  g_ring.device = device;
+  for (int i = g_ring.n_slots; i < n_slots; ++i) {
+    GV_HOST_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ring.slot[i]), UP_CHUNK, cudaHostAllocPortable));
+    GV_HOST_TRY(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));
+    g_ring.n_slots = i + 1;
+  }
+  return GV_OK;
+}
+
+}  // namespace gv
+
+using namespace gv;
+
+extern "C" {
+
+int gv_upload_pageable(void* dst_dev, const void* src_host, size_t bytes, int n_threads, void* stream) {
+  if (bytes == 0) return GV_OK;
+  if (!dst_dev || !src_host) return set_error(GV_ERR_ARG, "gv_upload_pageable: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int device = 0;
+  GV_HOST_TRY(cudaGetDevice(&device));
+  if (bytes < 2 * UP_CHUNK) {
+    // small arrays: the runtime's own staging is as good
+    GV_HOST_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    return GV_OK;
+  }
+  if (n_threads <= 0) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    n_threads = hw >= 16 ? 8 : (hw >= 8 ? 4 : 2);
+  }
+  if (n_threads > UP_MAX_THREADS) n_threads = UP_MAX_THREADS;
+  const size_t n_chunks = (bytes + UP_CHUNK - 1) / UP_CHUNK;
+  if (size_t(n_threads) > n_chunks) n_threads = int(n_chunks);
+  std::lock_guard<std::mutex> lock(g_ring.mu);
+  int rc = ring_prepare_locked(device, n_threads * UP_SLOTS_PER_THREAD);
+  if (rc != GV_OK) return rc;
+  std::atomic<int> err{0};
+  std::atomic<size_t> next{0};
+  auto worker = [&](int w) {
+    if (cudaSetDevice(device) != cudaSuccess) { err.store(1); return; }
+    int use = 0;
+    for (;;) {
+      const size_t c = next.fetch_add(1);
+      if (c >= n_chunks || err.load()) break;
+      const size_t off = c * UP_CHUNK;
+      const size_t n = bytes - off < UP_CHUNK ? bytes - off : UP_CHUNK;
+      const int s = w * UP_SLOTS_PER_THREAD + (use++ % UP_SLOTS_PER_THREAD);
+      // the DMA that last read this slot (this call or an earlier one) must be done
+      if (cudaEventSynchronize(g_ring.ev[s]) != cudaSuccess) { err.store(2); break; }
+      memcpy(g_ring.slot[s], static_cast<const uint8_t*>(src_host) + off, n);
+      if (cudaMemcpyAsync(static_cast<uint8_t*>(dst_dev) + off, g_ring.slot[s], n, cudaMemcpyHostToDevice, st) !=
+              cudaSuccess ||
+          cudaEventRecord(g_ring.ev[s], st) != cudaSuccess) {
+        err.store(3);
+        break;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  pool.reserve(n_threads - 1);
+  for (int w = 1; w < n_threads; ++w) pool.emplace_back(worker, w);
+  worker(0);
+  for (auto& t : pool) t.join();
+  if (err.load()) {
+    cudaError_t e = cudaGetLastError();
+    return e != cudaSuccess ? set_cuda_error(e, __FILE__, __LINE__)
+                            : set_error(GV_ERR_CUDA, "gv_upload_pageable: a staging copy failed");
+  }
+  return GV_OK;
+}
+
+int gv_runtime_shutdown(void) {
+  std::lock_guard<std::mutex> lock(g_ring.mu);
+  return ring_release_locked();
+}
+
+// ---------------------------------------------------------------- shared host segments
+int gv_shm_open(const char* name, size_t bytes, int create, int cuda_register, void** ptr_out_host) {
+  if (!name || name[0] != '/' || bytes == 0 || !ptr_out_host)
+    return set_error(GV_ERR_ARG, "gv_shm_open: name must start with '/', bytes > 0");
+  int fd = -1;
+  if (create) {
+    shm_unlink(name);                                   // a stale segment of a crashed run
+    fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  } else {
+    fd = shm_open(name, O_RDWR, 0600);
+  }
+  if (fd < 0) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "gv_shm_open: shm_open(%s) failed: %s", name, strerror(errno));
+    return set_error(GV_ERR_ARG, buf);
+  }
+  if (create && ftruncate(fd, off_t(bytes)) != 0) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "gv_shm_open: ftruncate(%s, %zu) failed: %s", name, bytes, strerror(errno));
+    close(fd);
+    shm_unlink(name);
+    return set_error(GV_ERR_ARG, buf);
+  }
+  if (!create) {
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || size_t(sb.st_size) < bytes) {
+      close(fd);
+      return set_error(GV_ERR_ARG, "gv_shm_open: segment is smaller than requested");
+    }
+  }
+  void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    if (create) shm_unlink(name);
+    return set_error(GV_ERR_ARG, "gv_shm_open: mmap failed");
+  }
+  if (cuda_register) {
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+      munmap(p, bytes);
+      if (create) shm_unlink(name);
+      return set_cuda_error(e, __FILE__, __LINE__);
+    }
+  }
+  *ptr_out_host = p;
+  return GV_OK;
+}
+
+int gv_shm_close(void* ptr, size_t bytes, int cuda_registered, const char* unlink_name) {
+  int rc = GV_OK;
+  if (ptr) {
+    if (cuda_registered) {
+      cudaError_t e = cudaHostUnregister(ptr);
+      if (e != cudaSuccess) rc = set_cuda_error(e, __FILE__, __LINE__);
+    }
+    munmap(ptr, bytes);
+  }
+  if (unlink_name && unlink_name[0] == '/') shm_unlink(unlink_name);
+  return rc;
+}
+
+int gv_flag_store(uint64_t* flag, uint64_t value) {
+  if (!flag) return set_error(GV_ERR_ARG, "gv_flag_store: null");
+  __atomic_store_n(flag, value, __ATOMIC_RELEASE);
+  return GV_OK;
+}
+
+uint64_t gv_flag_load(const uint64_t* flag) { return flag ? __atomic_load_n(flag, __ATOMIC_ACQUIRE) : 0; }
+
+int gv_flag_wait_ge(const uint64_t* flag, uint64_t value, int timeout_ms) {
+  if (!flag) return set_error(GV_ERR_ARG, "gv_flag_wait_ge: null");
+  const auto t0 = std::chrono::steady_clock::now();
+  int spins = 0;
+  while (__atomic_load_n(flag, __ATOMIC_ACQUIRE) < value) {
+    if (++spins < 2000) {
+      __builtin_ia32_pause();
+    } else {
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+      const auto dt = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0);
+      if (timeout_ms >= 0 && dt.count() > timeout_ms)
+        return set_error(GV_ERR_TIMEOUT, "gv_flag_wait_ge: timed out waiting for another rank");
+    }
+  }
+  return GV_OK;
+}
+
+// ---------------------------------------------------------------- result rectangles
+int gv_copy_rect_d2h(void* dst_host, size_t dst_pitch_bytes, const void* src_dev, size_t src_pitch_bytes,
+                     size_t width_bytes, size_t rows, void* stream) {
+  if (width_bytes == 0 || rows == 0) return GV_OK;
+  if (!dst_host || !src_dev || dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes)
+    return set_error(GV_ERR_ARG, "gv_copy_rect_d2h: bad argument");
+  GV_HOST_TRY(cudaMemcpy2DAsync(dst_host, dst_pitch_bytes, src_dev, src_pitch_bytes, width_bytes, rows,
+                                cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return GV_OK;
+}
+
+// ---------------------------------------------------------------- peer-mapped device buffers
+int gv_ipc_alloc(size_t bytes, void** dev_ptr_out, void* handle_out_64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+  if (bytes == 0 || !dev_ptr_out || !handle_out_64) return set_error(GV_ERR_ARG, "gv_ipc_alloc: bad argument");
+  void* p = nullptr;
+  GV_HOST_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return set_cuda_error(e, __FILE__, __LINE__); }
+  memcpy(handle_out_64, &h, 64);
+  *dev_ptr_out = p;
+  return GV_OK;
+}
+
+int gv_ipc_open(const void* handle_64, void** dev_ptr_out) {
+  if (!handle_64 || !dev_ptr_out) return set_error(GV_ERR_ARG, "gv_ipc_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, 64);
+  GV_HOST_TRY(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return GV_OK;
+}
+
+int gv_ipc_close(void* dev_ptr) {
+  if (dev_ptr) GV_HOST_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return GV_OK;
+}
+
+int gv_ipc_free(void* dev_ptr) {
+  if (dev_ptr) GV_HOST_TRY(cudaFree(dev_ptr));
+  return GV_OK;
+}
+
+}  // extern "C"

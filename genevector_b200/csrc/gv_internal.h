@@ -34,6 +34,8 @@ size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value
 int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx,
                           const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int G, double* ent,
                           void* workspace, size_t ws_bytes, cudaStream_t st);
+int csr_check_dispatch(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int G,
+                       int* scratch_dev, int* result_host, cudaStream_t st);
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
                            void* onehot, int64_t kp, int n_blocks, int operand_format,
                            cudaStream_t st);

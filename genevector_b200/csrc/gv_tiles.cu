@@ -104,15 +104,35 @@ static int launch_gram(const void* operand, int64_t op_rows, int64_t kp, const i
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // The wave barrier spins on all clusters of the grid, so every CTA must be resident at once: the
-  // grid is one CTA per SM and nothing else runs on the stream's device meanwhile.  GV_COOPERATIVE=1
-  // additionally asks for a cooperative launch (a launch error instead of a spin if something else
-  // holds SMs); it is off by default because Nsight Compute cannot replay cooperative cluster launches.
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  static const bool coop = getenv("GV_COOPERATIVE") != nullptr && getenv("GV_COOPERATIVE")[0] == '1';
-  cfg.numAttrs = (sync_ws != nullptr && coop) ? 2 : 1;
+  cfg.numAttrs = 1;
+  // The persistent grid is one CTA per SM; never more clusters than the device can hold at once
+  // (GPC floorsweeping, a smaller part): the wave barrier counts on every cluster being resident.
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0 &&
+      clusters > max_clusters) {
+    clusters = max_clusters;
+    cfg.gridDim = dim3(unsigned(clusters * CG));
+  } else {
+    cudaGetLastError();
+  }
+  if (sync_ws != nullptr) {
+    // Wave lockstep: a cooperative launch, so that SMs held by anything else (another stream, an MPS
+    // client, NCCL) give a launch error here instead of clusters spinning on a barrier that cannot
+    // complete; the launch then falls back to the plain one, whose barrier gives itself up after a
+    // second (gv_gram.cuh).  GV_COOPERATIVE=0 skips the attempt (Nsight Compute cannot replay
+    // cooperative cluster launches).
+    static const bool coop = !(getenv("GV_COOPERATIVE") != nullptr && getenv("GV_COOPERATIVE")[0] == '0');
+    if (coop) {
+      cfg.numAttrs = 2;
+      e = cudaLaunchKernelEx(&cfg, kern, map, map_b, ga, ep);
+      if (e == cudaSuccess) return GV_OK;
+      cudaGetLastError();                    // not launched: clear and retry as a plain launch
+      cfg.numAttrs = 1;
+    }
+  }
   e = cudaLaunchKernelEx(&cfg, kern, map, map_b, ga, ep);
   if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
   return GV_OK;
@@ -190,8 +210,10 @@ int moment_tiles_dispatch(int kind, const void* val_rows, int64_t op_rows, int64
                           const int64_t* gsum, const int64_t* gsq, const int32_t* marg,
                           const double* edges, int64_t n_cells, int n_genes, int n_limbs, int limb_bits,
                           const int32_t* tiles, int64_t n_tiles, int8_t* sgn, int64_t ld_sgn,
-                          float* out, int64_t ld_out, int cta_group, void* sync_ws, cudaStream_t st) {
+                          float* out, int64_t ld_out, int cta_group, void* sync_ws, int sign_zero,
+                          cudaStream_t st) {
   MomentParams p;
+  p.sign_zero = sign_zero;
   p.gsum = gsum; p.gsq = gsq; p.marg = marg; p.edges = edges; p.sgn = sgn; p.ld_sgn = ld_sgn; p.out = out;
   p.ld_out = ld_out; p.G = n_genes; p.n_cells = n_cells; p.limb_bits = limb_bits;
   if (kind == GV_MOM_SIGN && (!sgn || !gsum || !gsq)) return set_error(GV_ERR_ARG, "sign needs sgn, gsum, gsq");

@@ -45,8 +45,12 @@ def compute_target_scores(X, gene_names, target="mi", target_kwargs=None, signed
     else:
         raise TypeError(f"target must be str or callable, got {type(target)}")
     if use_cache:
+        # one process per GPU: every rank holds the same full matrix (metrics._run_to_host); rank 0
+        # alone writes the cache file
         from .cache import save_scores
-        save_scores(cache_key, scores, gene_names)
+        from .metrics import _dist_info
+        if _dist_info()[0] == 0:
+            save_scores(cache_key, scores, gene_names)
     return scores
 
 

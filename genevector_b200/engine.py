@@ -153,17 +153,119 @@ def _views(buf, n_cells, n_genes, n_bins, val_mode, n_limbs, limb_bits, flags=(0
         val_mode=val_mode, n_limbs=n_limbs, limb_bits=limb_bits, data_flags=flags)
 
 
+_host_schedules = {}
+
+
+def schedule_host(op_rows: int, cta_group: int, band: int):
+    """The whole band-ordered upper-triangular tile schedule (host, int32 [n,2]) and tile_m."""
+    key = (op_rows, cta_group, band)
+    if key not in _host_schedules:
+        lib = _lib.load()
+        tile_m = _lib.call("gv_tile_m", cta_group)
+        n = _lib.check("gv_tile_schedule", lib.gv_tile_schedule(op_rows, tile_m, band, None, 0))
+        host = np.zeros((max(n, 1), 2), dtype=np.int32)
+        _lib.check("gv_tile_schedule", lib.gv_tile_schedule(op_rows, tile_m, band, host.ctypes.data, n))
+        _host_schedules[key] = (host[:n], tile_m)
+    return _host_schedules[key]
+
+
+def _cut_points(th: np.ndarray, tile_m: int, band: int):
+    """Tile indices at which the schedule may be cut between ranks (or between host-copy pieces):
+    the first tile of a band, or the first tile of a tile column that lies entirely to the right of
+    the band's own rows.  The tiles of a band's diagonal block (columns overlapping the band's rows)
+    so stay with one owner, and what an owner writes is a set of full rectangles of the result
+    matrix: (band rows) x (its columns) and the mirror image."""
+    n = len(th)
+    if n == 0:
+        return np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    row0, col0 = th[:, 0].astype(np.int64), th[:, 1].astype(np.int64)
+    band_id = row0 // (tile_m * band)
+    band_end = (band_id + 1) * tile_m * band
+    first_of_band = np.diff(band_id, prepend=-1) != 0
+    first_of_col = first_of_band | (np.diff(col0, prepend=-1) != 0)
+    ok = first_of_band | (first_of_col & (col0 >= band_end))
+    return np.append(np.flatnonzero(ok), n), band_id
+
+
+def rank_bounds(th: np.ndarray, tile_m: int, band: int, world: int):
+    """world + 1 tile indices: rank r owns tiles [b[r], b[r+1]).  Equal shares snapped to the nearest
+    allowed cut (a tile column is at most `band` tiles, so the shares differ by a few tiles)."""
+    n = len(th)
+    cuts, _ = _cut_points(th, tile_m, band)
+    b = [0]
+    for r in range(1, world):
+        want = n * r // world
+        c = int(cuts[np.abs(cuts - want).argmin()])
+        b.append(max(c, b[-1]))
+    b.append(n)
+    return b
+
+
 def tile_slice(op_rows: int, cta_group: int, band: int, rank: int = 0, world: int = 1):
     """This rank's contiguous slice of the band-ordered upper-triangular tile schedule
     (host, int32 [n,2]) and the total tile count.  Tiles cost the same (same K), so equal counts
     are equal work; the slices are disjoint and cover the schedule."""
-    lib = _lib.load()
-    tile_m = _lib.call("gv_tile_m", cta_group)
-    n = _lib.check("gv_tile_schedule", lib.gv_tile_schedule(op_rows, tile_m, band, None, 0))
-    host = np.zeros((max(n, 1), 2), dtype=np.int32)
-    _lib.check("gv_tile_schedule", lib.gv_tile_schedule(op_rows, tile_m, band, host.ctypes.data, n))
-    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-    return np.ascontiguousarray(host[lo:hi]), n
+    th, tile_m = schedule_host(op_rows, cta_group, band)
+    b = rank_bounds(th, tile_m, band, world)
+    return np.ascontiguousarray(th[b[rank]:b[rank + 1]]), len(th)
+
+
+def host_pieces(op_rows: int, cta_group: int, band: int, genes_per_block: int, n_genes: int,
+                rank: int = 0, world: int = 1, chunks: int = 6):
+    """How a rank's slice of the schedule is launched so that its results can stream to the host
+    under the computation: a list of (t0, t1, rects) with t0 / t1 tile offsets inside the slice and
+    rects = [(row0, row1, col0, col1), ...] the gene rectangles of the result matrix that are final
+    once tiles [0, t1) of the slice have run and that no other piece (or rank) writes.
+
+    world == 1: pieces end at band boundaries and a tile of band b only writes rows of bands >= b, so
+    the rows of the finished bands are final: one contiguous block of full rows per piece.
+    world > 1: a piece is a run of whole tile columns of bands (see _cut_points); per band it owns
+    the rectangle (band rows) x (its columns) and the mirror image below the band."""
+    th, tile_m = schedule_host(op_rows, cta_group, band)
+    b = rank_bounds(th, tile_m, band, world)
+    lo, hi = b[rank], b[rank + 1]
+    n = hi - lo
+    if n == 0:
+        return []
+    cuts, band_id = _cut_points(th, tile_m, band)
+    gpb = genes_per_block
+
+    def genes(rows):
+        return min(n_genes, int(rows) // 32 * gpb)
+
+    if world == 1:
+        starts = np.flatnonzero(np.diff(band_id, prepend=-1))
+        inner = sorted({int(starts[np.abs(starts - n * k // chunks).argmin()]) for k in range(1, chunks)} - {0})
+        ends = inner + [n]
+        out, t0, g0 = [], 0, 0
+        for t1 in ends:
+            g1 = n_genes if t1 == n else genes(th[t1, 0])
+            out.append((t0, t1, [(g0, g1, 0, n_genes)] if g1 > g0 else []))
+            t0, g0 = t1, g1
+        return out
+    inside = cuts[(cuts > lo) & (cuts < hi)]
+    inner = sorted({int(inside[np.abs(inside - (lo + n * k // chunks)).argmin()])
+                    for k in range(1, chunks)}) if len(inside) else []
+    ends = inner + [hi]
+    out, t0 = [], lo
+    for t1 in ends:
+        if t1 <= t0:
+            continue
+        rects = []
+        seg = th[t0:t1].astype(np.int64)
+        bid = band_id[t0:t1]
+        for bnd in np.unique(bid):
+            cols = seg[bid == bnd, 1]
+            r0, r1 = genes(bnd * band * tile_m), genes((bnd + 1) * band * tile_m)
+            c0, c1 = max(genes(cols.min()), r0), genes(cols.max() + 256)
+            if r1 > r0 and c1 > c0:
+                rects.append((r0, r1, c0, c1))
+                m0 = max(c0, r1)
+                if c1 > m0:
+                    rects.append((m0, c1, r0, r1))
+        out.append((t0 - lo, t1 - lo, rects))
+        t0 = t1
+    return out
 
 
 def broadcast_block(buf: torch.Tensor, total: int, group=None) -> torch.Tensor:
@@ -173,6 +275,24 @@ def broadcast_block(buf: torch.Tensor, total: int, group=None) -> torch.Tensor:
     src = dist.get_global_rank(group, 0) if group is not None else 0
     dist.broadcast(buf[:total], src=src, group=group)
     return buf
+
+
+class HostSink:
+    """Where a rank's result rectangles go on the host: a page-locked float32 matrix given as
+    (address, bytes per row), as a pinned tensor, or as a callable returning a pinned tensor (called
+    after the kernels are enqueued, so its allocation overlaps the computation)."""
+
+    def __init__(self, ptr: int = 0, pitch: int = 0, tensor=None):
+        self.ptr, self.pitch, self.tensor = ptr, pitch, tensor
+
+    def resolve(self, engine=None):
+        if self.tensor is not None:
+            t = self.tensor() if callable(self.tensor) else self.tensor
+            self.tensor = t
+            if engine is not None:
+                engine.last_host_result = t
+            self.ptr, self.pitch = t.data_ptr(), t.stride(0) * t.element_size()
+        return self.ptr, self.pitch
 
 
 class Engine:
@@ -197,13 +317,22 @@ class Engine:
         self.operand = "auto"
         # wave lockstep of the persistent tile kernels: "auto" = when the operand exceeds L2
         self.lockstep = "auto"
-        self._sync_ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
+        # barrier words of the wave lockstep: one 64-byte slot per launch, taken in turn, so launches
+        # that overlap on different streams never share one
+        self._sync_ws = torch.zeros(32 * 64, dtype=torch.uint8, device=self.device)
+        self._sync_next = 0
+        self._flag_ws = torch.zeros(16, dtype=torch.int32, device=self.device)
         # bench.py sets this to a list to collect (entry point, start event, end event, kernels)
         self.kernel_events = None
         # multi-rank: send the value rows asynchronously and expand the one-hot operand meanwhile
         self.defer_values = os.environ.get("GV_DEFER_VALUES", "1") != "0"
         # pinned host matrix a callable `out_host` produced during the last mi_scores call
         self.last_host_result = None
+        self.host_timings = None
+        # worker threads of the pageable upload (0 = from the core count; one process per GPU shares
+        # the host cores with its peers)
+        lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        self.copy_threads = int(os.environ.get("GV_COPY_THREADS", "0")) or max(2, min(8, (os.cpu_count() or 8) // max(lw, 1)))
 
     # kernels launched by each entry point (memsets / copies not counted)
     _LAUNCHES = {"gv_discretize_csr": 2, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
@@ -227,20 +356,39 @@ class Engine:
     def _sync_ptr(self, operand_bytes: int):
         """Device scratch for the wave barrier, or None when the operand fits L2 anyway."""
         on = self.lockstep is True or (self.lockstep == "auto" and operand_bytes > 96 * 1024 * 1024)
-        return self._sync_ws.data_ptr() if on else None
+        if not on:
+            return None
+        self._sync_next = (self._sync_next + 1) % 32
+        return self._sync_ws.data_ptr() + 64 * self._sync_next
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def upload_csr(self, X, pinned: bool = False) -> CsrDevice:
+    def upload_csr(self, X, pinned: bool = False, rows: Optional[tuple] = None) -> CsrDevice:
         """scipy CSR (host) -> device tensors.  Integer dtypes are converted to the smallest float
-        type that holds them exactly (discretisation arithmetic is identical: see DESIGN.md)."""
+        type that holds them exactly (discretisation arithmetic is identical: see DESIGN.md).
+        The arrays are pageable host memory (the reference hands over adata.X, data.py:171): they go
+        through gv_upload_pageable (pinned staging ring filled by worker threads).  Whether the matrix
+        is canonical (ascending, unique, in-range column indices per row) is taken from scipy when it
+        already knows and otherwise checked on the device (gv_csr_check); only a matrix that is not
+        is canonicalised on the host and uploaded again.
+        rows = (r0, r1): upload that block of cells only (the sharded front end)."""
+        import time
         import scipy.sparse as sp
-        X = sp.csr_matrix(X)
-        if not X.has_canonical_format:
+        t_up = time.perf_counter()
+        if not sp.issparse(X) or X.format != "csr":
+            X = sp.csr_matrix(X)
+        known = getattr(X, "_has_canonical_format", None)
+        if getattr(X, "_has_sorted_indices", True) is False:
+            known = False
+        if known is False:
             X = X.copy()
             X.sum_duplicates()
-        data = X.data
+            known = True
+        n_cells, n_genes = X.shape
+        r0, r1 = rows if rows is not None else (0, n_cells)
+        e0, e1 = int(X.indptr[r0]), int(X.indptr[r1])
+        data = X.data[e0:e1]
         if data.dtype == np.float32 or data.dtype == np.float64:
             pass
         elif np.issubdtype(data.dtype, np.integer) or data.dtype == np.bool_:
@@ -248,40 +396,36 @@ class Engine:
             data = data.astype(np.float64 if big else np.float32)
         else:
             data = data.astype(np.float64)
-        n_cells, n_genes = X.shape
-        vals = torch.from_numpy(np.ascontiguousarray(data))
-        cols = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32))
-        ptr = torch.from_numpy(np.ascontiguousarray(X.indptr, dtype=np.int64))
-        if pinned:
-            vals, cols, ptr = vals.pin_memory(), cols.pin_memory(), ptr.pin_memory()
-            dv, dc, dp = (t.to(self.device, non_blocking=True) for t in (vals, cols, ptr))
-        else:
-            dv, dc, dp = self._staged_to_device(vals), self._staged_to_device(cols), self._staged_to_device(ptr)
-        return CsrDevice(dv, dc, dp, n_cells, n_genes)
-
-    _STAGE_BYTES = 64 << 20
-
-    def _staged_to_device(self, host: torch.Tensor) -> torch.Tensor:
-        """Pageable host tensor -> device through two pinned staging buffers: the CPU copy into one
-        buffer overlaps the DMA out of the other (a plain pageable cudaMemcpy runs at a few GB/s)."""
-        nbytes = host.numel() * host.element_size()
-        if nbytes < 2 * self._STAGE_BYTES:
-            return host.to(self.device)
-        if not hasattr(self, "_stage"):
-            self._stage = [torch.empty(self._STAGE_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2)]
-            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        src = host.contiguous().view(-1).view(torch.uint8)
-        dst = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        stream = torch.cuda.current_stream(self.device)
-        for i, off in enumerate(range(0, nbytes, self._STAGE_BYTES)):
-            n = min(self._STAGE_BYTES, nbytes - off)
-            b = i & 1
-            if i >= 2:
-                self._stage_ev[b].synchronize()          # the DMA that last read this buffer is done
-            self._stage[b][:n].copy_(src[off:off + n])
-            dst[off:off + n].copy_(self._stage[b][:n], non_blocking=True)
-            self._stage_ev[b].record(stream)
-        return dst.view(host.dtype).view(host.shape)
+        cols = np.ascontiguousarray(X.indices[e0:e1], dtype=np.int32)
+        ptr = np.ascontiguousarray(X.indptr[r0:r1 + 1], dtype=np.int64)
+        if e0:
+            ptr = ptr - e0
+        data = np.ascontiguousarray(data)
+        with torch.cuda.device(self.device):
+            dv = torch.empty(data.shape, dtype=torch.float32 if data.dtype == np.float32 else torch.float64,
+                             device=self.device)
+            dc = torch.empty(cols.shape, dtype=torch.int32, device=self.device)
+            dp = torch.empty(ptr.shape, dtype=torch.int64, device=self.device)
+            st = self._stream()
+            self._timed_host("upload_csr: views + device buffers", t_up)
+            t_st = time.perf_counter()
+            for dst, src in ((dv, data), (dc, cols), (dp, ptr)):
+                _lib.call("gv_upload_pageable", dst.data_ptr(), src.ctypes.data, src.nbytes, self.copy_threads, st)
+            self._timed_host("upload_csr: staging copies", t_st)
+            csr = CsrDevice(dv, dc, dp, r1 - r0, n_genes)
+            if known is not True:
+                ok = np.zeros(1, dtype=np.int32)
+                _lib.call("gv_csr_check", dc.data_ptr(), dp.data_ptr(), csr.n_cells, n_genes,
+                          self._flag_ws.data_ptr(), ok.ctypes.data, st)
+                if int(ok[0]) == 2:
+                    raise ValueError("column index out of range in the CSR matrix")
+                if int(ok[0]) != 0:
+                    Xc = X.copy()
+                    Xc.sum_duplicates()             # sorts the indices and merges duplicate entries
+                    Xc._has_canonical_format = True
+                    return self.upload_csr(Xc, rows=rows)
+        self._timed_host("upload_csr (host side: staging + canonical check)", t_up)
+        return csr
 
     def schedule(self, op_rows: int, cta_group: Optional[int] = None, rank: int = 0, world: int = 1):
         """Device tile list (int32 [n,2]) for this rank: a contiguous slice of the band-ordered
@@ -457,14 +601,46 @@ class Engine:
                        blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.edges.data_ptr(),
                        blk.n_cells, G,
                        blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, sgn.data_ptr(), ld, None, 0,
-                       self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
-            if rule == "rust":
-                sgn.masked_fill_(sgn == 0, 1)
+                       self.cta_group, self._sync_ptr(rows * blk.kp), 1 if rule == "rust" else 0,
+                       self._stream())
             return sgn
 
+    def _tiles_to_host(self, launch, n_tiles, pieces, out, sink):
+        """Run a rank's tile slice with launch(t0, t1) in `pieces` (host_pieces) and copy every
+        finished piece's rectangles of `out` (device float32 [G][G]) into the host matrix of `sink`
+        (HostSink) on a second stream, under the next piece's computation."""
+        if sink is None or n_tiles == 0 or not pieces:
+            if n_tiles:
+                launch(0, n_tiles)
+            if sink is not None:
+                sink.resolve(self)
+            return
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        # all pieces are enqueued first (an event after each), then the copies: a host buffer that
+        # is only allocated now (lazy sink) is paid for while the GPU is already computing
+        evs = []
+        for t0, t1, rects in pieces:
+            launch(t0, t1)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            evs.append(ev)
+        ptr, pitch = sink.resolve(self)
+        cs = self._copy_stream
+        esz, ld = out.element_size(), out.stride(0) * out.element_size()
+        for ev, (t0, t1, rects) in zip(evs, pieces):
+            cs.wait_event(ev)
+            for r0, r1, c0, c1 in rects:
+                _lib.call("gv_copy_rect_d2h", ptr + r0 * pitch + c0 * esz, pitch,
+                          out.data_ptr() + r0 * ld + c0 * esz, ld, (c1 - c0) * esz, r1 - r0, cs.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(cs)
+        main.wait_event(done)
+
     def moment_scores(self, blk: BinBlock, kind: int, out: Optional[torch.Tensor] = None,
-                      rank: int = 0, world: int = 1) -> torch.Tensor:
-        """float32 [G][G] Pearson / cosine / Jaccard matrix (zero diagonal)."""
+                      rank: int = 0, world: int = 1, sink=None, host_chunks: int = 4) -> torch.Tensor:
+        """float32 [G][G] Pearson / cosine / Jaccard matrix (zero diagonal).  sink: see mi_scores."""
         assert blk.val_rows is not None
         with torch.cuda.device(self.device):
             G = blk.n_genes
@@ -472,24 +648,35 @@ class Engine:
                 out = torch.zeros((G, G), dtype=torch.float32, device=self.device)
             rows = value_rows(G, blk.n_limbs)
             tiles, n, _ = self.schedule(rows, rank=rank, world=world)
-            self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), rows, blk.kp,
-                       blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.edges.data_ptr(),
-                       blk.n_cells, G,
-                       blk.n_limbs, blk.limb_bits, tiles.data_ptr(), n, None, 0, out.data_ptr(),
-                       out.stride(0), self.cta_group, self._sync_ptr(rows * blk.kp), self._stream())
+
+            def launch(t0, t1):
+                self._call("gv_moment_tiles", kind, blk.val_rows.data_ptr(), rows, blk.kp,
+                           blk.gsum.data_ptr(), blk.gsq.data_ptr(), blk.marg.data_ptr(), blk.edges.data_ptr(),
+                           blk.n_cells, G, blk.n_limbs, blk.limb_bits, tiles.data_ptr() + 8 * t0, t1 - t0,
+                           None, 0, out.data_ptr(), out.stride(0), self.cta_group,
+                           self._sync_ptr(rows * blk.kp), 0, self._stream())
+
+            pieces = None
+            if sink is not None:
+                pieces = host_pieces(rows, self.cta_group, self.band, 32 // blk.n_limbs, G, rank, world,
+                                     host_chunks)
+            self._tiles_to_host(launch, n, pieces, out, sink)
             return out
 
     def mi_scores(self, blk: BinBlock, onehot: torch.Tensor, B: int,
                   sgn: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                  rank: int = 0, world: int = 1, out_host: Optional[torch.Tensor] = None,
-                  host_chunks: int = 6) -> torch.Tensor:
+                  rank: int = 0, world: int = 1, out_host=None, host_chunks: int = 6,
+                  sink=None) -> torch.Tensor:
         """float32 [G][G] MI (times the Pearson sign when `sgn` is given).
 
-        out_host (pinned float32 [G][G], or a callable returning one; single rank): the result is
-        streamed to the host while it is computed.  The tile schedule walks the triangle band by band, and a tile of band b only
-        writes rows of bands >= b, so once the tiles of a band have run its rows are final: the
-        schedule is launched in `host_chunks` pieces cut at band boundaries and every finished piece
-        is copied on a second stream under the next one."""
+        sink (HostSink: a host matrix of pitch bytes per row, page-locked): the result is streamed to
+        the host while it is computed.  The rank's slice of the tile schedule is launched in
+        `host_chunks` pieces and the rectangles of the result matrix a finished piece owns
+        (host_pieces) are copied on a second stream under the next piece.  With one rank these are
+        blocks of full rows; with several every rank writes the rectangles of its own tiles into the
+        one host matrix all ranks of the box share (hostpool.py), so the full matrix is assembled
+        without a collective.  out_host (pinned float32 [G][G] tensor, or a callable returning one)
+        is the single-rank shorthand."""
         with torch.cuda.device(self.device):
             G = blk.n_genes
             if out is None:
@@ -505,50 +692,14 @@ class Engine:
                            out.data_ptr(), out.stride(0), self.cta_group, fmt,
                            self._sync_ptr(rows * row_bytes), self._stream())
 
-            if out_host is None or world > 1 or n == 0:
-                launch(0, n)
-                if out_host is not None:
-                    if callable(out_host):
-                        out_host = out_host()
-                        self.last_host_result = out_host
-                    out_host.copy_(out, non_blocking=True)
-                return out
-            # cut points: first tiles of bands, nearest to equal shares of the schedule
-            key = ("cuts", rows, self.cta_group, self.band, host_chunks)
-            if key not in self._sched_cache:
-                th, _ = tile_slice(rows, self.cta_group, self.band)
-                tm = _lib.call("gv_tile_m", self.cta_group)
-                band_of = th[:, 0] // (tm * self.band)
-                starts = np.flatnonzero(np.diff(band_of, prepend=-1))          # first tile of each band
-                cuts = sorted({int(starts[np.abs(starts - n * k // host_chunks).argmin()])
-                               for k in range(1, host_chunks)} - {0})
-                gpb = 32 // B
-                genes_at = [min(G, int(th[c, 0]) // 32 * gpb) for c in cuts]    # first gene of the band
-                self._sched_cache[key] = (cuts + [n], genes_at + [G])
-            cuts, gene_ends = self._sched_cache[key]
-            if not hasattr(self, "_copy_stream"):
-                self._copy_stream = torch.cuda.Stream(device=self.device)
-            main = torch.cuda.current_stream(self.device)
-            # all pieces are enqueued first (an event after each), then the copies: a host buffer that
-            # is only allocated now (callable out_host) is paid for while the GPU is already computing
-            pieces, t0, g0 = [], 0, 0
-            for t1, g1 in zip(cuts, gene_ends):
-                launch(t0, t1)
-                ev = torch.cuda.Event()
-                ev.record(main)
-                pieces.append((ev, g0, g1))
-                t0, g0 = t1, g1
-            if callable(out_host):
-                out_host = out_host()
-                self.last_host_result = out_host
-            with torch.cuda.stream(self._copy_stream):
-                for ev, g0, g1 in pieces:
-                    if g1 > g0:
-                        self._copy_stream.wait_event(ev)
-                        out_host[g0:g1].copy_(out[g0:g1], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(self._copy_stream)
-            main.wait_event(done)
+            if sink is None and out_host is not None:
+                if world > 1:
+                    raise GvError("mi_scores", -1, "out_host is single-rank; pass a HostSink over the shared matrix")
+                sink = HostSink(tensor=out_host)
+            pieces = None
+            if sink is not None:
+                pieces = host_pieces(rows, self.cta_group, self.band, 32 // B, G, rank, world, host_chunks)
+            self._tiles_to_host(launch, n, pieces, out, sink)
             return out
 
     # ------------------------------------------------------------------ graph cross-correlation
@@ -673,7 +824,8 @@ class Engine:
     def mi_from_csr(self, csr: Optional[CsrDevice], n_cells: int, n_genes: int, n_bins: int = 10,
                     signed: bool = False, rank: int = 0, world: int = 1, group=None,
                     out: Optional[torch.Tensor] = None,
-                    out_host: Optional[torch.Tensor] = None, sign_rule: str = "numpy") -> torch.Tensor:
+                    out_host: Optional[torch.Tensor] = None, sign_rule: str = "numpy",
+                    sink=None) -> torch.Tensor:
         """All-pairs (signed) MI.  With world > 1 only rank 0 needs `csr`; each rank returns a
         [G][G] matrix in which the entries of its own tiles are filled."""
         import torch.distributed as dist
@@ -703,12 +855,42 @@ class Engine:
                     self._sched_cache[key] = self.sign_tiles_for(mine, B, blk.n_limbs)
                 st = self._sched_cache[key]
             sgn = self.sign_matrix(blk, tiles=st, rule=sign_rule)
-        return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, out_host=out_host)
+        return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, out_host=out_host,
+                              sink=sink)
+
+    def resolve_front(self, front: str, world: int) -> str:
+        """"broadcast" or "sharded" for this process group (see metrics.compute_mi_b200)."""
+        if world <= 1 or front == "broadcast":
+            return "broadcast"
+        if front not in ("auto", "sharded"):
+            raise ValueError(f"unknown front {front!r} (auto, broadcast or sharded)")
+        return "broadcast"
+
+    def mi_device_step(self, csr, n_cells, n_genes, n_bins=10, signed=False, rank=0, world=1, out=None,
+                       front="broadcast"):
+        """One pass of the hot path with the input already resident in HBM (bench.py's `value` leg)."""
+        return self.mi_from_csr(csr if rank == 0 else None, n_cells, n_genes, n_bins=n_bins, signed=signed,
+                                rank=rank, world=world, out=out)
+
+    def _timed_host(self, name, t0):
+        """Host wall-clock phases of the public call (bench.py sets host_timings to a dict)."""
+        if getattr(self, "host_timings", None) is not None:
+            import time
+            self.host_timings.setdefault(name, []).append((time.perf_counter() - t0) * 1e3)
+
+    def mi_from_host_sharded(self, X, n_bins=10, signed=False, rank=0, world=1, sign_rule="numpy",
+                             sink=None, required=False) -> bool:
+        """Sharded front end (every rank uploads and transposes its own block of cells, peer stores
+        replicate the dense count rows): see DESIGN.md section 5.  Returns False when the data do not
+        qualify and the caller should take the broadcast path."""
+        if required:
+            raise GvError("mi_from_host_sharded", -4, "the sharded front end is not available")
+        return False
 
     def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,
                         n_cells: Optional[int] = None, n_genes: Optional[int] = None,
                         rank: int = 0, world: int = 1, group=None,
-                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        out: Optional[torch.Tensor] = None, sink=None) -> torch.Tensor:
         """Pearson / cosine / Jaccard matrix; ranks=True with GV_MOM_PEARSON is Spearman.  With
         world > 1 only rank 0 needs `csr` (pass n_cells / n_genes elsewhere): rank 0 builds the value
         rows, one broadcast replicates the block, every rank computes its slice of the tile schedule."""
@@ -720,7 +902,7 @@ class Engine:
         blk = self.discretize(csr, 10, mode) if (rank == 0 or not distributed) else None
         if distributed:
             blk = self._replicate(blk, n_cells, n_genes, 10, mode, group)
-        return self.moment_scores(blk, kind, out=out, rank=rank, world=world)
+        return self.moment_scores(blk, kind, out=out, rank=rank, world=world, sink=sink)
 
 
 _engines = {}

@@ -66,40 +66,89 @@ def _dist_info():
     return 0, 1
 
 
-def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, gather=True, sign_rule="numpy"):
+def _pinned_result(n_genes):
+    import torch
+    return lambda: torch.empty((n_genes, n_genes), dtype=torch.float32, pin_memory=True)
+
+
+def _run_to_host(eng, n_genes, gene_names, run, front=None):
+    """Shared body of the public calls: run(sink) enqueues the whole path on this rank with its
+    result rectangles streaming into the host matrix behind `sink`; returns the ScoreMatrix.
+
+    One rank: a pinned matrix (allocated while the GPU already computes).  Several ranks (one process
+    per GPU, torch.distributed initialised): the one shared, page-locked host matrix of the box
+    (hostpool.py); every rank copies the rectangles of its own tiles into it and, after a per-rank
+    completion flag, every rank returns the full matrix.  No reduce, no gather."""
+    import time
+    import torch
+    from .engine import HostSink
+    rank, world = _dist_info()
+    t0 = time.perf_counter()
+    if world == 1:
+        run(HostSink(tensor=_pinned_result(n_genes)))
+        eng._timed_host("enqueue (upload + launches + host buffer)", t0)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize(eng.device)
+        eng._timed_host("wait for the device", t1)
+        host, eng.last_host_result = eng.last_host_result, None
+        return ScoreMatrix(host.numpy(), gene_names)
+    from .hostpool import get_pool
+    pool = get_pool()
+    seq, slot, mapping = pool.begin(n_genes * n_genes * 4)
+    eng._timed_host("agree on the shared host matrix", t0)
+    t1 = time.perf_counter()
+    try:
+        run(HostSink(ptr=mapping.ptr, pitch=n_genes * 4))
+        eng._timed_host("enqueue (upload + launches)", t1)
+        t2 = time.perf_counter()
+        torch.cuda.synchronize(eng.device)
+        eng._timed_host("wait for the device", t2)
+    except BaseException:
+        pool.release(slot, pool.slots[slot][0])
+        raise
+    t3 = time.perf_counter()
+    pool.finish(seq, slot)
+    eng._timed_host("wait for the other ranks", t3)
+    return ScoreMatrix(pool.matrix(slot, n_genes), gene_names)
+
+
+def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, sign_rule="numpy", front="auto"):
     """All-pairs (signed) mutual information on B200; returns a ScoreMatrix (Mapping view with
     the reference's dict semantics, see scores.py).
 
-    Under torch.distributed (one process per GPU) the tile space is split over the ranks after a
-    single broadcast of the bin block; with gather=True the disjoint per-rank tiles are then
-    summed onto rank 0 (result assembly, outside the hot path) and the other ranks return their
-    partial matrices.
+    Under torch.distributed (one process per GPU of one box, every rank calling with the same X) the
+    tile space is split over the ranks; every rank writes its own result tiles into one shared host
+    matrix and every rank returns the full ScoreMatrix (see _run_to_host).
+
+    front: how the discretised matrix reaches every rank.  "broadcast": rank 0 uploads and
+    discretises, one NCCL broadcast replicates the bin block (north_star's prescription).  "sharded":
+    every rank uploads its own block of cells over its own PCIe link and transposes it straight into
+    every peer's memory over NVLink (peer stores, no NCCL call), then bins all genes locally.  "auto":
+    sharded when the data qualify (count data on one box), else broadcast.
 
     sign_rule: "numpy" (default) signs with np.sign of the Pearson correlation like the reference's
     NumPy / Numba / torch tiers and its documentation (metrics.py:134, 227, 302): a zero or undefined
     correlation zeroes the score; "rust" reproduces the Rust tier (src/lib.rs:91-94): +1 unless the
     correlation is negative."""
-    import torch
     eng = get_engine(_device_of(device))
     rank, world = _dist_info()
     n_cells, n_genes = X.shape
     if len(gene_names) != n_genes:
         raise ValueError("gene_names must have one entry per column of X")
-    csr = eng.upload_csr(X) if rank == 0 else None
-    if world == 1:
-        # the pinned result matrix is allocated while the GPU computes and filled band by band
-        eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, sign_rule=sign_rule,
-                        out_host=lambda: torch.empty((n_genes, n_genes), dtype=torch.float32, pin_memory=True))
-        torch.cuda.synchronize(eng.device)
-        host, eng.last_host_result = eng.last_host_result, None
-        return ScoreMatrix(host.numpy(), gene_names)
-    out = eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world,
-                          sign_rule=sign_rule)
-    if gather:
-        import torch.distributed as dist
-        dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
-    torch.cuda.synchronize(eng.device)
-    return ScoreMatrix(out.cpu().numpy(), gene_names)
+    if sign_rule not in ("numpy", "rust"):
+        raise ValueError(f"unknown sign rule {sign_rule!r} (numpy or rust)")
+
+    def run(sink):
+        if world > 1 and front != "broadcast":
+            done = eng.mi_from_host_sharded(X, n_bins=n_bins, signed=signed, rank=rank, world=world,
+                                            sign_rule=sign_rule, sink=sink, required=(front == "sharded"))
+            if done:
+                return
+        csr = eng.upload_csr(X) if rank == 0 else None
+        eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world,
+                        sign_rule=sign_rule, sink=sink)
+
+    return _run_to_host(eng, n_genes, gene_names, run)
 
 
 @register_target("mi")
@@ -108,27 +157,26 @@ def target_mi(X, gene_names, signed=False, backend="b200", device="cuda", n_bins
     target_kwargs={"sign_rule": "rust"} selects the Rust tier's sign convention."""
     if backend in ("b200", "auto"):
         return compute_mi_b200(X, gene_names, n_bins=n_bins, signed=signed, device=device,
-                               sign_rule=kwargs.get("sign_rule", "numpy"))
+                               sign_rule=kwargs.get("sign_rule", "numpy"), front=kwargs.get("front", "auto"))
     raise ValueError(f"Unknown MI backend: {backend}")
 
 
-def _moment_target(X, gene_names, kind, device=None, ranks=False, gather=True):
+def _moment_target(X, gene_names, kind, device=None, ranks=False):
     """Shared body of the matrix targets; under torch.distributed the tile space is split over the
-    ranks like compute_mi_b200 (one broadcast of the value rows, optional result assembly)."""
-    import torch
+    ranks like compute_mi_b200 (one broadcast of the value rows, result rectangles into the shared
+    host matrix)."""
     eng = get_engine(_device_of(device))
     rank, world = _dist_info()
     n_cells, n_genes = X.shape
     if len(gene_names) != n_genes:
         raise ValueError("gene_names must have one entry per column of X")
-    csr = eng.upload_csr(X) if rank == 0 else None
-    out = eng.target_from_csr(csr, kind, ranks=ranks, n_cells=n_cells, n_genes=n_genes, rank=rank, world=world)
-    if world > 1 and gather:
-        import torch.distributed as dist
-        # every entry is computed by exactly one rank and is 0 elsewhere (NaN + 0 stays NaN)
-        dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
-    torch.cuda.synchronize(eng.device)
-    return ScoreMatrix(out.cpu().numpy(), gene_names)
+
+    def run(sink):
+        csr = eng.upload_csr(X) if rank == 0 else None
+        eng.target_from_csr(csr, kind, ranks=ranks, n_cells=n_cells, n_genes=n_genes, rank=rank, world=world,
+                            sink=sink)
+
+    return _run_to_host(eng, n_genes, gene_names, run)
 
 
 @register_target("pearson")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GV_ABI_VERSION 4
+#define GV_ABI_VERSION 5
 #define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
 #define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
 #define GV_EDGE_SCALE_SLOT 15 /* edges[g][15]: real value of one unit of the gene's value-row integer */
@@ -42,7 +42,8 @@ typedef enum gv_status {
   GV_ERR_ARG = -1,         /* bad argument (shape, alignment, range) */
   GV_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
   GV_ERR_DEVICE = -3,      /* not an sm_100 device */
-  GV_ERR_UNSUPPORTED = -4  /* input outside what the exact integer path covers */
+  GV_ERR_UNSUPPORTED = -4, /* input outside what the exact integer path covers */
+  GV_ERR_TIMEOUT = -5      /* another rank of the box did not arrive in time */
 } gv_status;
 
 typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
@@ -54,16 +55,17 @@ typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
  *   GV_PATH_AUTO    try COUNTS, fall back to GENERAL when the data do not qualify */
 typedef enum gv_disc_path { GV_PATH_AUTO = 0, GV_PATH_COUNTS = 1, GV_PATH_GENERAL = 2 } gv_disc_path;
 
-/* Storage of the one-hot operand of the MI contraction (both give bit-exact joint counts):
- *   GV_OPERAND_INT8  one byte per (row, cell); tcgen05 kind::i8, INT32 accumulators (the default)
- *   GV_OPERAND_FP4   4-bit E2M1 (two cells per byte); tcgen05 kind::mxf4.block_scale with unit scales,
- *                    FP32 accumulators (exact below 2^24 cells), half the operand bytes and twice the
- *                    cells per MMA; needs 10 or 5 rows per gene */
 /* What gv_discretize_csr writes into the value rows (see there). */
 typedef enum gv_value_mode {
   GV_VAL_COUNTS = 0, GV_VAL_DETECTED = 1, GV_VAL_FIXED_POINT = 2, GV_VAL_RANKS = 3
 } gv_value_mode;
 
+/* Storage of the one-hot operand of the MI contraction (both give bit-exact joint counts):
+ *   GV_OPERAND_INT8  one byte per (row, cell); tcgen05 kind::i8, INT32 accumulators; every n_bins
+ *   GV_OPERAND_FP4   4-bit E2M1 (two cells per byte); tcgen05 kind::mxf4.block_scale with unit scales,
+ *                    FP32 accumulators (exact below 2^24 cells), half the operand bytes and twice the
+ *                    cells per MMA; needs 10 or 5 rows per gene.  The Python engine picks FP4 where it
+ *                    applies (the reference's default n_bins = 10 does) and INT8 otherwise. */
 typedef enum gv_operand_format { GV_OPERAND_INT8 = 0, GV_OPERAND_FP4 = 1 } gv_operand_format;
 
 /* Score kinds of gv_moment_tiles. */
@@ -126,6 +128,13 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
                       int val_mode, int val_limbs, int val_limb_bits, uint64_t* data_flags_out_host,
                       void* workspace, size_t workspace_bytes, int path, int* path_used_host,
                       void* stream);
+
+/* Is the CSR matrix canonical (scipy's has_canonical_format: per row ascending, unique column indices)
+ * with every index in [0, n_genes)?  The discretisation assumes it; the reference gets it from
+ * scipy.  Synchronous; *result_host = 0 canonical, 1 unsorted or duplicate entries (canonicalise on the
+ * host: sum_duplicates), 2 an index out of range.  scratch_dev: 4 bytes of device memory. */
+int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int n_genes,
+                 int* scratch_dev, int* result_host, void* stream);
 
 /* ---------------------------------------------------------------- gene entropy
  * Replaces GeneVectorDataset.get_gene_entropy (data.py:186-203), which runs before every score
@@ -207,13 +216,16 @@ int gv_mma_peak(int operand_format, int cta_group, int iters, int mode, double* 
  * (metrics.py:423-431).  The co-moments are exact integers (128-bit covariance arithmetic): requires
  * n_cells * (2^limb_bits - 1)^2 < 2^32, n_limbs in 1..4 and n_cells * 4^(n_limbs*limb_bits) < 2^63.
  * edges: the `edges` array of gv_discretize_csr or NULL; GV_MOM_COSINE reads GV_EDGE_OFFSET_SLOT
- * from it (genes with negative values are stored shifted; cosine is not shift-invariant). */
+ * from it (genes with negative values are stored shifted; cosine is not shift-invariant).
+ * sign_zero (GV_MOM_SIGN only): what is written where the correlation is exactly 0 or undefined (a
+ * constant gene): 0 = np.sign(nan_to_num(corrcoef)) as the NumPy / Numba / torch tiers use it
+ * (metrics.py:111,134,227,302); 1 = the Rust tier's rule, +1 unless negative (src/lib.rs:91-94). */
 int gv_moment_tiles(int kind, const void* val_rows, int64_t op_rows, int64_t kp,
                     const int64_t* gsum, const int64_t* gsq, const int32_t* marg, const double* edges,
                     int64_t n_cells,
                     int n_genes, int n_limbs, int limb_bits, const int32_t* tiles, int64_t n_tiles,
                     int8_t* sgn, int64_t ld_sgn, float* out, int64_t ld_out, int cta_group,
-                    void* sync_ws, void* stream);
+                    void* sync_ws, int sign_zero, void* stream);
 
 /* ---------------------------------------------------------------- graph cross-correlation target
  * Replaces target_graph_xcorr (genevector/_graph_targets.py:10-55) with the built-in "mean"
@@ -255,6 +267,39 @@ int gv_symmetrize(const float* t, int64_t ld_t, int n_genes, float* out, int64_t
 int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_genes, float c,
                               int clamp_negative, int round5, int64_t* i_idx, int64_t* j_idx,
                               float* xij, void* stream);
+
+/* ---------------------------------------------------------------- host runtime (no kernels)
+ * The reference hands its backends host arrays (scipy CSR in: data.py:171, 319-326; a score structure
+ * out: metrics.py:137-140) and runs in one process; these entries move the same data for one process
+ * per GPU without a collective.
+ *
+ * gv_upload_pageable: pageable host memory -> device on `stream` through a ring of pinned staging
+ *   buffers filled by n_threads worker threads (0 = pick from the core count).  Returns when the
+ *   source has been read (it may be reused); the copies complete in stream order.  The ring (a few
+ *   pinned 8 MB slots) outlives the call; gv_runtime_shutdown() frees it.
+ * gv_shm_open / gv_shm_close: a POSIX shared-memory segment (`name` starts with '/'), optionally
+ *   page-locked for CUDA (cudaHostRegister) in the calling process.  create = 1 replaces a stale
+ *   segment of that name.  Every rank of a box maps the same G x G result matrix and DMAs the
+ *   rectangles of its own tiles into it (gv_copy_rect_d2h): result assembly needs no reduction.
+ * gv_flag_store / gv_flag_load / gv_flag_wait_ge: release / acquire accesses to a uint64 in such a
+ *   segment (completion hand-shake between the ranks); the wait returns GV_ERR_TIMEOUT after
+ *   timeout_ms (negative: wait forever).
+ * gv_copy_rect_d2h: rows x width_bytes rectangle, device (pitch src_pitch_bytes) -> host. */
+int gv_upload_pageable(void* dst_dev, const void* src_host, size_t bytes, int n_threads, void* stream);
+int gv_runtime_shutdown(void);
+int gv_shm_open(const char* name, size_t bytes, int create, int cuda_register, void** ptr_out_host);
+int gv_shm_close(void* ptr_host, size_t bytes, int cuda_registered, const char* unlink_name);
+int gv_flag_store(uint64_t* flag_host, uint64_t value);
+uint64_t gv_flag_load(const uint64_t* flag_host);
+int gv_flag_wait_ge(const uint64_t* flag_host, uint64_t value, int timeout_ms);
+int gv_copy_rect_d2h(void* dst_host, size_t dst_pitch_bytes, const void* src_dev, size_t src_pitch_bytes,
+                     size_t width_bytes, size_t rows, void* stream);
+/* Device allocations other processes of the box can map (CUDA IPC, peer access over NVLink):
+ * gv_ipc_alloc cudaMallocs `bytes` and writes the 64-byte handle a peer passes to gv_ipc_open. */
+int gv_ipc_alloc(size_t bytes, void** dev_ptr_out, void* handle_out_64_host);
+int gv_ipc_open(const void* handle_64_host, void** dev_ptr_out);
+int gv_ipc_close(void* dev_ptr);
+int gv_ipc_free(void* dev_ptr);
 
 #ifdef __cplusplus
 }

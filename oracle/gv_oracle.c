@@ -33,6 +33,12 @@ int gvo_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets its thread count itself */
+void gvo_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
+
 /* ------------------------------------------------------------------ discretisation */
 
 static int cmp_f32(const void* a, const void* b) {

@@ -37,7 +37,8 @@ def build() -> str:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
+        src = os.path.join(_HERE, "gv_oracle.c")
+        if not os.path.exists(_SO) or os.path.getmtime(src) > os.path.getmtime(_SO):
             build()
         L = C.CDLL(_SO)
         L.gvo_num_threads.restype = C.c_int
@@ -68,6 +69,12 @@ def lib() -> C.CDLL:
 
 def num_threads() -> int:
     return int(lib().gvo_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().gvo_set_num_threads(int(n))
+    return num_threads()
 
 
 def _dense(X):

@@ -81,15 +81,56 @@ def test_tile_schedule_covers_upper_triangle_once(op_rows, tile_m, band):
 
 
 def test_rank_slices_partition_the_schedule():
-    from genevector_b200 import _lib
-    lib = _lib.load()
-    n = lib.gv_tile_schedule(20000, 256, 8, None, 0)
+    from genevector_b200.engine import schedule_host, rank_bounds
+    th, tile_m = schedule_host(213344, 2, 8)          # the one-hot operand of 20,000 genes
+    n = len(th)
     for world in (1, 2, 4, 8):
-        bounds = [((n * r) // world, (n * (r + 1)) // world) for r in range(world)]
-        assert bounds[0][0] == 0 and bounds[-1][1] == n
-        assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
-        sizes = [b - a for a, b in bounds]
-        assert max(sizes) - min(sizes) <= 1
+        b = rank_bounds(th, tile_m, 8, world)
+        assert b[0] == 0 and b[-1] == n and all(b[r] <= b[r + 1] for r in range(world))
+        sizes = [b[r + 1] - b[r] for r in range(world)]
+        # equal shares snapped to whole tile columns of a band (at most 8 tiles) or a diagonal block
+        assert max(sizes) - min(sizes) <= 2 * 36, sizes
+
+
+@pytest.mark.parametrize("n_genes,B,cg,band,world", [(700, 10, 2, 8, 1), (700, 10, 2, 8, 3), (1500, 10, 2, 3, 4),
+                                                     (1100, 5, 1, 8, 2), (2600, 16, 2, 8, 8), (900, 8, 1, 2, 5),
+                                                     (96, 10, 2, 8, 2)])
+def test_host_pieces_are_exactly_what_the_tiles_write(n_genes, B, cg, band, world):
+    """The rectangles a rank copies to the shared host matrix (engine.host_pieces) are exactly the
+    entries its tiles write (pair (i, j), its mirror and the diagonal), every entry of the matrix is
+    owned by exactly one rank, and a piece's rectangles are final once its tiles have run."""
+    from genevector_b200 import _lib
+    from genevector_b200.engine import host_pieces, tile_slice
+    lib = _lib.load()
+    gpb = 32 // B
+    op_rows = lib.gv_onehot_rows(n_genes, B)
+    tile_m = lib.gv_tile_m(cg)
+    owner = np.zeros((n_genes, n_genes), dtype=np.int32)
+    for rank in range(world):
+        tiles, _ = tile_slice(op_rows, cg, band, rank, world)
+        pieces = host_pieces(op_rows, cg, band, gpb, n_genes, rank, world, chunks=3)
+        assert not pieces or (pieces[0][0] == 0 and pieces[-1][1] == len(tiles))
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        written = np.zeros((n_genes, n_genes), dtype=bool)      # by the tiles run so far
+        copied = np.zeros((n_genes, n_genes), dtype=np.int32)
+        for t0, t1, rects in pieces:
+            for r0, c0 in tiles[t0:t1]:
+                gi = np.arange(r0 // 32 * gpb, min(n_genes, (r0 + tile_m) // 32 * gpb))
+                gj = np.arange(c0 // 32 * gpb, min(n_genes, (c0 + 256) // 32 * gpb))
+                I, J = np.meshgrid(gi, gj, indexing="ij")
+                m = I <= J
+                written[I[m], J[m]] = True
+                written[J[m], I[m]] = True
+            for r0, r1, c0, c1 in rects:
+                assert 0 <= r0 < r1 <= n_genes and 0 <= c0 < c1 <= n_genes
+                if world > 1:
+                    assert written[r0:r1, c0:c1].all(), "a rectangle is copied before its tiles ran"
+                copied[r0:r1, c0:c1] += 1
+        assert copied.max() <= 1, "a rank copies an entry twice"
+        if world > 1:
+            assert np.array_equal(copied.astype(bool), written), "rectangles != entries written by the tiles"
+        owner += copied
+    assert np.array_equal(owner, np.ones_like(owner)), "an entry of the matrix has zero or two owners"
 
 
 def test_block_layout_and_limbs():

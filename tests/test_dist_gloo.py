@@ -86,6 +86,39 @@ def _worker(rank, world, port, tmp):
         iu = np.triu_indices(n_genes, 1)
         assert np.all(t_owned.numpy()[iu] == 1), "a pair is owned by zero or two ranks"
         assert np.array_equal(t_part.numpy(), full)
+
+    # ---- result assembly without a collective: every rank writes the rectangles of its own tiles
+    # into the one shared host matrix (hostpool.py; not page-locked here: no CUDA on the CPU box)
+    from genevector_b200.hostpool import get_pool
+    pool = get_pool(cuda=False)
+    full32 = full.astype(np.float32)
+    G2 = 1500                                             # several bands and tile columns per rank
+    rng = np.random.default_rng(5)
+    big_full = rng.standard_normal((G2, G2)).astype(np.float32)
+    rows2 = lib.gv_onehot_rows(G2, B)
+    held = []
+    for it, (G, M, rows) in enumerate([(n_genes, full32, op_rows), (G2, big_full, rows2), (G2, big_full, rows2),
+                                       (n_genes, full32, op_rows)]):
+        seq, slot, mapping = pool.begin(G * G * 4)
+        dst = mapping.array(np.float32, (G, G))
+        if it != 2:
+            dst[:] = -7.0 if rank == 0 else dst             # stale contents must be overwritten
+        dist.barrier()                                      # (test only: rank 0's fill before the writes)
+        for _, _, rects in E.host_pieces(rows, 2, 8, gpb, G, rank, world, chunks=3):
+            for r0, r1, c0, c1 in rects:
+                dst[r0:r1, c0:c1] = M[r0:r1, c0:c1]
+        pool.finish(seq, slot)
+        got = pool.matrix(slot, G)
+        assert np.array_equal(got, M), f"rank {rank}: assembled matrix differs (call {it})"
+        if it == 1:
+            held.append((slot, got))                        # keep this result alive: its slot is not reused
+        elif it == 2:
+            assert slot != held[0][0], "a slot still referenced on some rank was handed out again"
+            assert np.array_equal(held[0][1], big_full)
+        del got, dst
+        dist.barrier()
+    assert not os.path.exists("/dev/shm" + pool.base + ".s0.g1"), "segment names are unlinked once mapped"
+    if rank == 0:
         open(os.path.join(tmp, "ok"), "w").write("ok")
     dist.destroy_process_group()
 

@@ -1,0 +1,136 @@
+"""GPU tests of the host runtime around the kernels: pageable upload, canonical-CSR check, result
+rectangles into one host matrix (the multi-rank assembly, ranks emulated one after another on one
+GPU), the public call's shared-matrix path under a real process group when several GPUs are visible."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_upload_pageable_is_byte_exact_while_the_stream_is_busy(engine):
+    """Several arrays of many staging chunks each, uploaded back to back while earlier DMAs still sit
+    behind queued GPU work: every staging slot is reused many times and must never be overwritten
+    before its DMA has read it."""
+    import torch
+    from genevector_b200 import _lib
+    rng = np.random.default_rng(0)
+    arrays = [rng.integers(0, 2 ** 63 - 1, size=n, dtype=np.int64) for n in (9_000_011, 5_000_003, 12_345_678)]
+    dev = engine.device
+    busy = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for threads in (1, 3, 8):
+            outs = []
+            for _ in range(20):
+                busy.mul_(1.0001)                          # keeps the stream busy: DMAs queue up behind it
+            for a in arrays:
+                d = torch.empty(a.shape, dtype=torch.int64, device=dev)
+                _lib.call("gv_upload_pageable", d.data_ptr(), a.ctypes.data, a.nbytes, threads, st)
+                outs.append(d)
+            torch.cuda.synchronize(dev)
+            for a, d in zip(arrays, outs):
+                assert np.array_equal(d.cpu().numpy(), a), f"upload with {threads} threads corrupted the data"
+
+
+def test_csr_check_finds_unsorted_duplicate_and_out_of_range(engine):
+    import scipy.sparse as sp
+    import torch
+    from genevector_b200 import _lib
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(400, 60, seed=1)
+    dev = engine.device
+
+    def check(indices, indptr, n_genes=60):
+        with torch.cuda.device(dev):
+            c = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(dev)
+            p = torch.from_numpy(np.ascontiguousarray(indptr, dtype=np.int64)).to(dev)
+            ok = np.zeros(1, dtype=np.int32)
+            scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.call("gv_csr_check", c.data_ptr(), p.data_ptr(), len(indptr) - 1, n_genes, scratch.data_ptr(),
+                      ok.ctypes.data, torch.cuda.current_stream(dev).cuda_stream)
+            return int(ok[0])
+
+    assert check(X.indices, X.indptr) == 0
+    row = int(np.flatnonzero(np.diff(X.indptr) >= 2)[0])
+    e = X.indptr[row]
+    swapped, sdata = X.indices.copy(), X.data.copy()
+    swapped[e], swapped[e + 1] = swapped[e + 1], swapped[e]
+    sdata[e], sdata[e + 1] = sdata[e + 1], sdata[e]              # the same matrix, one row unsorted
+    assert check(swapped, X.indptr) == 1
+    dup = X.indices.copy()
+    dup[e + 1] = dup[e]
+    assert check(dup, X.indptr) == 1
+    oob = X.indices.copy()
+    oob[e] = 60
+    assert check(oob, X.indptr) == 2
+    # the public path repairs case 1 on the host and refuses case 2
+    from genevector_b200.metrics import discretize_genes
+    Xs = sp.csr_matrix((sdata, swapped, X.indptr.copy()), shape=X.shape)
+    got, nb = discretize_genes(Xs, 10)
+    want, nb_w = discretize_genes(X, 10)
+    assert np.array_equal(got, want) and np.array_equal(nb, nb_w)
+    Xo = sp.csr_matrix(X.shape, dtype=np.float32)
+    Xo.data, Xo.indices, Xo.indptr = X.data.copy(), oob, X.indptr.copy()
+    with pytest.raises(ValueError):
+        engine.upload_csr(Xo)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("target", ["signed_mi", "pearson"])
+def test_rank_rectangles_assemble_the_single_rank_matrix_bit_for_bit(engine, world, target):
+    """Every emulated rank streams the rectangles of its own tiles into ONE host matrix (what the
+    shared host matrix is under a process group); the result equals the single-rank matrix bit for
+    bit and nothing is left untouched."""
+    import torch
+    from genevector_b200 import _lib
+    from genevector_b200.engine import HostSink
+    from genevector_b200.synth import synth_counts
+    n_cells, n_genes = 1200, 2100
+    X = synth_counts(n_cells, n_genes, seed=33)
+    csr = engine.upload_csr(X)
+    host = torch.full((n_genes, n_genes), float("nan"), dtype=torch.float32).pin_memory()
+    if target == "signed_mi":
+        full = engine.mi_from_csr(csr, n_cells, n_genes, signed=True)
+    else:
+        full = engine.target_from_csr(csr, _lib.GV_MOM_PEARSON)
+    for rank in range(world):
+        sink = HostSink(ptr=host.data_ptr(), pitch=n_genes * 4)
+        if target == "signed_mi":
+            engine.mi_from_csr(csr, n_cells, n_genes, signed=True, rank=rank, world=world, sink=sink)
+        else:
+            engine.target_from_csr(csr, _lib.GV_MOM_PEARSON, rank=rank, world=world, sink=sink)
+    torch.cuda.synchronize()
+    assert np.array_equal(host.numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
+
+
+def test_public_call_reuses_its_pinned_result_buffers(engine):
+    """compute_mi_b200 twice: results are independent objects (the first stays valid after the second)."""
+    from genevector_b200.metrics import compute_mi_b200
+    from genevector_b200.synth import synth_counts, gene_names
+    Xa, Xb = synth_counts(600, 300, seed=1), synth_counts(600, 300, seed=2)
+    genes = gene_names(300)
+    a = compute_mi_b200(Xa, genes, signed=True)
+    a_copy = a.matrix.copy()
+    b = compute_mi_b200(Xb, genes, signed=True)
+    assert np.array_equal(a.matrix, a_copy) and not np.array_equal(a.matrix, b.matrix)
+
+
+def test_sharded_public_calls_on_all_visible_gpus():
+    """The real thing: one process per visible GPU (torch.distributed.run, NCCL), signed MI / Pearson /
+    Spearman through the public calls, every rank's full matrix compared bitwise with the single-rank
+    result (tools/dist_check.py).  Skipped on a one-GPU box."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731",
+                        os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "DIST CHECK OK" in r.stdout
