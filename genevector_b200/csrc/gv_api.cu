@@ -128,6 +128,54 @@ int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells
                             static_cast<cudaStream_t>(stream));
 }
 
+int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,
+                       int64_t n_cells_local, int n_genes, int64_t blk_begin, int64_t blk_end,
+                       void* const* raw_dests_host, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
+                       void* flags_dev, uint64_t* data_flags_out_host, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!row_ptr_local || !raw_dests_host || !ghist_local || !flags_dev || !data_flags_out_host || n_genes <= 0 ||
+      n_cells_local < 0)
+    return set_error(GV_ERR_ARG, "gv_shard_transpose: bad argument");
+  for (int p = 0; p < n_dests && p < 8; ++p)
+    if (!raw_dests_host[p]) return set_error(GV_ERR_ARG, "gv_shard_transpose: null destination");
+  if (n_cells_local > (blk_end - blk_begin) * 128)
+    return set_error(GV_ERR_ARG, "gv_shard_transpose: more local cells than the block range holds");
+  unsigned long long hf[2] = {0, 0};
+  rc = shard_transpose_dispatch(values, value_dtype, col_idx, row_ptr_local, n_cells_local, n_genes, blk_begin,
+                                blk_end, raw_dests_host, n_dests, raw_pitch, ghist_local,
+                                static_cast<unsigned long long*>(flags_dev), hf, static_cast<cudaStream_t>(stream));
+  data_flags_out_host[0] = hf[0];
+  data_flags_out_host[1] = hf[1];
+  return rc;
+}
+
+int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, const double* q_table_host,
+                  const void* raw, const void* const* hists_host, int n_hists, uint32_t* ghist_total,
+                  double* qtab_dev, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,
+                  int32_t* marg, double* edges, int64_t* gsum, int64_t* gsq, int value_rows,
+                  int64_t val_rows_alloc, int val_limb_bits, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!q_table_host || !raw || !hists_host || !ghist_total || !qtab_dev || !bins_packed || !n_bins_per_gene ||
+      !marg || !edges || !gsum || !gsq || n_genes <= 0 || n_cells < 0)
+    return set_error(GV_ERR_ARG, "gv_shard_bins: bad argument");
+  if (bins_pitch_bytes % 64 != 0 || bins_pitch_bytes * 2 < n_cells)
+    return set_error(GV_ERR_ARG, "gv_shard_bins: bins pitch must be a multiple of 64 bytes covering n_cells/2");
+  DiscretizeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.value_dtype = value_dtype; a.n_cells = n_cells; a.n_genes = n_genes; a.n_bins = n_bins;
+  a.q_table = q_table_host; a.bins_packed = bins_packed; a.bins_pitch_bytes = bins_pitch_bytes;
+  a.n_bins_per_gene = n_bins_per_gene; a.marg = marg; a.edges = edges; a.gsum = gsum; a.gsq = gsq;
+  a.val_rows = value_rows ? const_cast<void*>(raw) : nullptr;
+  a.val_pitch = bins_pitch_bytes * 2; a.val_rows_alloc = val_rows_alloc; a.val_mode = 0; a.val_limbs = 1;
+  a.val_limb_bits = val_limb_bits;
+  if (value_rows && val_rows_alloc < gv_value_rows(n_genes, 1))
+    return set_error(GV_ERR_ARG, "gv_shard_bins: val_rows_alloc < gv_value_rows(n_genes, 1)");
+  return shard_bins_dispatch(a, static_cast<const uint8_t*>(raw), reinterpret_cast<const uint32_t* const*>(hists_host),
+                             n_hists, ghist_total, qtab_dev, static_cast<cudaStream_t>(stream));
+}
+
 int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
                     const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int n_genes,
                     double* entropy_out, void* workspace, size_t workspace_bytes, void* stream) {

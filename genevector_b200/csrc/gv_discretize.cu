@@ -728,11 +728,22 @@ constexpr size_t TP_TILE_BYTES = size_t(TP_GR) * TP_STRIDE;
 constexpr size_t TP_HIST_BYTES = size_t(TP_GR) * TP_HV;   // one byte per (gene, value): <= 128 cells
 constexpr size_t TP_SMEM = TP_TILE_BYTES + TP_HIST_BYTES + 2 * TP_CB * sizeof(int64_t);
 
+// Destinations of the dense rows: this GPU's own buffer and, for the sharded front end, the same
+// buffer of every peer GPU of the box (peer-mapped device memory: the stores travel over NVLink /
+// NVSwitch, so the transposition of a rank's block of cells IS its part of the all-gather).
+constexpr int TP_MAX_PEERS = 8;
+struct RawDests {
+  uint8_t* raw[TP_MAX_PEERS];
+  int n;
+};
+
+// row_ptr / n_cells describe the CSR rows this launch owns (all of them, or a rank's block of cells);
+// blk_offset is the index of its first 128-cell block in the whole matrix (column offset in `raw`).
 template <typename T>
 __global__ void __launch_bounds__(TP_THREADS, 2)
 k_transpose_counts(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
                    const int64_t* __restrict__ row_ptr, int64_t n_cells, int G,
-                   uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t n_blocks,
+                   const RawDests dests, int64_t raw_pitch, int64_t n_blocks, int64_t blk_offset,
                    uint32_t* __restrict__ ghist, unsigned long long* __restrict__ flags) {
   // ghist [G][256]: per-gene value histogram, accumulated on the way (small values in packed byte
   // counters in shared memory, flushed once per (cell block, gene range); the rest directly)
@@ -817,7 +828,8 @@ k_transpose_counts(const T* __restrict__ values, const int32_t* __restrict__ col
         uint32_t* w = reinterpret_cast<uint32_t*>(tile + gl * TP_STRIDE) + lane;
         const uint32_t x = *w;
         *w = 0u;
-        *reinterpret_cast<uint32_t*>(raw + int64_t(g0 + gl) * raw_pitch + c0 + 4 * lane) = x;
+        const int64_t o = int64_t(g0 + gl) * raw_pitch + (blk_offset * TP_CB + c0) + 4 * lane;
+        for (int p = 0; p < dests.n; ++p) *reinterpret_cast<uint32_t*>(dests.raw[p] + o) = x;
       }
       // ---- flush the packed byte counters of this (cell block, gene range)
       for (int gl = tid; gl < g1 - g0; gl += TP_THREADS) {
@@ -1274,8 +1286,11 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
     const int64_t n_blocks = kcells / TP_CB;
     const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
-    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, G, raw,
-                                                     kcells, n_blocks, ghist, flags);
+    RawDests dests;
+    dests.n = 1;
+    dests.raw[0] = raw;
+    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, G, dests,
+                                                     kcells, n_blocks, 0, ghist, flags);
     GV_LAUNCH_CHECK();
     GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
     GV_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1582,6 +1597,108 @@ int csr_check_dispatch(const int32_t* col_idx, const int64_t* row_ptr, int64_t n
   GV_CUDA_TRY(cudaMemcpyAsync(result_host, scratch_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   GV_CUDA_TRY(cudaStreamSynchronize(st));
   return GV_OK;
+}
+
+// ================================================================ sharded front end
+// One process per GPU: every rank owns a contiguous run of 128-cell blocks of the matrix, uploads
+// only those CSR rows over its own PCIe link and transposes them into the dense rows of EVERY rank
+// (shard_transpose_dispatch: k_transpose_counts with peer destinations).  After a host hand-shake all
+// ranks hold the same dense rows; each sums the ranks' partial value histograms (k_sum_hists, peer
+// loads) and bins all genes locally (shard_bins_dispatch: k_rows_to_bins), so the bin block is
+// replicated without a broadcast.
+struct HistSrcs {
+  const uint32_t* h[TP_MAX_PEERS];
+  int n;
+};
+__global__ void k_sum_hists(const HistSrcs srcs, int64_t n_words, uint32_t* __restrict__ total) {
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n_words;
+       i += int64_t(gridDim.x) * blockDim.x * 4) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    for (int p = 0; p < srcs.n; ++p) {
+      const uint4 v = *reinterpret_cast<const uint4*>(srcs.h[p] + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<uint4*>(total + i) = acc;
+  }
+}
+
+template <typename T>
+static int shard_transpose_impl(const void* values_v, const int32_t* col_idx, const int64_t* row_ptr,
+                                int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
+                                void* const* raw_dests, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
+                                unsigned long long* flags_dev, unsigned long long* flags_host, cudaStream_t st) {
+  const T* values = static_cast<const T*>(values_v);
+  RawDests dests;
+  dests.n = n_dests;
+  for (int p = 0; p < n_dests; ++p) dests.raw[p] = static_cast<uint8_t*>(raw_dests[p]);
+  GV_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 64, st));
+  GV_CUDA_TRY(cudaMemsetAsync(ghist_local, 0, size_t(G) * VH * 4, st));
+  const int64_t n_blocks = blk_end - blk_begin;
+  if (n_blocks > 0) {
+    auto kt = k_transpose_counts<T>;
+    GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
+    const int sms = device_sm_count();
+    const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
+    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, row_ptr, n_cells_local, G, dests, raw_pitch,
+                                                     n_blocks, blk_begin, ghist_local, flags_dev);
+    GV_LAUNCH_CHECK();
+  }
+  GV_CUDA_TRY(cudaMemcpyAsync(flags_host, flags_dev, 16, cudaMemcpyDeviceToHost, st));
+  GV_CUDA_TRY(cudaStreamSynchronize(st));      // the peer stores are complete when the kernel is
+  return GV_OK;
+}
+
+int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr,
+                             int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
+                             void* const* raw_dests, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
+                             unsigned long long* flags_dev, unsigned long long* flags_host, cudaStream_t st) {
+  if (n_dests < 1 || n_dests > TP_MAX_PEERS) return set_error(GV_ERR_ARG, "shard transpose: 1..8 destinations");
+  if (raw_pitch % TP_CB != 0 || blk_begin < 0 || blk_end < blk_begin || blk_end * TP_CB > raw_pitch)
+    return set_error(GV_ERR_ARG, "shard transpose: cell blocks outside the dense rows");
+  if (value_dtype == GV_F32)
+    return shard_transpose_impl<float>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
+                                       n_dests, raw_pitch, ghist_local, flags_dev, flags_host, st);
+  if (value_dtype == GV_F64)
+    return shard_transpose_impl<double>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
+                                        n_dests, raw_pitch, ghist_local, flags_dev, flags_host, st);
+  return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
+}
+
+template <typename T>
+static int shard_bins_impl(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
+                           uint32_t* ghist_total, double* qtab_dev, cudaStream_t st) {
+  const int G = a.n_genes;
+  const int sms = device_sm_count();
+  const int64_t kcells = a.bins_pitch_bytes * 2;
+  int8_t* val_rows = static_cast<int8_t*>(a.val_rows);
+  HistSrcs srcs;
+  srcs.n = n_hists;
+  for (int p = 0; p < n_hists; ++p) srcs.h[p] = hists[p];
+  GV_CUDA_TRY(cudaMemcpyAsync(qtab_dev, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st));
+  k_sum_hists<<<sms * 4, 256, 0, st>>>(srcs, int64_t(G) * VH, ghist_total);
+  GV_LAUNCH_CHECK();
+  if (val_rows != nullptr && a.val_rows_alloc > G)
+    GV_CUDA_TRY(cudaMemsetAsync(val_rows + int64_t(G) * a.val_pitch, 0, size_t(a.val_rows_alloc - G) * a.val_pitch, st));
+  k_rows_to_bins<T><<<G < sms * 8 ? G : sms * 8, RB_THREADS, 0, st>>>(
+      raw, kcells, kcells, a.n_cells, G, a.n_bins, qtab_dev, static_cast<uint32_t*>(a.bins_packed),
+      int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
+      a.val_pitch, a.val_mode, a.val_limb_bits, 1, ghist_total);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
+// raw: this rank's complete dense rows [G][kcells] (== val_rows when value rows are wanted: count
+// digits, one per gene); hists: every rank's partial histogram (peer pointers).
+int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
+                        uint32_t* ghist_total, double* qtab_dev, cudaStream_t st) {
+  if (n_hists < 1 || n_hists > TP_MAX_PEERS) return set_error(GV_ERR_ARG, "shard bins: 1..8 histograms");
+  if (a.n_bins < 1 || a.n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
+  if (a.val_rows != nullptr && (a.val_mode != 0 || a.val_limbs != 1 || a.val_rows != raw ||
+                                a.val_pitch != a.bins_pitch_bytes * 2))
+    return set_error(GV_ERR_ARG, "shard bins: value rows must be the dense count rows themselves (one digit)");
+  if (a.value_dtype == GV_F32) return shard_bins_impl<float>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
+  if (a.value_dtype == GV_F64) return shard_bins_impl<double>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
+  return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {

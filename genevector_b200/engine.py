@@ -277,6 +277,23 @@ def broadcast_block(buf: torch.Tensor, total: int, group=None) -> torch.Tensor:
     return buf
 
 
+class _DevPtr:
+    """A device allocation made outside torch (gv_ipc_alloc), exposed through
+    __cuda_array_interface__ so that torch can view it without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerBlock:
+    """The bin block of one (n_cells, n_genes) shape in peer-mapped device memory: this rank's own
+    allocation plus the mappings of every other rank's (same layout), for the sharded front end."""
+
+    def __init__(self, own_ptr, total, ptrs, offsets, tensor):
+        self.own_ptr, self.total, self.ptrs, self.off, self.tensor = own_ptr, total, ptrs, offsets, tensor
+
+
 class HostSink:
     """Where a rank's result rectangles go on the host: a page-locked float32 matrix given as
     (address, bytes per row), as a pinned tensor, or as a callable returning a pinned tensor (called
@@ -858,17 +875,187 @@ class Engine:
         return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, out_host=out_host,
                               sink=sink)
 
+    # ------------------------------------------------------------------ sharded front end
+    # scratch words of hostpool (per rank): 0 handle epoch, 1..8 the 64-byte IPC handle, 9 idle epoch,
+    # 10 transposition-done epoch, 11 / 12 data flags, 13 peers-opened epoch * 2 + ok
     def resolve_front(self, front: str, world: int) -> str:
         """"broadcast" or "sharded" for this process group (see metrics.compute_mi_b200)."""
         if world <= 1 or front == "broadcast":
             return "broadcast"
         if front not in ("auto", "sharded"):
             raise ValueError(f"unknown front {front!r} (auto, broadcast or sharded)")
-        return "broadcast"
+        if getattr(self, "_shard_disabled", False) or world > 8:
+            return "broadcast"
+        env = os.environ.get("GV_FRONT", "")
+        if front == "auto" and env in ("broadcast", "sharded"):
+            return env
+        return "sharded"
+
+    def _peer_block(self, n_cells, n_genes, rank, world, pool):
+        """Allocate (once per shape) this rank's peer-visible block and map the other ranks'."""
+        import ctypes as C
+        if not hasattr(self, "_peer_blocks"):
+            self._peer_blocks, self._peer_epoch = {}, 0
+        key = (n_cells, n_genes, world)
+        if key in self._peer_blocks:
+            return self._peer_blocks[key]
+        if len(self._peer_blocks) >= 4:
+            return None
+        kp, pitch, lay, total1 = block_layout(n_cells, n_genes, 0, 1)
+        off = dict(lay)
+        cur = total1
+        for name, nbytes in (("ghist", n_genes * 256 * 4), ("ghist_total", n_genes * 256 * 4),
+                             ("flags", 256), ("qtab", 2048)):
+            off[name] = (cur, nbytes)
+            cur += _align(nbytes)
+        self._peer_epoch += 1
+        epoch = self._peer_epoch
+        own, ok = C.c_void_p(), 1
+        handle = (C.c_uint8 * 64)()
+        try:
+            with torch.cuda.device(self.device):
+                _lib.call("gv_ipc_alloc", cur, C.byref(own), handle)
+        except GvError:
+            ok = 0
+        words = np.frombuffer(bytes(handle), dtype=np.uint64)
+        for k in range(8):
+            pool.scratch_store(1 + k, int(words[k]))
+        pool.scratch_store(0, epoch * 2 + ok)
+        ptrs = [None] * world
+        for r in range(world):
+            _lib.call("gv_flag_wait_ge", pool.scratch_addr(r, 0), epoch * 2, pool.timeout_ms)
+            ok &= pool.scratch_load(r, 0) & 1
+        if ok:
+            for r in range(world):
+                if r == rank:
+                    ptrs[r] = own.value
+                    continue
+                h = np.array([pool.scratch_load(r, 1 + k) for k in range(8)], dtype=np.uint64).tobytes()
+                p = C.c_void_p()
+                try:
+                    with torch.cuda.device(self.device):
+                        _lib.call("gv_ipc_open", h, C.byref(p))
+                    ptrs[r] = p.value
+                except GvError:
+                    ok = 0
+                    break
+        pool.scratch_store(13, epoch * 2 + ok)
+        for r in range(world):
+            _lib.call("gv_flag_wait_ge", pool.scratch_addr(r, 13), epoch * 2, pool.timeout_ms)
+            ok &= pool.scratch_load(r, 13) & 1
+        if not ok:
+            # some rank cannot allocate or map peer memory: every rank drops the sharded front end
+            self._shard_disabled = True
+            self._peer_blocks[key] = None
+            return None
+        tensor = torch.as_tensor(_DevPtr(own.value, cur), device=self.device)
+        pb = PeerBlock(own.value, cur, ptrs, off, tensor)
+        self._peer_blocks[key] = pb
+        return pb
+
+    def _shard_front(self, csr_local, blk_range, n_cells, n_genes, n_bins, signed, rank, world, pool):
+        """Sharded discretisation: returns the BinBlock (views into this rank's peer block), or None
+        when the data do not qualify (every rank decides the same from the combined data flags)."""
+        import ctypes as C
+        if not 1 <= n_bins <= 15:
+            raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
+        pb = self._peer_block(n_cells, n_genes, rank, world, pool)
+        if pb is None:
+            return None
+        if not hasattr(self, "_front_seq"):
+            self._front_seq = 0
+        self._front_seq += 1
+        step = self._front_seq
+        kp, pitch, lay, _ = block_layout(n_cells, n_genes, 0, 1)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            # nobody may still be reading what this step overwrites (peers' dense rows, my histogram)
+            stream.synchronize()
+            pool.scratch_store(9, step)
+            pool.scratch_wait_all(9, step)
+            ev = None
+            if self.kernel_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record(stream)
+            dests = (C.c_void_p * world)(*[p + pb.off["val"][0] for p in pb.ptrs])
+            flags = np.zeros(2, dtype=np.uint64)
+            dt = _lib.GV_F32 if csr_local.values.dtype == torch.float32 else _lib.GV_F64
+            _lib.call("gv_shard_transpose", csr_local.values.data_ptr(), dt, csr_local.col_idx.data_ptr(),
+                      csr_local.row_ptr.data_ptr(), csr_local.n_cells, n_genes, blk_range[0], blk_range[1],
+                      dests, world, kp, pb.own_ptr + pb.off["ghist"][0], pb.own_ptr + pb.off["flags"][0],
+                      flags.ctypes.data, stream.cuda_stream)
+            pool.scratch_store(11, int(flags[0]))
+            pool.scratch_store(12, int(flags[1]))
+            pool.scratch_store(10, step)
+            pool.scratch_wait_all(10, step)
+            f0 = f1 = 0
+            for r in range(world):
+                f0 |= pool.scratch_load(r, 11)
+                f1 = max(f1, pool.scratch_load(r, 12))
+            if ev is not None:
+                ev[1].record(stream)
+                self.kernel_events.append(("gv_shard_transpose (+ peer stores)", ev[0], ev[1], 1))
+            # signed MI: the dense count rows are the one-digit INT8 operand of the sign pass
+            lb = limb_bits_for(max(n_cells, 1)) if signed else 7
+            limit = ((1 << lb) - 1) if signed else 255
+            if (f0 & 14) or (signed and (f0 & 1)) or f1 > limit:
+                return None
+            hists = (C.c_void_p * world)(*[p + pb.off["ghist"][0] for p in pb.ptrs])
+            val_mode = 0 if signed else -1
+            blk = _views(pb.tensor, n_cells, n_genes, n_bins, val_mode, 1, lb, (f0, f1))
+            q = quantile_table()
+            vrows = value_rows(n_genes, 1)
+            self._call("gv_shard_bins", dt, n_cells, n_genes, n_bins, q.ctypes.data,
+                       pb.own_ptr + pb.off["val"][0], hists, world, pb.own_ptr + pb.off["ghist_total"][0],
+                       pb.own_ptr + pb.off["qtab"][0], blk.bins.data_ptr(), pitch, blk.n_bins_per_gene.data_ptr(),
+                       blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(), blk.gsq.data_ptr(),
+                       1 if signed else 0, vrows, lb, stream.cuda_stream)
+            blk.path_used = _lib.GV_PATH_COUNTS
+            return blk
+
+    @staticmethod
+    def shard_cells(n_cells, rank, world):
+        """(first block, end block, first cell, end cell) of a rank: contiguous runs of 128-cell blocks of
+        the padded cell axis."""
+        kp = _align(max(n_cells, 1), 256)
+        blocks = kp // 128
+        b0, b1 = blocks * rank // world, blocks * (rank + 1) // world
+        return b0, b1, min(n_cells, b0 * 128), min(n_cells, b1 * 128)
+
+    def _mi_after_front(self, blk, signed, rank, world, out, sink, sign_rule):
+        B = _lib.call("gv_rows_per_gene", blk.n_bins)
+        onehot, B = self.expand_onehot(blk)
+        sgn = None
+        if signed:
+            st = None
+            if world > 1:
+                rows = _lib.check("gv_onehot_rows", self.lib.gv_onehot_rows(blk.n_genes, B))
+                key = ("sign", rows, self.cta_group, self.band, rank, world, blk.n_limbs)
+                if key not in self._sched_cache:
+                    mine, _ = tile_slice(rows, self.cta_group, self.band, rank, world)
+                    self._sched_cache[key] = self.sign_tiles_for(mine, B, blk.n_limbs)
+                st = self._sched_cache[key]
+            sgn = self.sign_matrix(blk, tiles=st, rule=sign_rule)
+        return self.mi_scores(blk, onehot, B, sgn=sgn, out=out, rank=rank, world=world, sink=sink)
 
     def mi_device_step(self, csr, n_cells, n_genes, n_bins=10, signed=False, rank=0, world=1, out=None,
                        front="broadcast"):
-        """One pass of the hot path with the input already resident in HBM (bench.py's `value` leg)."""
+        """One pass of the hot path with the input already resident in HBM (bench.py's `value` leg).
+        `csr` is the whole matrix on this rank's device; the sharded front end uses this rank's block
+        of cells of it."""
+        if front == "sharded" and world > 1:
+            from .hostpool import get_pool
+            pool = get_pool()
+            b0, b1, r0, r1 = self.shard_cells(n_cells, rank, world)
+            key = ("slice", csr.values.data_ptr(), rank, world)
+            if key not in self._sched_cache:
+                e0, e1 = int(csr.row_ptr[r0]), int(csr.row_ptr[r1])
+                self._sched_cache[key] = CsrDevice(csr.values[e0:e1], csr.col_idx[e0:e1],
+                                                   (csr.row_ptr[r0:r1 + 1] - e0).contiguous(), r1 - r0, n_genes)
+            blk = self._shard_front(self._sched_cache[key], (b0, b1), n_cells, n_genes, n_bins, signed, rank,
+                                    world, pool)
+            if blk is not None:
+                return self._mi_after_front(blk, signed, rank, world, out, None, "numpy")
         return self.mi_from_csr(csr if rank == 0 else None, n_cells, n_genes, n_bins=n_bins, signed=signed,
                                 rank=rank, world=world, out=out)
 
@@ -880,12 +1067,27 @@ class Engine:
 
     def mi_from_host_sharded(self, X, n_bins=10, signed=False, rank=0, world=1, sign_rule="numpy",
                              sink=None, required=False) -> bool:
-        """Sharded front end (every rank uploads and transposes its own block of cells, peer stores
-        replicate the dense count rows): see DESIGN.md section 5.  Returns False when the data do not
-        qualify and the caller should take the broadcast path."""
-        if required:
-            raise GvError("mi_from_host_sharded", -4, "the sharded front end is not available")
-        return False
+        """Sharded front end from a host scipy CSR: every rank uploads its own block of cells over its
+        own PCIe link, transposes it into every rank's dense rows over NVLink (peer stores) and bins
+        all genes locally; no NCCL call.  Returns False when the data do not qualify (not count data
+        <= 127 / 255, peer memory unavailable): the caller then takes the broadcast path."""
+        from .hostpool import get_pool
+        if self.resolve_front("sharded" if required else "auto", world) != "sharded":
+            if required:
+                raise GvError("mi_from_host_sharded", -4, "the sharded front end is not available here")
+            return False
+        pool = get_pool()
+        n_cells, n_genes = X.shape
+        b0, b1, r0, r1 = self.shard_cells(n_cells, rank, world)
+        csr_local = self.upload_csr(X, rows=(r0, r1))
+        blk = self._shard_front(csr_local, (b0, b1), n_cells, n_genes, n_bins, signed, rank, world, pool)
+        if blk is None:
+            if required:
+                raise GvError("mi_from_host_sharded", -4, "the data do not qualify for the sharded front end "
+                              "(count data <= 127 signed / 255 unsigned in canonical CSR)")
+            return False
+        self._mi_after_front(blk, signed, rank, world, None, sink, sign_rule)
+        return True
 
     def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,
                         n_cells: Optional[int] = None, n_genes: Optional[int] = None,

@@ -136,6 +136,34 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
 int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int n_genes,
                  int* scratch_dev, int* result_host, void* stream);
 
+/* ---------------------------------------------------------------- sharded discretisation front end
+ * One process per GPU of one box; count data (integers <= 255, canonical CSR).  Instead of rank 0
+ * discretising everything and broadcasting the result, every rank uploads only its own run of 128-cell
+ * blocks [blk_begin, blk_end) of the matrix (row_ptr_local: the n_cells_local + 1 row pointers of those
+ * cells, starting at 0) and gv_shard_transpose writes their dense uint8 rows raw[gene][cell] into the
+ * `raw` buffer of EVERY rank: raw_dests_host holds n_dests device pointers (own buffer and the
+ * gv_ipc_open mappings of the peers'; the stores cross NVLink), each [n_genes][raw_pitch], raw_pitch =
+ * padded cell count (% 256 == 0).  The block ranges of the ranks must tile [0, raw_pitch / 128).
+ * ghist_local (uint32 [n_genes][256]) receives this rank's part of the per-gene value histogram;
+ * flags_dev: 64 bytes of device scratch; data_flags_out_host as gv_discretize_csr (the caller combines
+ * them over the ranks: OR of [0], max of [1]).  Synchronous: when it returns, this rank's stores have
+ * landed in every destination.
+ * After every rank has returned from it (host hand-shake, gv_flag_*), gv_shard_bins sums the ranks'
+ * histograms (hists_host: n_hists device pointers, peers' via gv_ipc_open) into ghist_total and bins all
+ * genes from this rank's complete `raw`: the same outputs as gv_discretize_csr on the count path.
+ * value_rows = 1: `raw` itself is the one-digit INT8 value-row operand (needs every value <= 127 and
+ * val_rows_alloc = gv_value_rows(n_genes, 1) rows allocated; rows >= n_genes are zeroed).
+ * qtab_dev: 2 KB of device scratch. */
+int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,
+                       int64_t n_cells_local, int n_genes, int64_t blk_begin, int64_t blk_end,
+                       void* const* raw_dests_host, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
+                       void* flags_dev, uint64_t* data_flags_out_host, void* stream);
+int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, const double* q_table_host,
+                  const void* raw, const void* const* hists_host, int n_hists, uint32_t* ghist_total,
+                  double* qtab_dev, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,
+                  int32_t* marg, double* edges, int64_t* gsum, int64_t* gsq, int value_rows,
+                  int64_t val_rows_alloc, int val_limb_bits, void* stream);
+
 /* ---------------------------------------------------------------- gene entropy
  * Replaces GeneVectorDataset.get_gene_entropy (data.py:186-203), which runs before every score
  * computation (data.py:349): per gene the entropy (nats) of the counts of its unique values after

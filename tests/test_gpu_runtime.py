@@ -109,6 +109,71 @@ def test_rank_rectangles_assemble_the_single_rank_matrix_bit_for_bit(engine, wor
     assert np.array_equal(host.numpy().view(np.uint32), full.cpu().numpy().view(np.uint32))
 
 
+@pytest.mark.parametrize("world,signed", [(2, True), (3, False), (8, True)])
+def test_sharded_front_end_kernels_reproduce_the_bin_block(engine, world, signed):
+    """gv_shard_transpose / gv_shard_bins with the ranks emulated one after another on one GPU (the
+    "peer" buffers are plain buffers of this device): every rank's dense rows, bins, marginals, edges
+    and sums equal what gv_discretize_csr produces from the whole matrix."""
+    import ctypes as C
+    import torch
+    from genevector_b200 import _lib
+    from genevector_b200.engine import Engine, CsrDevice, block_layout, quantile_table, value_rows, limb_bits_for
+    from genevector_b200.synth import synth_counts
+    n_cells, n_genes, n_bins = 2999, 777, 10
+    X = synth_counts(n_cells, n_genes, seed=44)
+    csr = engine.upload_csr(X)
+    want = engine.discretize(csr, n_bins, 0 if signed else -1)
+    dev = engine.device
+    kp, pitch, lay, total = block_layout(n_cells, n_genes, 0, 1)
+    vrows = value_rows(n_genes, 1)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        raws = [torch.full((vrows, kp), 0x55, dtype=torch.uint8, device=dev) for _ in range(world)]
+        hists = [torch.empty((n_genes, 256), dtype=torch.int32, device=dev) for _ in range(world)]
+        fl = torch.zeros(64, dtype=torch.uint8, device=dev)
+        dests = (C.c_void_p * world)(*[r.data_ptr() for r in raws])
+        f0 = f1 = 0
+        for rank in range(world):
+            b0, b1, r0, r1 = Engine.shard_cells(n_cells, rank, world)
+            e0, e1 = int(csr.row_ptr[r0]), int(csr.row_ptr[r1])
+            loc = CsrDevice(csr.values[e0:e1], csr.col_idx[e0:e1], (csr.row_ptr[r0:r1 + 1] - e0).contiguous(),
+                            r1 - r0, n_genes)
+            flags = np.zeros(2, dtype=np.uint64)
+            _lib.call("gv_shard_transpose", loc.values.data_ptr(), _lib.GV_F32, loc.col_idx.data_ptr(),
+                      loc.row_ptr.data_ptr(), loc.n_cells, n_genes, b0, b1, dests, world, kp,
+                      hists[rank].data_ptr(), fl.data_ptr(), flags.ctypes.data, st)
+            f0 |= int(flags[0])
+            f1 = max(f1, int(flags[1]))
+        assert f0 == 0 and f1 == int(X.data.max())
+        hp = (C.c_void_p * world)(*[h.data_ptr() for h in hists])
+        lb = limb_bits_for(n_cells)
+        q = quantile_table()
+        for rank in range(world):
+            bins = torch.empty((n_genes, pitch), dtype=torch.uint8, device=dev)
+            nbpg = torch.empty(n_genes, dtype=torch.int32, device=dev)
+            marg = torch.empty((n_genes, 16), dtype=torch.int32, device=dev)
+            edges = torch.empty((n_genes, 16), dtype=torch.float64, device=dev)
+            gsum = torch.empty(n_genes, dtype=torch.int64, device=dev)
+            gsq = torch.empty_like(gsum)
+            tot = torch.empty((n_genes, 256), dtype=torch.int32, device=dev)
+            qd = torch.empty(2048, dtype=torch.uint8, device=dev)
+            _lib.call("gv_shard_bins", _lib.GV_F32, n_cells, n_genes, n_bins, q.ctypes.data, raws[rank].data_ptr(),
+                      hp, world, tot.data_ptr(), qd.data_ptr(), bins.data_ptr(), pitch, nbpg.data_ptr(),
+                      marg.data_ptr(), edges.data_ptr(), gsum.data_ptr(), gsq.data_ptr(), 1 if signed else 0,
+                      vrows, lb, st)
+            torch.cuda.synchronize(dev)
+            assert torch.equal(bins, want.bins), f"rank {rank}: packed bins differ"
+            assert torch.equal(nbpg, want.n_bins_per_gene) and torch.equal(marg, want.marg)
+            assert torch.equal(edges.view(torch.int64), want.edges.view(torch.int64))
+            assert torch.equal(gsum, want.gsum) and torch.equal(gsq, want.gsq)
+            if signed:
+                assert torch.equal(raws[rank].view(torch.int8), want.val_rows), f"rank {rank}: dense rows differ"
+            else:
+                dense = torch.from_numpy(np.asarray(X.todense()).T.astype(np.uint8)).to(dev)
+                assert torch.equal(raws[rank][:n_genes, :n_cells], dense)
+                assert not raws[rank][:n_genes, n_cells:].any()
+
+
 def test_public_call_reuses_its_pinned_result_buffers(engine):
     """compute_mi_b200 twice: results are independent objects (the first stays valid after the second)."""
     from genevector_b200.metrics import compute_mi_b200
@@ -132,5 +197,8 @@ def test_sharded_public_calls_on_all_visible_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29731",
                         os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_world{n}.log"), "w") as f:
+        f.write(r.stdout + "\n---- stderr ----\n" + r.stderr[-20000:])
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "DIST CHECK OK" in r.stdout

@@ -30,7 +30,8 @@ def main():
     Xf.data = np.log1p(Xf.data * 0.37).astype(np.float32)          # non-count data: fixed-point rows
     genes = gene_names(G)
     eng = get_engine(dev)
-    fronts = ["broadcast"] + (["sharded"] if eng.resolve_front("sharded", world) == "sharded" else [])
+    # "auto" takes the sharded front end where the data qualify (counts) and the broadcast otherwise
+    fronts = ["broadcast", "auto"]
     calls = [(f"signed_mi[{f}]", (lambda M, f=f: compute_mi_b200(M, genes, signed=True, front=f))) for f in fronts]
     calls += [("mi_unsigned", lambda M: compute_mi_b200(M, genes, signed=False)),
               ("pearson", lambda M: target_pearson(M, genes)),

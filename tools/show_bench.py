@@ -14,3 +14,5 @@ for path in sys.argv[1:]:
           f"kernel_ms={r.get('kernel_ms')} TOPS={r.get('achieved')} frac={r.get('frac')} "
           f"nominal_frac={r.get('frac_of_nominal')} of_int8_nominal={r.get('frac_of_nominal_int8')} operand={d['config'].get('operand')}")
     print("   clocks:", d.get("clocks"), "phases:", d.get("phases_ms"), "cpu:", d.get("cpu_baseline"))
+    print("   host phases:", d["e2e"].get("host_phases_ms"), "parity:", d.get("parity_check"),
+          "parallelism:", d["config"].get("parallelism"))
