@@ -72,6 +72,8 @@ SIGNATURES = {
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),
     "gv_upload_pageable": (_i32, [_vp, _vp, _sz, _i32, _vp]),
+    "gv_upload_registered": (_i32, [_vp, _vp, _sz, _vp, C.POINTER(_vp)]),
+    "gv_upload_release": (_i32, [_vp]),
     "gv_runtime_shutdown": (_i32, []),
     "gv_shm_open": (_i32, [C.c_char_p, _sz, _i32, _i32, C.POINTER(_vp)]),
     "gv_shm_close": (_i32, [_vp, _sz, _i32, C.c_char_p]),

@@ -16,6 +16,8 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <immintrin.h>
+#include <cstdlib>
 #include <atomic>
 #include <cerrno>
 #include <chrono>
@@ -39,6 +41,31 @@ namespace gv {
 constexpr size_t UP_CHUNK = size_t(8) << 20;   // bytes per staging slot
 constexpr int UP_SLOTS_PER_THREAD = 2;
 constexpr int UP_MAX_THREADS = 16;
+
+// Copy into a staging slot with non-temporal stores: the slot is read next by the copy engine, not by
+// this core, so its lines need neither be fetched for ownership nor kept in the cache.  With every rank
+// of a box staging at once the copies are bound by host memory traffic; this removes a quarter of it.
+__attribute__((target("avx2"))) static void copy_stream_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t i = 0;
+  // dst is 4 KB aligned (pinned slot); src has any alignment
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  if (i < n) memcpy(dst + i, src + i, n - i);
+}
+static void copy_to_slot(uint8_t* dst, const uint8_t* src, size_t n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !(getenv("GV_STAGE_MEMCPY") && getenv("GV_STAGE_MEMCPY")[0] == '1');
+  if (avx2) copy_stream_avx2(dst, src, n);
+  else memcpy(dst, src, n);
+}
 
 struct UploadRing {
   std::mutex mu;                  // one upload at a time per process
@@ -111,7 +138,7 @@ int gv_upload_pageable(void* dst_dev, const void* src_host, size_t bytes, int n_
       const int s = w * UP_SLOTS_PER_THREAD + (use++ % UP_SLOTS_PER_THREAD);
       // the DMA that last read this slot (this call or an earlier one) must be done
       if (cudaEventSynchronize(g_ring.ev[s]) != cudaSuccess) { err.store(2); break; }
-      memcpy(g_ring.slot[s], static_cast<const uint8_t*>(src_host) + off, n);
+      copy_to_slot(g_ring.slot[s], static_cast<const uint8_t*>(src_host) + off, n);
       if (cudaMemcpyAsync(static_cast<uint8_t*>(dst_dev) + off, g_ring.slot[s], n, cudaMemcpyHostToDevice, st) !=
               cudaSuccess ||
           cudaEventRecord(g_ring.ev[s], st) != cudaSuccess) {
@@ -131,6 +158,83 @@ int gv_upload_pageable(void* dst_dev, const void* src_host, size_t bytes, int n_
                             : set_error(GV_ERR_CUDA, "gv_upload_pageable: a staging copy failed");
   }
   return GV_OK;
+}
+
+// ---------------------------------------------------------------- registered upload
+// The other way to read pageable memory at PCIe speed: page-lock the caller's pages in place
+// (cudaHostRegister), DMA straight out of them, unlock afterwards.  No CPU copy touches the data, so
+// it does not compete for host memory bandwidth -- what matters when the eight ranks of a box upload
+// their blocks of the matrix at the same time.  The range is registered in page-aligned chunks, each
+// chunk's DMA running under the registration of the next.
+struct RegToken {
+  std::vector<std::pair<void*, size_t>> ranges;
+  cudaEvent_t done = nullptr;
+};
+// chunk size of the registration (bytes); GV_REG_CHUNK_MB overrides (0 = the whole range in one call)
+static size_t reg_chunk_bytes() {
+  static const size_t v = [] {
+    const char* e = getenv("GV_REG_CHUNK_MB");
+    if (!e) return size_t(0);
+    return size_t(atol(e)) << 20;
+  }();
+  return v;
+}
+
+int gv_upload_registered(void* dst_dev, const void* src_host, size_t bytes, void* stream, void** token_out) {
+  if (!token_out) return set_error(GV_ERR_ARG, "gv_upload_registered: null token");
+  *token_out = nullptr;
+  if (bytes == 0) return GV_OK;
+  if (!dst_dev || !src_host) return set_error(GV_ERR_ARG, "gv_upload_registered: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t page = size_t(sysconf(_SC_PAGESIZE));
+  const uintptr_t begin = reinterpret_cast<uintptr_t>(src_host), end = begin + bytes;
+  RegToken* tok = new RegToken();
+  uintptr_t cur = begin;
+  int rc = GV_OK;
+  while (cur < end) {
+    const size_t chunk = reg_chunk_bytes();
+    uintptr_t nxt = chunk ? ((cur + chunk) / page) * page : end;      // chunk boundaries on page boundaries
+    if (nxt > end || nxt <= cur) nxt = end;
+    const uintptr_t p0 = (cur / page) * page, p1 = ((nxt + page - 1) / page) * page;
+    cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(p0), p1 - p0, cudaHostRegisterPortable);
+    if (e == cudaSuccess) {
+      tok->ranges.emplace_back(reinterpret_cast<void*>(p0), p1 - p0);
+    } else {
+      cudaGetLastError();      // e.g. a page shared with a range that is already registered: plain copy
+    }
+    e = cudaMemcpyAsync(static_cast<uint8_t*>(dst_dev) + (cur - begin), reinterpret_cast<const void*>(cur),
+                        nxt - cur, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = set_cuda_error(e, __FILE__, __LINE__); break; }
+    cur = nxt;
+  }
+  if (rc == GV_OK) {
+    cudaError_t e = cudaEventCreateWithFlags(&tok->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(tok->done, st);
+    if (e != cudaSuccess) rc = set_cuda_error(e, __FILE__, __LINE__);
+  }
+  if (rc != GV_OK) {
+    cudaStreamSynchronize(st);
+    for (auto& r : tok->ranges) cudaHostUnregister(r.first);
+    if (tok->done) cudaEventDestroy(tok->done);
+    delete tok;
+    return rc;
+  }
+  *token_out = tok;
+  return GV_OK;
+}
+
+int gv_upload_release(void* token) {
+  if (!token) return GV_OK;
+  RegToken* tok = static_cast<RegToken*>(token);
+  int rc = GV_OK;
+  if (tok->done) {
+    cudaError_t e = cudaEventSynchronize(tok->done);      // the DMAs have read the pages
+    if (e != cudaSuccess) rc = set_cuda_error(e, __FILE__, __LINE__);
+    cudaEventDestroy(tok->done);
+  }
+  for (auto& r : tok->ranges) cudaHostUnregister(r.first);
+  delete tok;
+  return rc;
 }
 
 int gv_runtime_shutdown(void) {

@@ -350,6 +350,13 @@ class Engine:
         # the host cores with its peers)
         lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
         self.copy_threads = int(os.environ.get("GV_COPY_THREADS", "0")) or max(2, min(8, (os.cpu_count() or 8) // max(lw, 1)))
+        # how pageable arrays are read: "staged" (worker threads copy into a pinned ring) or
+        # "registered" (the caller's pages are page-locked in place: no CPU pass over the data, which is
+        # what the ranks of a box want when they all upload at once)
+        self.upload_mode = os.environ.get("GV_UPLOAD_MODE", "") or "staged"
+        self._upload_tokens = []
+        # metrics._run_to_host sets this: registered pages are unlocked after the whole call is enqueued
+        self.defer_release = False
 
     # kernels launched by each entry point (memsets / copies not counted)
     _LAUNCHES = {"gv_discretize_csr": 2, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
@@ -427,8 +434,16 @@ class Engine:
             self._timed_host("upload_csr: views + device buffers", t_up)
             t_st = time.perf_counter()
             for dst, src in ((dv, data), (dc, cols), (dp, ptr)):
-                _lib.call("gv_upload_pageable", dst.data_ptr(), src.ctypes.data, src.nbytes, self.copy_threads, st)
-            self._timed_host("upload_csr: staging copies", t_st)
+                if self.upload_mode == "registered" and src.nbytes >= (32 << 20):
+                    import ctypes as C
+                    tok = C.c_void_p()
+                    _lib.call("gv_upload_registered", dst.data_ptr(), src.ctypes.data, src.nbytes, st, C.byref(tok))
+                    if tok.value:
+                        self._upload_tokens.append((tok.value, src))      # src stays alive until released
+                else:
+                    _lib.call("gv_upload_pageable", dst.data_ptr(), src.ctypes.data, src.nbytes,
+                              self.copy_threads, st)
+            self._timed_host("upload_csr: host side of the copies", t_st)
             csr = CsrDevice(dv, dc, dp, r1 - r0, n_genes)
             if known is not True:
                 ok = np.zeros(1, dtype=np.int32)
@@ -441,8 +456,17 @@ class Engine:
                     Xc.sum_duplicates()             # sorts the indices and merges duplicate entries
                     Xc._has_canonical_format = True
                     return self.upload_csr(Xc, rows=rows)
+        if not self.defer_release:
+            self.release_uploads()
         self._timed_host("upload_csr (host side: staging + canonical check)", t_up)
         return csr
+
+    def release_uploads(self):
+        """Unlock the pages of registered uploads (waits for their DMAs).  Called once the rest of a
+        call's work is enqueued, so the host does it while the device computes."""
+        toks, self._upload_tokens = self._upload_tokens, []
+        for tok, _src in toks:
+            _lib.call("gv_upload_release", tok)
 
     def schedule(self, op_rows: int, cta_group: Optional[int] = None, rank: int = 0, world: int = 1):
         """Device tile list (int32 [n,2]) for this rank: a contiguous slice of the band-ordered

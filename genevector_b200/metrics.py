@@ -84,10 +84,23 @@ def _run_to_host(eng, n_genes, gene_names, run, front=None):
     from .engine import HostSink
     rank, world = _dist_info()
     t0 = time.perf_counter()
+    eng.defer_release = True
+    try:
+        return _run_to_host_inner(eng, n_genes, gene_names, run, rank, world, t0)
+    finally:
+        eng.defer_release = False
+        eng.release_uploads()
+
+
+def _run_to_host_inner(eng, n_genes, gene_names, run, rank, world, t0):
+    import time
+    import torch
+    from .engine import HostSink
     if world == 1:
         run(HostSink(tensor=_pinned_result(n_genes)))
         eng._timed_host("enqueue (upload + launches + host buffer)", t0)
         t1 = time.perf_counter()
+        eng.release_uploads()
         torch.cuda.synchronize(eng.device)
         eng._timed_host("wait for the device", t1)
         host, eng.last_host_result = eng.last_host_result, None
@@ -101,9 +114,11 @@ def _run_to_host(eng, n_genes, gene_names, run, front=None):
         run(HostSink(ptr=mapping.ptr, pitch=n_genes * 4))
         eng._timed_host("enqueue (upload + launches)", t1)
         t2 = time.perf_counter()
+        eng.release_uploads()
         torch.cuda.synchronize(eng.device)
         eng._timed_host("wait for the device", t2)
     except BaseException:
+        eng.release_uploads()
         pool.release(slot, pool.slots[slot][0])
         raise
     t3 = time.perf_counter()

@@ -314,6 +314,12 @@ int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_gene
  *   timeout_ms (negative: wait forever).
  * gv_copy_rect_d2h: rows x width_bytes rectangle, device (pitch src_pitch_bytes) -> host. */
 int gv_upload_pageable(void* dst_dev, const void* src_host, size_t bytes, int n_threads, void* stream);
+/* The same copy without a CPU pass over the data: the caller's pages are page-locked in place
+ * (cudaHostRegister, in 64 MB chunks, each chunk's DMA running under the next chunk's registration) and
+ * read by the copy engine directly.  The source must stay untouched until gv_upload_release(*token_out),
+ * which waits for the copies and unlocks the pages (call it once the rest of the work is enqueued). */
+int gv_upload_registered(void* dst_dev, const void* src_host, size_t bytes, void* stream, void** token_out);
+int gv_upload_release(void* token);
 int gv_runtime_shutdown(void);
 int gv_shm_open(const char* name, size_t bytes, int create, int cuda_register, void** ptr_out_host);
 int gv_shm_close(void* ptr_host, size_t bytes, int cuda_registered, const char* unlink_name);
