@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cfloat>
+#include <cstdlib>
 #include "gv_internal.h"
 
 namespace gv {
@@ -1622,15 +1623,42 @@ __global__ void k_sum_hists(const HistSrcs srcs, int64_t n_words, uint32_t* __re
   }
 }
 
+// Side streams for the peer copies of the sharded front end (one per destination, per device).
+static cudaStream_t* peer_streams(int device) {
+  static cudaStream_t streams[16][TP_MAX_PEERS] = {};
+  static bool made[16] = {};
+  if (device < 0 || device >= 16) return nullptr;
+  if (!made[device]) {
+    for (int p = 0; p < TP_MAX_PEERS; ++p)
+      if (cudaStreamCreateWithFlags(&streams[device][p], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    made[device] = true;
+  }
+  return streams[device];
+}
+
+// own_index: which of raw_dests is this rank's own buffer.  The rank's block of cells is transposed into
+// its own dense rows; the slab [G][its cells] then goes to every peer.  Two ways (GV_SHARD_PUSH):
+//   "dma" (default)  one 2-D peer copy per destination on its own stream (copy engines over NVLink:
+//                    full-rate 25 KB rows, the SMs are free again after the 0.5 ms transposition)
+//   "stores"         the transposition kernel stores every 128-byte line to all destinations itself
+//                    (measured on 8 GPUs: 53 ms for 3.5 GB per GPU -- 4-byte peer stores from a
+//                    latency-bound kernel do not fill NVLink; kept for the comparison)
 template <typename T>
 static int shard_transpose_impl(const void* values_v, const int32_t* col_idx, const int64_t* row_ptr,
                                 int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
-                                void* const* raw_dests, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
-                                unsigned long long* flags_dev, unsigned long long* flags_host, cudaStream_t st) {
+                                void* const* raw_dests, int n_dests, int own_index, int64_t raw_pitch,
+                                uint32_t* ghist_local, unsigned long long* flags_dev,
+                                unsigned long long* flags_host, cudaStream_t st) {
   const T* values = static_cast<const T*>(values_v);
+  static const bool push_stores = getenv("GV_SHARD_PUSH") != nullptr && getenv("GV_SHARD_PUSH")[0] == 's';
   RawDests dests;
-  dests.n = n_dests;
-  for (int p = 0; p < n_dests; ++p) dests.raw[p] = static_cast<uint8_t*>(raw_dests[p]);
+  if (push_stores) {
+    dests.n = n_dests;
+    for (int p = 0; p < n_dests; ++p) dests.raw[p] = static_cast<uint8_t*>(raw_dests[p]);
+  } else {
+    dests.n = 1;
+    dests.raw[0] = static_cast<uint8_t*>(raw_dests[own_index]);
+  }
   GV_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 64, st));
   GV_CUDA_TRY(cudaMemsetAsync(ghist_local, 0, size_t(G) * VH * 4, st));
   const int64_t n_blocks = blk_end - blk_begin;
@@ -1642,25 +1670,51 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx, co
     kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, row_ptr, n_cells_local, G, dests, raw_pitch,
                                                      n_blocks, blk_begin, ghist_local, flags_dev);
     GV_LAUNCH_CHECK();
+    if (!push_stores && n_dests > 1) {
+      int device = 0;
+      GV_CUDA_TRY(cudaGetDevice(&device));
+      cudaStream_t* ps = peer_streams(device);
+      if (!ps) return set_error(GV_ERR_CUDA, "shard transpose: could not create the peer copy streams");
+      cudaEvent_t ready, done;
+      GV_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+      GV_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      cudaError_t e = cudaEventRecord(ready, st);
+      const uint8_t* src = static_cast<const uint8_t*>(raw_dests[own_index]) + blk_begin * TP_CB;
+      const size_t width = size_t(n_blocks) * TP_CB;
+      for (int k = 1; k < n_dests && e == cudaSuccess; ++k) {
+        const int p = (own_index + k) % n_dests;            // every rank starts with a different peer
+        e = cudaStreamWaitEvent(ps[p], ready, 0);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync(static_cast<uint8_t*>(raw_dests[p]) + blk_begin * TP_CB, size_t(raw_pitch), src,
+                                size_t(raw_pitch), width, size_t(G), cudaMemcpyDeviceToDevice, ps[p]);
+        if (e == cudaSuccess) e = cudaEventRecord(done, ps[p]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, done, 0);
+      }
+      cudaEventDestroy(ready);
+      cudaEventDestroy(done);
+      if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    }
   }
   GV_CUDA_TRY(cudaMemcpyAsync(flags_host, flags_dev, 16, cudaMemcpyDeviceToHost, st));
-  GV_CUDA_TRY(cudaStreamSynchronize(st));      // the peer stores are complete when the kernel is
+  GV_CUDA_TRY(cudaStreamSynchronize(st));      // the peer stores / copies are complete
   return GV_OK;
 }
 
 int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr,
                              int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
-                             void* const* raw_dests, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
-                             unsigned long long* flags_dev, unsigned long long* flags_host, cudaStream_t st) {
+                             void* const* raw_dests, int n_dests, int own_index, int64_t raw_pitch,
+                             uint32_t* ghist_local, unsigned long long* flags_dev,
+                             unsigned long long* flags_host, cudaStream_t st) {
   if (n_dests < 1 || n_dests > TP_MAX_PEERS) return set_error(GV_ERR_ARG, "shard transpose: 1..8 destinations");
+  if (own_index < 0 || own_index >= n_dests) return set_error(GV_ERR_ARG, "shard transpose: own_index out of range");
   if (raw_pitch % TP_CB != 0 || blk_begin < 0 || blk_end < blk_begin || blk_end * TP_CB > raw_pitch)
     return set_error(GV_ERR_ARG, "shard transpose: cell blocks outside the dense rows");
   if (value_dtype == GV_F32)
     return shard_transpose_impl<float>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
-                                       n_dests, raw_pitch, ghist_local, flags_dev, flags_host, st);
+                                       n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, st);
   if (value_dtype == GV_F64)
     return shard_transpose_impl<double>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
-                                        n_dests, raw_pitch, ghist_local, flags_dev, flags_host, st);
+                                        n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 

@@ -1006,7 +1006,7 @@ class Engine:
             dt = _lib.GV_F32 if csr_local.values.dtype == torch.float32 else _lib.GV_F64
             _lib.call("gv_shard_transpose", csr_local.values.data_ptr(), dt, csr_local.col_idx.data_ptr(),
                       csr_local.row_ptr.data_ptr(), csr_local.n_cells, n_genes, blk_range[0], blk_range[1],
-                      dests, world, kp, pb.own_ptr + pb.off["ghist"][0], pb.own_ptr + pb.off["flags"][0],
+                      dests, world, rank, kp, pb.own_ptr + pb.off["ghist"][0], pb.own_ptr + pb.off["flags"][0],
                       flags.ctypes.data, stream.cuda_stream)
             pool.scratch_store(11, int(flags[0]))
             pool.scratch_store(12, int(flags[1]))

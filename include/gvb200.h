@@ -141,9 +141,10 @@ int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells
  * discretising everything and broadcasting the result, every rank uploads only its own run of 128-cell
  * blocks [blk_begin, blk_end) of the matrix (row_ptr_local: the n_cells_local + 1 row pointers of those
  * cells, starting at 0) and gv_shard_transpose writes their dense uint8 rows raw[gene][cell] into the
- * `raw` buffer of EVERY rank: raw_dests_host holds n_dests device pointers (own buffer and the
- * gv_ipc_open mappings of the peers'; the stores cross NVLink), each [n_genes][raw_pitch], raw_pitch =
- * padded cell count (% 256 == 0).  The block ranges of the ranks must tile [0, raw_pitch / 128).
+ * `raw` buffer of EVERY rank: raw_dests_host holds n_dests device pointers (own buffer, at index
+ * own_index, and the gv_ipc_open mappings of the peers'), each [n_genes][raw_pitch], raw_pitch = padded
+ * cell count (% 256 == 0).  The rank's slab [n_genes][its cells] is transposed into its own buffer and
+ * pushed to every peer by one 2-D peer copy per destination (copy engines over NVLink / NVSwitch).  The block ranges of the ranks must tile [0, raw_pitch / 128).
  * ghist_local (uint32 [n_genes][256]) receives this rank's part of the per-gene value histogram;
  * flags_dev: 64 bytes of device scratch; data_flags_out_host as gv_discretize_csr (the caller combines
  * them over the ranks: OR of [0], max of [1]).  Synchronous: when it returns, this rank's stores have
@@ -156,8 +157,8 @@ int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells
  * qtab_dev: 2 KB of device scratch. */
 int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,
                        int64_t n_cells_local, int n_genes, int64_t blk_begin, int64_t blk_end,
-                       void* const* raw_dests_host, int n_dests, int64_t raw_pitch, uint32_t* ghist_local,
-                       void* flags_dev, uint64_t* data_flags_out_host, void* stream);
+                       void* const* raw_dests_host, int n_dests, int own_index, int64_t raw_pitch,
+                       uint32_t* ghist_local, void* flags_dev, uint64_t* data_flags_out_host, void* stream);
 int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, const double* q_table_host,
                   const void* raw, const void* const* hists_host, int n_hists, uint32_t* ghist_total,
                   double* qtab_dev, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,

@@ -140,7 +140,7 @@ def test_sharded_front_end_kernels_reproduce_the_bin_block(engine, world, signed
                             r1 - r0, n_genes)
             flags = np.zeros(2, dtype=np.uint64)
             _lib.call("gv_shard_transpose", loc.values.data_ptr(), _lib.GV_F32, loc.col_idx.data_ptr(),
-                      loc.row_ptr.data_ptr(), loc.n_cells, n_genes, b0, b1, dests, world, kp,
+                      loc.row_ptr.data_ptr(), loc.n_cells, n_genes, b0, b1, dests, world, rank, kp,
                       hists[rank].data_ptr(), fl.data_ptr(), flags.ctypes.data, st)
             f0 |= int(flags[0])
             f1 = max(f1, int(flags[1]))
