@@ -501,6 +501,12 @@ def main():
     host_ms = {k: float(np.mean(v)) for k, v in (eng.host_timings or {}).items()}
     eng.host_timings = None
     sm = last[0]
+    # bytes that crossed the PCIe links in one step: every rank's own upload (count data are packed to
+    # 3 bytes per entry by the staging pass) and the result rectangles (G x G float32 in all)
+    h2d = torch.tensor([eng.last_upload_bytes], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d)
+    h2d_bytes = int(h2d.item())
 
     # correctness guards inside the bench: symmetric, finite, bounded by log2(11); with several ranks a
     # sample of tiles of the other ranks is recomputed on rank 0 and compared bitwise
@@ -576,7 +582,7 @@ def main():
         "e2e": {"value": pairs / (ms_e2e / args.steps * 1e-3), "unit": "gene-pairs/s",
                 "ms_per_step": ms_e2e / args.steps,
                 "ms_per_step_events": ms_e2e_ev / args.steps, "ms_per_step_wall": ms_e2e_wall / args.steps,
-                "h2d_bytes_per_step": csr_bytes(X),
+                "h2d_bytes_per_step": h2d_bytes, "host_csr_bytes": csr_bytes(X),
                 "d2h_bytes_per_step": int(G) * int(G) * 4,
                 "host_phases_ms": host_ms,
                 "note": "genevector_b200.metrics.target_mi(scipy CSR in pageable host memory, gene names, signed=True, "

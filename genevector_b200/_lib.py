@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GVB200_LIB") or os.path.join(_HERE, "libgvb200.so")
 
 GV_OK = 0
-GV_F32, GV_F64 = 0, 1
+GV_F32, GV_F64, GV_COUNTS_U8_COL16 = 0, 1, 2
 GV_MOM_SIGN, GV_MOM_PEARSON, GV_MOM_COSINE, GV_MOM_JACCARD = 0, 1, 2, 3
 GV_PATH_AUTO, GV_PATH_COUNTS, GV_PATH_GENERAL = 0, 1, 2
 GV_VAL_COUNTS, GV_VAL_DETECTED, GV_VAL_FIXED_POINT, GV_VAL_RANKS = 0, 1, 2, 3
@@ -47,7 +47,7 @@ SIGNATURES = {
     "gv_discretize_csr": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp,
                                  _vp, _sz, _i32, _vp, _vp]),
-    "gv_csr_check": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "gv_csr_check": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "gv_shard_transpose": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _vp, _i32, _i32, _i64, _vp, _vp, _vp,
                                   _vp]),
     "gv_shard_bins": (_i32, [_i32, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
@@ -73,6 +73,8 @@ SIGNATURES = {
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),
     "gv_upload_pageable": (_i32, [_vp, _vp, _sz, _i32, _vp]),
+    "gv_upload_packed_counts": (_i32, [_vp, _vp, _vp, _vp, _sz, _i32, _vp, _vp]),
+    "gv_pack_counts_host": (_i32, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "gv_upload_registered": (_i32, [_vp, _vp, _sz, _vp, C.POINTER(_vp)]),
     "gv_upload_release": (_i32, [_vp]),
     "gv_runtime_shutdown": (_i32, []),

@@ -117,15 +117,15 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
   return discretize_dispatch(a, static_cast<cudaStream_t>(stream));
 }
 
-int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int n_genes,
+int gv_csr_check(const void* col_idx, int value_dtype, const int64_t* row_ptr, int64_t n_cells, int n_genes,
                  int* scratch_dev, int* result_host, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!row_ptr || !scratch_dev || !result_host || n_cells < 0 || n_genes <= 0)
     return set_error(GV_ERR_ARG, "gv_csr_check: bad argument");
   *result_host = 0;
-  return csr_check_dispatch(col_idx, row_ptr, n_cells, n_genes, scratch_dev, result_host,
-                            static_cast<cudaStream_t>(stream));
+  return csr_check_dispatch(col_idx, value_dtype == GV_COUNTS_U8_COL16 ? 1 : 0, row_ptr, n_cells, n_genes,
+                            scratch_dev, result_host, static_cast<cudaStream_t>(stream));
 }
 
 int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,

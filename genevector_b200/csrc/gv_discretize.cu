@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <cfloat>
 #include <cstdlib>
+#include <type_traits>
 #include "gv_internal.h"
 
 namespace gv {
@@ -740,9 +741,12 @@ struct RawDests {
 
 // row_ptr / n_cells describe the CSR rows this launch owns (all of them, or a rank's block of cells);
 // blk_offset is the index of its first 128-cell block in the whole matrix (column offset in `raw`).
-template <typename T>
+// VT / CT: storage types of the CSR values and column indices (T / int32_t as handed over, or
+// uint8_t / uint16_t for count data packed on the way up: gv_upload_packed_counts); T stays the dtype the
+// edges are computed in.
+template <typename T, typename VT = T, typename CT = int32_t>
 __global__ void __launch_bounds__(TP_THREADS, 2)
-k_transpose_counts(const T* __restrict__ values, const int32_t* __restrict__ col_idx,
+k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx,
                    const int64_t* __restrict__ row_ptr, int64_t n_cells, int G,
                    const RawDests dests, int64_t raw_pitch, int64_t n_blocks, int64_t blk_offset,
                    uint32_t* __restrict__ ghist, unsigned long long* __restrict__ flags) {
@@ -785,8 +789,8 @@ k_transpose_counts(const T* __restrict__ values, const int32_t* __restrict__ col
           for (int k = 0; k < 4; ++k) {
             const int64_t e = cur[k] + lane;
             const bool ok = e < end[k];
-            cc[k] = ok ? col_idx[e] : 0x7fffffff;
-            vv[k] = ok ? values[e] : T(0);
+            cc[k] = ok ? int32_t(col_idx[e]) : 0x7fffffff;
+            vv[k] = ok ? T(values[e]) : T(0);
           }
           more = false;
 #pragma unroll
@@ -1251,8 +1255,12 @@ static int check_val_config(const DiscretizeArgs& a, const unsigned long long* h
 
 static inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
 
-template <typename T>
+// PACKED: the CSR arrays are uint8 values + uint16 column indices (count data packed on the way up,
+// gv_upload_packed_counts); such input always qualifies for the count path.
+template <typename T, bool PACKED = false>
 static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
+  using VT = typename std::conditional<PACKED, uint8_t, T>::type;
+  using CT = typename std::conditional<PACKED, uint16_t, int32_t>::type;
   const int G = a.n_genes;
   // workspace carve-up (all 256-byte aligned); the two paths share the front part
   uint8_t* ws = static_cast<uint8_t*>(a.workspace);
@@ -1261,7 +1269,8 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   unsigned long long* flags = static_cast<unsigned long long*>(take(64));
   double* qtab = static_cast<double*>(take(16 * 16 * 8));
   const size_t front = off;
-  const T* values = static_cast<const T*>(a.values);
+  const VT* values = static_cast<const VT*>(a.values);
+  const CT* col_idx = reinterpret_cast<const CT*>(a.col_idx);
   const int sms = device_sm_count();
   int8_t* val_rows = static_cast<int8_t*>(a.val_rows);
   const int n_limbs = a.val_mode == 1 ? 1 : a.val_limbs;
@@ -1283,14 +1292,14 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     uint32_t* ghist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
     if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
     GV_CUDA_TRY(cudaMemsetAsync(ghist, 0, size_t(G) * VH * 4, st));
-    auto kt = k_transpose_counts<T>;
+    auto kt = k_transpose_counts<T, VT, CT>;
     GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
     const int64_t n_blocks = kcells / TP_CB;
     const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
     RawDests dests;
     dests.n = 1;
     dests.raw[0] = raw;
-    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, a.col_idx, a.row_ptr, a.n_cells, G, dests,
+    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, a.row_ptr, a.n_cells, G, dests,
                                                      kcells, n_blocks, 0, ghist, flags);
     GV_LAUNCH_CHECK();
     GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
@@ -1331,6 +1340,9 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
                                          "matching val_pitch, and count value rows");
   }
 
+  if constexpr (PACKED) {
+    return set_error(GV_ERR_UNSUPPORTED, "packed count input (uint8 values, uint16 columns) takes the count path only");
+  } else {
   GV_CUDA_TRY(cudaMemsetAsync(a.bins_packed, 0, size_t(G) * a.bins_pitch_bytes, st));
   if (val_rows != nullptr)
     GV_CUDA_TRY(cudaMemsetAsync(val_rows, 0, size_t(a.val_rows_alloc) * a.val_pitch, st));
@@ -1432,6 +1444,7 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   }
   if (a.path_used) *a.path_used = GV_PATH_GENERAL;
   return GV_OK;
+  }  // !PACKED
 }
 
 // ---------------------------------------------------------------- gene entropy, general data
@@ -1569,7 +1582,8 @@ int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* co
 // One warp per row: every column index must lie in [0, G) and exceed its predecessor in the row
 // (sorted, no duplicate entries) -- what scipy calls canonical format and what the discretisation
 // kernels assume.  result: 0 canonical, 1 unsorted or duplicate entries, 2 an index out of range.
-__global__ void k_csr_check(const int32_t* __restrict__ col_idx, const int64_t* __restrict__ row_ptr,
+template <typename CT>
+__global__ void k_csr_check(const CT* __restrict__ col_idx, const int64_t* __restrict__ row_ptr,
                             int64_t n_cells, int G, int* __restrict__ result) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -1578,21 +1592,26 @@ __global__ void k_csr_check(const int32_t* __restrict__ col_idx, const int64_t* 
     const int64_t e0 = row_ptr[r], e1 = row_ptr[r + 1];
     if (e1 < e0) bad = 2;
     for (int64_t e = e0 + lane; e < e1; e += 32) {
-      const int32_t c = col_idx[e];
+      const int32_t c = int32_t(col_idx[e]);
       if (c < 0 || c >= G) bad = 2;
-      else if (e > e0 && col_idx[e - 1] >= c && bad < 1) bad = 1;
+      else if (e > e0 && int32_t(col_idx[e - 1]) >= c && bad < 1) bad = 1;
     }
   }
   bad = __reduce_max_sync(0xffffffffu, bad);
   if (lane == 0 && bad) atomicMax(result, bad);
 }
 
-int csr_check_dispatch(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int G,
+int csr_check_dispatch(const void* col_idx, int col16, const int64_t* row_ptr, int64_t n_cells, int G,
                        int* scratch_dev, int* result_host, cudaStream_t st) {
   GV_CUDA_TRY(cudaMemsetAsync(scratch_dev, 0, sizeof(int), st));
   if (n_cells > 0) {
     const int sms = device_sm_count();
-    k_csr_check<<<sms * 8, 256, 0, st>>>(col_idx, row_ptr, n_cells, G, scratch_dev);
+    if (col16)
+      k_csr_check<uint16_t><<<sms * 8, 256, 0, st>>>(static_cast<const uint16_t*>(col_idx), row_ptr, n_cells, G,
+                                                      scratch_dev);
+    else
+      k_csr_check<int32_t><<<sms * 8, 256, 0, st>>>(static_cast<const int32_t*>(col_idx), row_ptr, n_cells, G,
+                                                     scratch_dev);
     GV_LAUNCH_CHECK();
   }
   GV_CUDA_TRY(cudaMemcpyAsync(result_host, scratch_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1643,13 +1662,16 @@ static cudaStream_t* peer_streams(int device) {
 //   "stores"         the transposition kernel stores every 128-byte line to all destinations itself
 //                    (measured on 8 GPUs: 53 ms for 3.5 GB per GPU -- 4-byte peer stores from a
 //                    latency-bound kernel do not fill NVLink; kept for the comparison)
-template <typename T>
-static int shard_transpose_impl(const void* values_v, const int32_t* col_idx, const int64_t* row_ptr,
+template <typename T, bool PACKED = false>
+static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, const int64_t* row_ptr,
                                 int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
                                 void* const* raw_dests, int n_dests, int own_index, int64_t raw_pitch,
                                 uint32_t* ghist_local, unsigned long long* flags_dev,
                                 unsigned long long* flags_host, cudaStream_t st) {
-  const T* values = static_cast<const T*>(values_v);
+  using VT = typename std::conditional<PACKED, uint8_t, T>::type;
+  using CT = typename std::conditional<PACKED, uint16_t, int32_t>::type;
+  const VT* values = static_cast<const VT*>(values_v);
+  const CT* col_idx = reinterpret_cast<const CT*>(col_idx_v);
   static const bool push_stores = getenv("GV_SHARD_PUSH") != nullptr && getenv("GV_SHARD_PUSH")[0] == 's';
   RawDests dests;
   if (push_stores) {
@@ -1663,7 +1685,7 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx, co
   GV_CUDA_TRY(cudaMemsetAsync(ghist_local, 0, size_t(G) * VH * 4, st));
   const int64_t n_blocks = blk_end - blk_begin;
   if (n_blocks > 0) {
-    auto kt = k_transpose_counts<T>;
+    auto kt = k_transpose_counts<T, VT, CT>;
     GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
     const int sms = device_sm_count();
     const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
@@ -1715,6 +1737,10 @@ int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t*
   if (value_dtype == GV_F64)
     return shard_transpose_impl<double>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
                                         n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, st);
+  if (value_dtype == GV_COUNTS_U8_COL16)
+    return shard_transpose_impl<float, true>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end,
+                                             raw_dests, n_dests, own_index, raw_pitch, ghist_local, flags_dev,
+                                             flags_host, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
@@ -1750,7 +1776,8 @@ int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint3
   if (a.val_rows != nullptr && (a.val_mode != 0 || a.val_limbs != 1 || a.val_rows != raw ||
                                 a.val_pitch != a.bins_pitch_bytes * 2))
     return set_error(GV_ERR_ARG, "shard bins: value rows must be the dense count rows themselves (one digit)");
-  if (a.value_dtype == GV_F32) return shard_bins_impl<float>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
+  if (a.value_dtype == GV_F32 || a.value_dtype == GV_COUNTS_U8_COL16)
+    return shard_bins_impl<float>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
   if (a.value_dtype == GV_F64) return shard_bins_impl<double>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
@@ -1761,6 +1788,7 @@ int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
     return set_error(GV_ERR_ARG, "bins pitch must be a multiple of 16 bytes covering n_cells/2");
   if (a.value_dtype == GV_F32) return discretize_impl<float>(a, st);
   if (a.value_dtype == GV_F64) return discretize_impl<double>(a, st);
+  if (a.value_dtype == GV_COUNTS_U8_COL16) return discretize_impl<float, true>(a, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 

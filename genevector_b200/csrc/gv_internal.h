@@ -34,7 +34,7 @@ size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value
 int gene_entropy_dispatch(const void* values, int value_dtype, const int32_t* col_idx,
                           const int64_t* row_ptr, int64_t nnz, int64_t n_cells, int G, double* ent,
                           void* workspace, size_t ws_bytes, cudaStream_t st);
-int csr_check_dispatch(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int G,
+int csr_check_dispatch(const void* col_idx, int col16, const int64_t* row_ptr, int64_t n_cells, int G,
                        int* scratch_dev, int* result_host, cudaStream_t st);
 int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr,
                              int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,

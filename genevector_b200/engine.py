@@ -63,11 +63,18 @@ def max_limbs_for(n_cells: int, limb_bits: int) -> int:
 @dataclasses.dataclass
 class CsrDevice:
     """A cells x genes CSR matrix resident on the device."""
-    values: torch.Tensor     # float32 / float64 [nnz]
-    col_idx: torch.Tensor    # int32 [nnz]
+    values: torch.Tensor     # float32 / float64 [nnz]   (uint8 when packed)
+    col_idx: torch.Tensor    # int32 [nnz]               (uint16 when packed)
     row_ptr: torch.Tensor    # int64 [n_cells + 1]
     n_cells: int
     n_genes: int
+    packed: bool = False     # count data packed on the way up (gv_upload_packed_counts)
+
+    @property
+    def dtype_code(self) -> int:
+        if self.packed:
+            return _lib.GV_COUNTS_U8_COL16
+        return _lib.GV_F32 if self.values.dtype == torch.float32 else _lib.GV_F64
 
     @property
     def nnz(self) -> int:
@@ -357,6 +364,9 @@ class Engine:
         self._upload_tokens = []
         # metrics._run_to_host sets this: registered pages are unlocked after the whole call is enqueued
         self.defer_release = False
+        # pack count data while staging (GV_PACK_UPLOADS=0 turns it off); bytes of the last upload
+        self.pack_uploads = os.environ.get("GV_PACK_UPLOADS", "1") != "0"
+        self.last_upload_bytes = 0
 
     # kernels launched by each entry point (memsets / copies not counted)
     _LAUNCHES = {"gv_discretize_csr": 2, "gv_expand_onehot": 1, "gv_moment_tiles": 1,
@@ -388,7 +398,7 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def upload_csr(self, X, pinned: bool = False, rows: Optional[tuple] = None) -> CsrDevice:
+    def upload_csr(self, X, pinned: bool = False, rows: Optional[tuple] = None, pack: bool = False) -> CsrDevice:
         """scipy CSR (host) -> device tensors.  Integer dtypes are converted to the smallest float
         type that holds them exactly (discretisation arithmetic is identical: see DESIGN.md).
         The arrays are pageable host memory (the reference hands over adata.X, data.py:171): they go
@@ -396,7 +406,11 @@ class Engine:
         is canonical (ascending, unique, in-range column indices per row) is taken from scipy when it
         already knows and otherwise checked on the device (gv_csr_check); only a matrix that is not
         is canonicalised on the host and uploaded again.
-        rows = (r0, r1): upload that block of cells only (the sharded front end)."""
+        rows = (r0, r1): upload that block of cells only (the sharded front end).
+        pack: count data (float32 integers <= 255, at most 65,536 genes) are packed to uint8 values +
+        uint16 column indices by the staging pass itself (3 bytes per entry cross the PCIe link instead
+        of 8); data that do not fit are uploaded as they are.  Packed matrices feed the count path of the
+        discretisation only (the MI / matrix-target calls); other consumers upload with pack=False."""
         import time
         import scipy.sparse as sp
         t_up = time.perf_counter()
@@ -426,14 +440,29 @@ class Engine:
             ptr = ptr - e0
         data = np.ascontiguousarray(data)
         with torch.cuda.device(self.device):
-            dv = torch.empty(data.shape, dtype=torch.float32 if data.dtype == np.float32 else torch.float64,
-                             device=self.device)
-            dc = torch.empty(cols.shape, dtype=torch.int32, device=self.device)
-            dp = torch.empty(ptr.shape, dtype=torch.int64, device=self.device)
             st = self._stream()
+            dp = torch.empty(ptr.shape, dtype=torch.int64, device=self.device)
+            packed = False
+            if pack and data.dtype == np.float32 and n_genes <= 65536 and self.pack_uploads:
+                t_st = time.perf_counter()
+                dv = torch.empty(data.shape, dtype=torch.uint8, device=self.device)
+                dc = torch.empty(cols.shape, dtype=torch.uint16, device=self.device)
+                fits = np.zeros(1, dtype=np.int32)
+                _lib.call("gv_upload_packed_counts", dv.data_ptr(), dc.data_ptr(), data.ctypes.data, cols.ctypes.data,
+                          data.size, self.copy_threads, fits.ctypes.data, st)
+                packed = bool(fits[0])
+                if packed:
+                    _lib.call("gv_upload_pageable", dp.data_ptr(), ptr.ctypes.data, ptr.nbytes, self.copy_threads, st)
+                    self.last_upload_bytes = int(data.size * 3 + ptr.nbytes)
+                    self._timed_host("upload_csr: host side of the copies (packed counts)", t_st)
+            if not packed:
+                dv = torch.empty(data.shape, dtype=torch.float32 if data.dtype == np.float32 else torch.float64,
+                                 device=self.device)
+                dc = torch.empty(cols.shape, dtype=torch.int32, device=self.device)
+                self.last_upload_bytes = int(data.nbytes + cols.nbytes + ptr.nbytes)
             self._timed_host("upload_csr: views + device buffers", t_up)
             t_st = time.perf_counter()
-            for dst, src in ((dv, data), (dc, cols), (dp, ptr)):
+            for dst, src in (() if packed else ((dv, data), (dc, cols), (dp, ptr))):
                 if self.upload_mode == "registered" and src.nbytes >= (32 << 20):
                     import ctypes as C
                     tok = C.c_void_p()
@@ -443,11 +472,12 @@ class Engine:
                 else:
                     _lib.call("gv_upload_pageable", dst.data_ptr(), src.ctypes.data, src.nbytes,
                               self.copy_threads, st)
-            self._timed_host("upload_csr: host side of the copies", t_st)
-            csr = CsrDevice(dv, dc, dp, r1 - r0, n_genes)
+            if not packed:
+                self._timed_host("upload_csr: host side of the copies", t_st)
+            csr = CsrDevice(dv, dc, dp, r1 - r0, n_genes, packed)
             if known is not True:
                 ok = np.zeros(1, dtype=np.int32)
-                _lib.call("gv_csr_check", dc.data_ptr(), dp.data_ptr(), csr.n_cells, n_genes,
+                _lib.call("gv_csr_check", dc.data_ptr(), csr.dtype_code, dp.data_ptr(), csr.n_cells, n_genes,
                           self._flag_ws.data_ptr(), ok.ctypes.data, st)
                 if int(ok[0]) == 2:
                     raise ValueError("column index out of range in the CSR matrix")
@@ -455,7 +485,7 @@ class Engine:
                     Xc = X.copy()
                     Xc.sum_duplicates()             # sorts the indices and merges duplicate entries
                     Xc._has_canonical_format = True
-                    return self.upload_csr(Xc, rows=rows)
+                    return self.upload_csr(Xc, rows=rows, pack=pack)
         if not self.defer_release:
             self.release_uploads()
         self._timed_host("upload_csr (host side: staging + canonical check)", t_up)
@@ -489,7 +519,7 @@ class Engine:
         (no retry).  The block's val_mode / n_limbs say what was produced."""
         if not 1 <= n_bins <= 15:
             raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
-        if csr.values.dtype not in (torch.float32, torch.float64):
+        if csr.values.dtype not in (torch.float32, torch.float64) and not csr.packed:
             raise GvError("discretize", -1, "values must be float32 or float64")
         with torch.cuda.device(self.device):
             lb = limb_bits_for(max(csr.n_cells, 1)) if val_mode in (0, 2, 3) else 7
@@ -509,9 +539,10 @@ class Engine:
             if val_mode >= 0 and not 1 <= L <= max(l_max, 1):
                 raise GvError("discretize", -4, f"value rows would need {L} digits per gene; at most "
                               f"{l_max} keep the co-moments of {csr.n_cells} cells exact")
-            dt = _lib.GV_F32 if csr.values.dtype == torch.float32 else _lib.GV_F64
+            dt = csr.dtype_code
             sorted_ws = 1 if val_mode == 3 else 0
-            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_cells, csr.n_genes, dt, sorted_ws)
+            ws_bytes = self.lib.gv_discretize_workspace_bytes(csr.nnz, csr.n_cells, csr.n_genes,
+                                                              _lib.GV_F32 if csr.packed else dt, sorted_ws)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             q = quantile_table()
             mode = val_mode
@@ -1003,7 +1034,7 @@ class Engine:
                 ev[0].record(stream)
             dests = (C.c_void_p * world)(*[p + pb.off["val"][0] for p in pb.ptrs])
             flags = np.zeros(2, dtype=np.uint64)
-            dt = _lib.GV_F32 if csr_local.values.dtype == torch.float32 else _lib.GV_F64
+            dt = csr_local.dtype_code
             _lib.call("gv_shard_transpose", csr_local.values.data_ptr(), dt, csr_local.col_idx.data_ptr(),
                       csr_local.row_ptr.data_ptr(), csr_local.n_cells, n_genes, blk_range[0], blk_range[1],
                       dests, world, rank, kp, pb.own_ptr + pb.off["ghist"][0], pb.own_ptr + pb.off["flags"][0],
@@ -1103,7 +1134,7 @@ class Engine:
         pool = get_pool()
         n_cells, n_genes = X.shape
         b0, b1, r0, r1 = self.shard_cells(n_cells, rank, world)
-        csr_local = self.upload_csr(X, rows=(r0, r1))
+        csr_local = self.upload_csr(X, rows=(r0, r1), pack=True)
         blk = self._shard_front(csr_local, (b0, b1), n_cells, n_genes, n_bins, signed, rank, world, pool)
         if blk is None:
             if required:

@@ -159,7 +159,7 @@ def compute_mi_b200(X, gene_names, n_bins=10, signed=False, device=None, sign_ru
                                             sign_rule=sign_rule, sink=sink, required=(front == "sharded"))
             if done:
                 return
-        csr = eng.upload_csr(X) if rank == 0 else None
+        csr = eng.upload_csr(X, pack=True) if rank == 0 else None
         eng.mi_from_csr(csr, n_cells, n_genes, n_bins=n_bins, signed=signed, rank=rank, world=world,
                         sign_rule=sign_rule, sink=sink)
 
@@ -187,7 +187,7 @@ def _moment_target(X, gene_names, kind, device=None, ranks=False):
         raise ValueError("gene_names must have one entry per column of X")
 
     def run(sink):
-        csr = eng.upload_csr(X) if rank == 0 else None
+        csr = eng.upload_csr(X, pack=True) if rank == 0 else None
         eng.target_from_csr(csr, kind, ranks=ranks, n_cells=n_cells, n_genes=n_genes, rank=rank, world=world,
                             sink=sink)
 

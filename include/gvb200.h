@@ -46,7 +46,10 @@ typedef enum gv_status {
   GV_ERR_TIMEOUT = -5      /* another rank of the box did not arrive in time */
 } gv_status;
 
-typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1 } gv_dtype;
+/* Storage of the CSR arrays.  GV_COUNTS_U8_COL16: `values` are uint8 and `col_idx` uint16 -- count data
+ * (integers <= 255, fewer than 65,537 genes) packed on the way up by gv_upload_packed_counts; it takes
+ * the count path of the discretisation, with the edge arithmetic of float32 input (what the data were). */
+typedef enum gv_dtype { GV_F32 = 0, GV_F64 = 1, GV_COUNTS_U8_COL16 = 2 } gv_dtype;
 
 /* Discretisation strategies (same results, bit for bit):
  *   GV_PATH_COUNTS  dense uint8 transposition through shared memory + per-gene value histogram and
@@ -133,7 +136,7 @@ int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_id
  * with every index in [0, n_genes)?  The discretisation assumes it; the reference gets it from
  * scipy.  Synchronous; *result_host = 0 canonical, 1 unsorted or duplicate entries (canonicalise on the
  * host: sum_duplicates), 2 an index out of range.  scratch_dev: 4 bytes of device memory. */
-int gv_csr_check(const int32_t* col_idx, const int64_t* row_ptr, int64_t n_cells, int n_genes,
+int gv_csr_check(const void* col_idx, int value_dtype, const int64_t* row_ptr, int64_t n_cells, int n_genes,
                  int* scratch_dev, int* result_host, void* stream);
 
 /* ---------------------------------------------------------------- sharded discretisation front end
@@ -319,6 +322,15 @@ int gv_upload_pageable(void* dst_dev, const void* src_host, size_t bytes, int n_
  * (cudaHostRegister, in 64 MB chunks, each chunk's DMA running under the next chunk's registration) and
  * read by the copy engine directly.  The source must stay untouched until gv_upload_release(*token_out),
  * which waits for the copies and unlocks the pages (call it once the rest of the work is enqueued). */
+/* Count data (float32 values that are integers in [0, 255], column indices < 65,536): the staging pass
+ * packs while it copies -- uint8 values and uint16 column indices reach the device, 3 bytes per stored
+ * entry instead of 8 (storage GV_COUNTS_U8_COL16).  *ok_host = 0 when an entry does not fit (device
+ * contents are then undefined: upload the arrays as they are).  gv_pack_counts_host is the packing pass
+ * alone, host to host (destinations 32-byte aligned); it exists for the tests. */
+int gv_upload_packed_counts(void* dst_vals_u8, void* dst_cols_u16, const float* src_vals_host,
+                            const int32_t* src_cols_host, size_t nnz, int n_threads, int* ok_host, void* stream);
+int gv_pack_counts_host(const float* src_vals, const int32_t* src_cols, size_t nnz, uint8_t* dst_vals,
+                        uint16_t* dst_cols, int* ok_host);
 int gv_upload_registered(void* dst_dev, const void* src_host, size_t bytes, void* stream, void** token_out);
 int gv_upload_release(void* token);
 int gv_runtime_shutdown(void);

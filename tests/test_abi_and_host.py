@@ -388,3 +388,42 @@ def test_reference_consumers_accept_the_score_matrix(tmp_path, monkeypatch):
     assert got.genes == genes and np.abs(got.rounded() - M).max() <= 1.1e-5
     ds.load_target_scores(path_ours)
     assert abs(ds.mi_scores[genes[0]][genes[1]] - M[0, 1]) <= 1.1e-5 and genes[0] not in ds.mi_scores[genes[0]]
+
+
+def test_count_packer_matches_numpy_and_refuses_what_does_not_fit():
+    """gv_pack_counts_host (the staging pass of gv_upload_packed_counts, host to host): float32 counts ->
+    uint8, int32 columns -> uint16, in order, for lengths around the 32-entry vector width; anything that
+    is not an integer in [0, 255] / a column index in [0, 65535] makes it report "does not fit"."""
+    import ctypes as C
+    from genevector_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+
+    def pack(v, c):
+        n = len(v)
+        dv = np.zeros(n + 64, dtype=np.uint8)
+        dc = np.zeros(n + 64, dtype=np.uint16)
+        ov = (-dv.ctypes.data) % 32
+        oc = ((-dc.ctypes.data) % 32) // 2
+        ok = np.zeros(1, dtype=np.int32)
+        _lib.check("gv_pack_counts_host", lib.gv_pack_counts_host(
+            v.ctypes.data, c.ctypes.data, n, dv.ctypes.data + ov, dc.ctypes.data + 2 * oc, ok.ctypes.data))
+        return int(ok[0]), dv[ov:ov + n], dc[oc:oc + n]
+
+    for n in (0, 1, 31, 32, 33, 95, 1000, 100003):
+        v = rng.integers(0, 256, size=n).astype(np.float32)
+        c = rng.integers(0, 65536, size=n).astype(np.int32)
+        ok, dv, dc = pack(v, c)
+        assert ok == 1
+        assert np.array_equal(dv, v.astype(np.uint8)) and np.array_equal(dc, c.astype(np.uint16))
+    base_v = rng.integers(0, 256, size=1000).astype(np.float32)
+    base_c = rng.integers(0, 65536, size=1000).astype(np.int32)
+    for pos in (0, 17, 500, 991, 999):
+        for bad in (0.5, -1.0, 256.0, np.nan, np.inf, 3e9, -0.25):
+            v = base_v.copy()
+            v[pos] = bad
+            assert pack(v, base_c)[0] == 0, (pos, bad)
+        for badc in (65536, -1, 2 ** 31 - 1):
+            c = base_c.copy()
+            c[pos] = badc
+            assert pack(base_v, c)[0] == 0, (pos, badc)

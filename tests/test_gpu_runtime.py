@@ -52,7 +52,7 @@ def test_csr_check_finds_unsorted_duplicate_and_out_of_range(engine):
             p = torch.from_numpy(np.ascontiguousarray(indptr, dtype=np.int64)).to(dev)
             ok = np.zeros(1, dtype=np.int32)
             scratch = torch.zeros(1, dtype=torch.int32, device=dev)
-            _lib.call("gv_csr_check", c.data_ptr(), p.data_ptr(), len(indptr) - 1, n_genes, scratch.data_ptr(),
+            _lib.call("gv_csr_check", c.data_ptr(), _lib.GV_F32, p.data_ptr(), len(indptr) - 1, n_genes, scratch.data_ptr(),
                       ok.ctypes.data, torch.cuda.current_stream(dev).cuda_stream)
             return int(ok[0])
 
@@ -172,6 +172,36 @@ def test_sharded_front_end_kernels_reproduce_the_bin_block(engine, world, signed
                 dense = torch.from_numpy(np.asarray(X.todense()).T.astype(np.uint8)).to(dev)
                 assert torch.equal(raws[rank][:n_genes, :n_cells], dense)
                 assert not raws[rank][:n_genes, n_cells:].any()
+
+
+@pytest.mark.parametrize("vmax", [9, 255])
+def test_packed_count_upload_gives_the_same_bin_block(engine, vmax):
+    """upload_csr(pack=True): uint8 values + uint16 columns on the device; the discretisation (bins,
+    marginals, edges, value rows, sums) is bit-identical to the one from the float32 / int32 arrays.
+    Data that are not counts are uploaded as they are."""
+    import torch
+    from genevector_b200.synth import synth_counts
+    X = synth_counts(3000, 500, seed=51)
+    if vmax == 255:
+        X.data[::7] = 255.0
+        X.data[3::11] = 200.0
+    a = engine.upload_csr(X)
+    b = engine.upload_csr(X, pack=True)
+    assert b.packed and b.values.dtype == torch.uint8 and b.col_idx.dtype == torch.uint16 and not a.packed
+    assert engine.last_upload_bytes == X.nnz * 3 + (X.shape[0] + 1) * 8
+    for mode in (-1, 0, 1, 3):
+        A, B = engine.discretize(a, 10, mode), engine.discretize(b, 10, mode)
+        assert B.path_used == 1 and A.n_limbs == B.n_limbs and A.val_mode == B.val_mode
+        for f in ("bins", "marg", "n_bins_per_gene", "gsum", "gsq"):
+            assert torch.equal(getattr(A, f), getattr(B, f)), (mode, f)
+        assert torch.equal(A.edges.view(torch.int64), B.edges.view(torch.int64))
+        if mode >= 0:
+            assert torch.equal(A.val_rows, B.val_rows), mode
+    Xf = X.copy()
+    Xf.data = np.log1p(Xf.data).astype(np.float32)
+    assert not engine.upload_csr(Xf, pack=True).packed
+    X64 = X.astype(np.float64)
+    assert not engine.upload_csr(X64, pack=True).packed
 
 
 def test_public_call_reuses_its_pinned_result_buffers(engine):

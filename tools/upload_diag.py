@@ -38,7 +38,7 @@ def main():
         t.append(time.perf_counter())
         ok = np.zeros(1, dtype=np.int32)
         scratch = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.call("gv_csr_check", dc.data_ptr(), dp.data_ptr(), N, G, scratch.data_ptr(), ok.ctypes.data, st)
+        _lib.call("gv_csr_check", dc.data_ptr(), _lib.GV_F32, dp.data_ptr(), N, G, scratch.data_ptr(), ok.ctypes.data, st)
         t.append(time.perf_counter())
         names = ["views", "torch.empty", "upload data", "upload cols", "upload ptr", "sync", "csr_check"]
         print(f"iter {it} threads={eng.copy_threads}: " +
