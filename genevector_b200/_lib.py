@@ -71,6 +71,7 @@ SIGNATURES = {
     "gv_mma_peak": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp]),
     "gv_moment_tiles": (_i32, [_i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp,
                                _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp]),
+    "gv_compute_mi_pairs": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gv_build_training_tensors": (_i32, [_vp, _i64, _i32, C.c_float, _i32, _i32, _vp, _vp, _vp, _vp]),
     "gv_upload_pageable": (_i32, [_vp, _vp, _sz, _i32, _vp]),
     "gv_upload_packed_counts": (_i32, [_vp, _vp, _vp, _vp, _sz, _i32, _vp, _vp]),

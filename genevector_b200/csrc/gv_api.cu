@@ -65,6 +65,8 @@ int graph_aggregate_dispatch(const void*, int64_t, int, int, const double*, cons
 int symmetrize_dispatch(const float*, int64_t, int, float*, int64_t, cudaStream_t);
 int build_pairs_dispatch(const float*, int64_t, int, float, int, int, int64_t*, int64_t*, float*,
                          cudaStream_t);
+int compute_mi_pairs_impl(const int32_t*, int64_t, int, const int32_t*, const float*, float*, int64_t*, int,
+                          cudaStream_t);
 
 }  // namespace gv
 
@@ -359,6 +361,19 @@ int gv_mma_peak(int operand_format, int cta_group, int iters, int mode, double* 
   int rc = check_device();
   if (rc != GV_OK) return rc;
   return mma_peak_dispatch(operand_format, cta_group, iters, mode, tops_out_host, static_cast<cudaStream_t>(stream));
+}
+
+int gv_compute_mi_pairs(const int32_t* x_disc_host, int64_t n_cells, int n_genes,
+                        const int32_t* n_bins_per_gene_host, const float* corr_signs_host,
+                        float* scores_out_host, int64_t* n_pairs_out_host, int operand_format, void* stream) {
+  int rc = check_device();
+  if (rc != GV_OK) return rc;
+  if (!x_disc_host || !n_bins_per_gene_host || !scores_out_host || n_genes <= 0 || n_cells < 0)
+    return set_error(GV_ERR_ARG, "gv_compute_mi_pairs: bad argument");
+  if (n_cells >= (int64_t(1) << 31)) return set_error(GV_ERR_ARG, "n_cells must be < 2^31");
+  return compute_mi_pairs_impl(x_disc_host, n_cells, n_genes, n_bins_per_gene_host, corr_signs_host,
+                               scores_out_host, n_pairs_out_host, operand_format,
+                               static_cast<cudaStream_t>(stream));
 }
 
 int gv_build_training_tensors(const float* scores, int64_t ld_scores, int n_genes, float c,

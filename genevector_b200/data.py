@@ -122,3 +122,37 @@ def get_gene_entropy(X, gene_names, device="cuda"):
                   ws.data_ptr(), ws_bytes, torch.cuda.current_stream(eng.device).cuda_stream)
         vals = ent.cpu().numpy()
     return {g: float(v) for g, v in zip(gene_names, vals)}
+
+
+# ------------------------------------------------------------------ methods for the reference's dataset
+# metrics.install_into_reference binds these onto genevector.data.GeneVectorDataset; they only touch the
+# attributes the reference's own methods touch (adata.X, adata.var.index, data.genes, mi_scores,
+# signed_mi, device, _i_idx / _j_idx / _xij), so any object with those works.
+def dataset_get_gene_entropy(adata):
+    """GeneVectorDataset.get_gene_entropy (staticmethod, data.py:186-203)."""
+    return get_gene_entropy(adata.X, adata.var.index.tolist())
+
+
+def dataset_build_training_tensors(self, c=100.):
+    """GeneVectorDataset._build_training_tensors (data.py:377-411)."""
+    if not isinstance(self.mi_scores, ScoreMatrix):
+        ref = getattr(type(self), "_build_training_tensors_reference", None)
+        if ref is None:
+            raise TypeError("mi_scores is not a ScoreMatrix and the reference implementation is not available")
+        return ref(self, c=c)
+    dev = self.device if str(self.device).startswith("cuda") else "cuda"
+    i_idx, j_idx, xij = build_training_tensors(self.mi_scores, self.data.genes, c=c, signed_mi=self.signed_mi,
+                                               device=dev)
+    if not str(self.device).startswith("cuda"):
+        i_idx, j_idx, xij = i_idx.to(self.device), j_idx.to(self.device), xij.to(self.device)
+    self._i_idx, self._j_idx, self._xij = i_idx, j_idx, xij
+
+
+def dataset_load_target_scores(self, filepath):
+    """GeneVectorDataset.load_target_scores (data.py:241-251)."""
+    self.mi_scores = load_target_scores(filepath)
+
+
+def dataset_save_target_scores(self, filepath):
+    """GeneVectorDataset.save_target_scores (data.py:235-239)."""
+    return save_target_scores(self.mi_scores, self.data.genes, filepath)

@@ -246,9 +246,36 @@ def target_graph_xcorr(X, gene_names, graph=None, aggr="mean", aggr_params=None,
     return ScoreMatrix(out.cpu().numpy(), gene_names)
 
 
-def install_into_reference(ref_metrics_module):
-    """Plug the B200 tier into an imported `genevector.metrics`: overrides the
-    registry entries through the reference's own register_target hook."""
+def install_into_reference(ref_metrics_module, ref_data_module=None, ref_cache_module=None):
+    """Plug the B200 tier into an imported reference package.
+
+    ref_metrics_module (genevector.metrics): the targets are overridden through the reference's own
+    register_target hook.
+    ref_data_module (genevector.data) / ref_cache_module (genevector.cache), optional: the O(G^2) Python
+    around the targets is replaced by the matrix fast paths, so that the reference's own
+    GeneVectorDataset.create_inputs_outputs (data.py:336-375) runs at 5,000+ genes --
+      GeneVectorDataset.get_gene_entropy      data.py:186-203  (densifies X)   -> gv_gene_entropy
+      GeneVectorDataset._build_training_tensors  data.py:377-411 (double loop) -> gv_build_training_tensors
+      GeneVectorDataset.load_target_scores / save_target_scores  data.py:235-251
+      cache.save_scores / cache.load_scores   cache.py:64-110 (double loops)   -> array operations
+    The originals stay reachable as <name>_reference; a nested dict handed in by the user (load_targets)
+    still goes through them."""
     for name in ("mi", "pearson", "spearman", "cosine", "jaccard", "graph_xcorr"):
         ref_metrics_module.register_target(name)(TARGETS[name])
+    if ref_cache_module is not None:
+        from . import cache as fast_cache
+        for name in ("save_scores", "load_scores"):
+            if not hasattr(ref_cache_module, name + "_reference"):
+                setattr(ref_cache_module, name + "_reference", getattr(ref_cache_module, name))
+            setattr(ref_cache_module, name, getattr(fast_cache, name))
+    if ref_data_module is not None:
+        from . import data as fast_data
+        D = ref_data_module.GeneVectorDataset
+        for name in ("get_gene_entropy", "_build_training_tensors", "load_target_scores", "save_target_scores"):
+            if name + "_reference" not in D.__dict__:
+                setattr(D, name + "_reference", D.__dict__[name])
+        D.get_gene_entropy = staticmethod(fast_data.dataset_get_gene_entropy)
+        D._build_training_tensors = fast_data.dataset_build_training_tensors
+        D.load_target_scores = fast_data.dataset_load_target_scores
+        D.save_target_scores = fast_data.dataset_save_target_scores
     return ref_metrics_module

@@ -220,6 +220,24 @@ int gv_mi_tiles(const void* onehot, int64_t op_rows, int64_t row_bytes, int rows
                 const int32_t* tiles, int64_t n_tiles, float* out, int64_t ld_out, int cta_group,
                 int operand_format, void* sync_ws, void* stream);
 
+/* ---------------------------------------------------------------- the reference's FFI, shape for shape
+ * genevector._rust.compute_mi_pairs(x_disc, n_bins_per_gene, corr_signs) (src/lib.rs:9-15, stub
+ * genevector/_rust.pyi:1-5; called at genevector/metrics.py:330): what a maintainer binds who swaps only
+ * the Rust module.  HOST arrays in, as the PyO3 function borrows them:
+ *   x_disc_host           int32 [n_cells][n_genes], C order: discretize_genes' first return value
+ *   n_bins_per_gene_host  int32 [n_genes]: its second (a gene with <= 1 is skipped, lib.rs:33)
+ *   corr_signs_host       float32 [n_genes][n_genes] or NULL: the score is multiplied by +1 unless the
+ *                         entry is negative (lib.rs:91-94)
+ * and a dense float32 [n_genes][n_genes] matrix out: scores_out_host[i][j] = [j][i] = MI of the pair, 0
+ * on the diagonal and for the pairs the Rust function does not return; *n_pairs_out_host (optional) =
+ * the number of (i, j, mi) triples it would return.  Bin indices must be < 16 (n_bins <= 15).
+ * operand_format: GV_OPERAND_INT8, GV_OPERAND_FP4 or -1 (FP4 where it applies).  Synchronous; the device
+ * memory it needs (n_cells * n_genes * 4 bytes for x_disc among others) is allocated and freed inside:
+ * the caller of this entry has no device allocator. */
+int gv_compute_mi_pairs(const int32_t* x_disc_host, int64_t n_cells, int n_genes,
+                        const int32_t* n_bins_per_gene_host, const float* corr_signs_host,
+                        float* scores_out_host, int64_t* n_pairs_out_host, int operand_format, void* stream);
+
 /* Test-only: raw INT32 accumulators (= joint counts over non-zero bins) of the tiles.
  * active_rows = 32: every operand row is a column of the tile (N = 256); 30: the B side stages only
  * the first 30 rows of every 32-row block (N = 240, what gv_mi_tiles does for 10 or 5 rows per

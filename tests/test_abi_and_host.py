@@ -390,6 +390,59 @@ def test_reference_consumers_accept_the_score_matrix(tmp_path, monkeypatch):
     assert abs(ds.mi_scores[genes[0]][genes[1]] - M[0, 1]) <= 1.1e-5 and genes[0] not in ds.mi_scores[genes[0]]
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DIR, "genevector")),
+                    reason="reference sources only exist in the build container")
+def test_install_into_reference_replaces_the_python_loops_of_the_dataset(tmp_path, monkeypatch):
+    """install_into_reference(metrics, data, cache) on the reference's own modules (build container
+    only): GeneVectorDataset.get_gene_entropy / _build_training_tensors / load / save_target_scores and
+    cache.save_scores / load_scores become the matrix fast paths, the originals stay reachable, and a
+    nested dict a user side-loads still builds its tensors through the reference's own loop."""
+    import collections
+    import importlib
+    import sys
+    import types
+    from genevector_b200 import cache as our_cache, data as our_data, metrics as ours
+    from genevector_b200.scores import ScoreMatrix
+    pkg = types.ModuleType("genevector")
+    pkg.__path__ = [os.path.join(REF_DIR, "genevector")]
+    monkeypatch.setitem(sys.modules, "genevector", pkg)
+    for sub in ("genevector.data", "genevector.cache", "genevector.metrics", "genevector._aggregation",
+                "genevector._graph_targets"):
+        monkeypatch.delitem(sys.modules, sub, raising=False)
+    refm = importlib.import_module("genevector.metrics")
+    refd = importlib.import_module("genevector.data")
+    refc = importlib.import_module("genevector.cache")
+    D = refd.GeneVectorDataset
+    orig_btt, orig_save = D.__dict__["_build_training_tensors"], refc.save_scores
+    ours.install_into_reference(refm, refd, refc)
+    assert refm.TARGETS["mi"] is ours.TARGETS["mi"]
+    assert D.__dict__["_build_training_tensors"] is our_data.dataset_build_training_tensors
+    assert D.__dict__["_build_training_tensors_reference"] is orig_btt
+    assert D.get_gene_entropy is our_data.dataset_get_gene_entropy
+    assert D.__dict__["load_target_scores"] is our_data.dataset_load_target_scores
+    assert refc.save_scores is our_cache.save_scores and refc.save_scores_reference is orig_save
+    assert refc.load_scores is our_cache.load_scores
+    ours.install_into_reference(refm, refd, refc)                       # idempotent: originals are kept
+    assert D.__dict__["_build_training_tensors_reference"] is orig_btt and refc.save_scores_reference is orig_save
+    # a side-loaded nested dict (GeneVectorDataset.load_targets) still takes the reference's own loop
+    genes = ["A", "B", "C"]
+    d = collections.defaultdict(lambda: collections.defaultdict(float))
+    d["A"]["B"] = d["B"]["A"] = 0.5
+    ds = object.__new__(D)
+    ds.data = types.SimpleNamespace(genes=genes)
+    ds.mi_scores, ds.signed_mi, ds.device = d, True, "cpu"
+    ds._build_training_tensors(10.0)
+    assert ds._xij.tolist() == [50.0, 0.0, 50.0, 0.0, 0.0, 0.0]
+    # the cache round trip of the installed functions on a ScoreMatrix, through the reference's own
+    # _compute_target_scores protocol (data.py:300-334): key -> save -> load
+    monkeypatch.setattr(our_cache, "CACHE_DIR", str(tmp_path))
+    M = np.array([[0, .12345678, -.5], [.12345678, 0, .25], [-.5, .25, 0]], dtype=np.float32)
+    key = refc.compute_cache_key(np.eye(3), genes, "mi", {}, True)
+    refc.save_scores(key, ScoreMatrix(M, genes), genes)
+    back, g2 = refc.load_scores(key)
+    assert g2 == genes and isinstance(back, ScoreMatrix) and back["A"]["B"] == 0.12346 and back["A"]["C"] == -0.5
+
+
 def test_count_packer_matches_numpy_and_refuses_what_does_not_fit():
     """gv_pack_counts_host (the staging pass of gv_upload_packed_counts, host to host): float32 counts ->
     uint8, int32 columns -> uint16, in order, for lengths around the 32-entry vector width; anything that

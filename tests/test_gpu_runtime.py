@@ -204,6 +204,84 @@ def test_packed_count_upload_gives_the_same_bin_block(engine, vmax):
     assert not engine.upload_csr(X64, pack=True).packed
 
 
+@pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "ref_poisson_500x20_b5", "synth_counts_700x96_b10",
+                                  "synth_counts_400x30_b15", "lognorm_f32_300x40_b7"])
+def test_compute_mi_pairs_entry_matches_the_reference_goldens(engine, case):
+    """gv_compute_mi_pairs -- the reference's FFI shape (src/lib.rs:9-15): the golden x_disc and
+    n_bins_per_gene (outputs of the reference's discretize_genes) in, mi_raw (the reference's own MI) out
+    within 1e-6; with a correlation matrix the Rust tier's sign rule (C port of src/lib.rs, oracle)."""
+    from conftest import load_golden
+    from genevector_b200.rust_compat import compute_mi_pairs, compute_mi_pairs_matrix
+    from oracle import oracle as orc
+    z = load_golden(case)
+    xd, nb = z["x_disc"].astype(np.int32), z["n_bins_per_gene"].astype(np.int32)
+    for operand in ("auto", "int8"):
+        got, n_pairs = compute_mi_pairs_matrix(xd, nb, operand=operand)
+        assert np.abs(got.astype(np.float64) - z["mi_raw"]).max() <= 1e-6, operand
+        k = int((nb > 1).sum())
+        assert n_pairs == k * (k - 1) // 2
+    corr = orc.pearson_sign_np(z["X"]).astype(np.float32)
+    want, n_want = orc.mi_pairs_c(xd, nb, corr=corr.astype(np.float64), sign_mode=2)
+    got, n_pairs = compute_mi_pairs_matrix(xd, nb, corr)
+    assert np.abs(got.astype(np.float64) - want).max() <= 1e-6 and n_pairs == n_want
+    triples = compute_mi_pairs(xd, nb, corr)
+    assert len(triples) == n_want and all(i < j for i, j, _ in triples)
+    i, j, v = triples[len(triples) // 2]
+    assert abs(v - want[i, j]) <= 1e-6
+    bad = xd.copy()
+    bad[3, 1] = nb[1]                                    # a bin index the gene cannot have
+    with pytest.raises(Exception, match="bin index"):
+        compute_mi_pairs_matrix(bad, nb)
+
+
+def test_reference_shaped_dataset_flow_at_5000_genes(engine, tmp_path, monkeypatch):
+    """The flow of GeneVectorDataset.create_inputs_outputs (data.py:336-375) with the functions
+    install_into_reference binds onto the reference's classes, at 5,000 genes x 50,000 cells (C3): gene
+    entropy -> target scores through the registry and the cache protocol -> training tensors -> cache hit
+    -> .npz round trip, in seconds and without a Python loop over gene pairs."""
+    import time
+    import types
+    import torch
+    from genevector_b200 import cache as our_cache, data as our_data
+    from genevector_b200.scores import ScoreMatrix
+    from genevector_b200.synth import synth_counts_torch, gene_names
+    import scipy.sparse as sp
+    monkeypatch.setattr(our_cache, "CACHE_DIR", str(tmp_path))
+    G, N = 5000, 50000
+    v, c, p = synth_counts_torch(N, G, seed=2, device=engine.device)
+    X = sp.csr_matrix((v.cpu().numpy(), c.cpu().numpy(), p.cpu().numpy()), shape=(N, G))
+    genes = gene_names(G)
+    adata = types.SimpleNamespace(X=X, var=types.SimpleNamespace(index=types.SimpleNamespace(tolist=lambda: genes)))
+    ds = types.SimpleNamespace(adata=adata, data=types.SimpleNamespace(genes=genes), device="cuda", signed_mi=True,
+                               mi_scores=None)
+    t0 = time.perf_counter()
+    ent = our_data.dataset_get_gene_entropy(adata)                                   # data.py:349
+    assert len(ent) == G and all(np.isfinite(e) for e in list(ent.values())[:50])
+    ds.mi_scores = our_data.compute_target_scores(X, genes, target="mi", signed_mi=True, mi_backend="b200",
+                                                  device="cuda", use_cache=True)     # data.py:353-354
+    assert isinstance(ds.mi_scores, ScoreMatrix)
+    our_data.dataset_build_training_tensors(ds, c=100.0)                             # data.py:372
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert ds._xij.shape == (G * (G - 1),) and ds._i_idx.dtype == torch.int64 and ds._xij.is_cuda
+    # spot check against the mapping semantics the reference's loop reads (data.py:383-390)
+    for k in (0, 12345, G * (G - 1) - 1):
+        i, j = int(ds._i_idx[k]), int(ds._j_idx[k])
+        assert abs(float(ds._xij[k]) - np.float32(ds.mi_scores[genes[i]][genes[j]]) * np.float32(1e4)) <= 1e-2
+    # second call: served by the cache file the first one wrote (same key as the reference's)
+    t1 = time.perf_counter()
+    again = our_data.compute_target_scores(X, genes, target="mi", signed_mi=True, mi_backend="b200",
+                                           device="cuda", use_cache=True)
+    dt_hit = time.perf_counter() - t1
+    assert np.abs(again.matrix - ds.mi_scores.rounded()).max() <= 1e-6
+    our_data.dataset_save_target_scores(ds, "run/scores.npz")
+    ds2 = types.SimpleNamespace(mi_scores=None)
+    our_data.dataset_load_target_scores(ds2, our_cache.get_cache_path("run_scores"))
+    assert np.array_equal(ds2.mi_scores.matrix, again.matrix)
+    print(f"entropy + scores + cache save + training tensors: {dt:.2f} s; cache hit: {dt_hit:.2f} s")
+    assert dt < 60.0
+
+
 def test_public_call_reuses_its_pinned_result_buffers(engine):
     """compute_mi_b200 twice: results are independent objects (the first stays valid after the second)."""
     from genevector_b200.metrics import compute_mi_b200
