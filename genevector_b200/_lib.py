@@ -18,12 +18,13 @@ GV_F32, GV_F64, GV_COUNTS_U8_COL16 = 0, 1, 2
 GV_MOM_SIGN, GV_MOM_PEARSON, GV_MOM_COSINE, GV_MOM_JACCARD = 0, 1, 2, 3
 GV_PATH_AUTO, GV_PATH_COUNTS, GV_PATH_GENERAL = 0, 1, 2
 GV_VAL_COUNTS, GV_VAL_DETECTED, GV_VAL_FIXED_POINT, GV_VAL_RANKS = 0, 1, 2, 3
-GV_MARG_STRIDE = 16
-GV_EDGE_STRIDE = 16
-GV_EDGE_SCALE_SLOT = 15
-GV_EDGE_OFFSET_SLOT = 14
-GV_QTABLE_DIM = 16
-GV_ABI_VERSION = 5
+GV_MAX_BINS = 31
+GV_MARG_STRIDE = 32
+GV_EDGE_STRIDE = 32
+GV_EDGE_SCALE_SLOT = 31
+GV_EDGE_OFFSET_SLOT = 30
+GV_QTABLE_DIM = 32
+GV_ABI_VERSION = 6
 GV_OPERAND_INT8, GV_OPERAND_FP4 = 0, 1
 GV_ERR_TIMEOUT = -5
 

@@ -190,16 +190,18 @@ int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
 }
 
 int gv_rows_per_gene(int n_bins) {
-  if (n_bins < 1 || n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
+  if (n_bins < 1 || n_bins > GV_MAX_BINS) return set_error(GV_ERR_ARG, "n_bins must be in [1,31]");
   if (n_bins <= 5) return 5;
   if (n_bins <= 8) return 8;
   if (n_bins <= 10) return 10;
-  return 16;
+  if (n_bins <= 15) return 16;
+  return 32;
 }
 
 int64_t gv_onehot_rows(int n_genes, int rows_per_gene) {
-  if (rows_per_gene != 5 && rows_per_gene != 8 && rows_per_gene != 10 && rows_per_gene != 16)
-    return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10 or 16");
+  if (rows_per_gene != 5 && rows_per_gene != 8 && rows_per_gene != 10 && rows_per_gene != 16 &&
+      rows_per_gene != 32)
+    return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10, 16 or 32");
   const int gpb = 32 / rows_per_gene;
   return int64_t((n_genes + gpb - 1) / gpb) * 32;
 }

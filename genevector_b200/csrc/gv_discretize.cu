@@ -161,13 +161,15 @@ __global__ void k_scatter(const T* __restrict__ values, const int32_t* __restric
 }
 
 // ---------------------------------------------------------------- k_gene_bins
-constexpr int EDGE_SCALE_SLOT = 15;   // GV_EDGE_SCALE_SLOT
+constexpr int EDGE_SCALE_SLOT = GV_EDGE_SCALE_SLOT;
 constexpr int GB_THREADS = 256;
 constexpr int H0_BITS = 11;
 constexpr int H0_SIZE = 1 << H0_BITS;
-constexpr int MAX_T = 32;            // >= 2*(15-1) order statistics
-constexpr int SET_CAP = 64;          // distinct-value set capacity (n_bins <= 15)
+constexpr int SET_CAP = 64;          // distinct-value set capacity (n_bins <= 31)
 
+// WIDE = n_bins 16..31: up to 30 edges (60 order statistics) and one byte per cell in the bin matrix;
+// otherwise up to 14 edges and two cells per byte.  MAX_T >= 2 * edges.
+template <int MAX_T>
 struct GeneSmem {
   uint32_t h0[H0_SIZE];              // level-0 histogram, then its exclusive scan
   uint32_t hs[MAX_T][256];           // per-slot digit histograms of a refinement pass
@@ -180,8 +182,8 @@ struct GeneSmem {
   uint32_t tgt_rank[MAX_T];
   int tgt_slot[MAX_T];
   int tgt_done[MAX_T];
-  double edges[16];
-  uint32_t marg[16];
+  double edges[EDGE_STRIDE_];
+  uint32_t marg[MARG_STRIDE_];
   uint32_t scan_tmp[GB_THREADS];
   unsigned long long red[GB_THREADS / 32][2];
   unsigned long long kmax[GB_THREADS / 32];
@@ -190,7 +192,7 @@ struct GeneSmem {
   int n_undone;
 };
 
-template <typename T>
+template <typename T, bool WIDE>
 __global__ void __launch_bounds__(GB_THREADS)
 k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_cell,
             const T* __restrict__ g_val, int G, int n_bins, const double* __restrict__ q_table,
@@ -200,7 +202,10 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
             int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode, int limb_bits,
             int n_limbs, int64_t n_cells) {
   using K = ValKey<T>;
-  __shared__ GeneSmem sm;
+  constexpr int NE = WIDE ? 30 : 14;              // most edges a gene can have
+  constexpr int MAX_T = WIDE ? 64 : 32;
+  extern __shared__ __align__(16) uint8_t gb_smem[];
+  GeneSmem<MAX_T>& sm = *reinterpret_cast<GeneSmem<MAX_T>*>(gb_smem);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
@@ -214,13 +219,13 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
         gsum[g] = 0; gsq[g] = 0;
       }
       if (tid < MARG_STRIDE_) marg[int64_t(g) * MARG_STRIDE_ + tid] = 0;
-      if (tid < 16) edges_out[int64_t(g) * 16 + tid] = tid == EDGE_SCALE_SLOT ? 1.0 : DBL_MAX;
+      if (tid < EDGE_STRIDE_) edges_out[int64_t(g) * EDGE_STRIDE_ + tid] = tid == EDGE_SCALE_SLOT ? 1.0 : DBL_MAX;
       continue;
     }
     // ---- pass 0: level-0 histogram, distinct set, integer sums
     for (int i = tid; i < H0_SIZE; i += GB_THREADS) sm.h0[i] = 0;
     if (tid < SET_CAP) sm.set[tid] = 0;
-    if (tid < 16) sm.marg[tid] = 0;
+    if (tid < MARG_STRIDE_) sm.marg[tid] = 0;
     if (tid == 0) sm.n_distinct = 0;
     __syncthreads();
     unsigned long long kmax = 0;
@@ -255,13 +260,13 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
     const int k = n_dist < n_bins ? n_dist : n_bins;     // metrics.py:59
     const int n_edges = k > 1 ? k - 1 : 0;
     const int nt = 2 * n_edges;
-    if (tid < 16) sm.edges[tid] = DBL_MAX;
+    if (tid < EDGE_STRIDE_) sm.edges[tid] = DBL_MAX;
 
     if (n_edges > 0) {
       // ---- target ranks (numpy _get_indexes: floor(vi), floor(vi)+1, clamped at the top)
       if (tid < nt) {
         const int ei = tid >> 1;
-        const double q = q_table[k * 16 + ei];
+        const double q = q_table[k * QT_DIM_ + ei];
         const double vi = __dmul_rn(double(m - 1), q);
         int64_t rank;
         if (vi >= double(m - 1)) rank = m - 1;
@@ -364,7 +369,7 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
       }
       // ---- edges (numpy _lerp)
       if (tid < n_edges) {
-        const double q = q_table[k * 16 + tid];
+        const double q = q_table[k * QT_DIM_ + tid];
         const double vi = __dmul_rn(double(m - 1), q);
         const T a = K::val(sm.tgt_val[2 * tid]);
         const T b = K::val(sm.tgt_val[2 * tid + 1]);
@@ -397,8 +402,9 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
       const double vd = double(v);
       int bin = 1;
 #pragma unroll
-      for (int t = 0; t < 14; ++t) bin += (t < n_edges && sm.edges[t] <= vd) ? 1 : 0;
-      atomicOr(&brow[cell >> 3], uint32_t(bin) << ((cell & 7) * 4));
+      for (int t = 0; t < NE; ++t) bin += (t < n_edges && sm.edges[t] <= vd) ? 1 : 0;
+      if constexpr (WIDE) reinterpret_cast<uint8_t*>(brow)[cell] = uint8_t(bin);
+      else atomicOr(&brow[cell >> 3], uint32_t(bin) << ((cell & 7) * 4));
       atomicAdd(&sm.marg[bin], 1u);
       // the integer behind the value rows and the per-gene sums
       unsigned long long xi;
@@ -437,12 +443,12 @@ k_gene_bins(const int64_t* __restrict__ gene_ptr, const int32_t* __restrict__ g_
     if (tid == 0) {
       n_bins_per_gene[g] = (k <= 1) ? 2 : k + 1;             // metrics.py:62,67
       marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
-    } else if (tid < 16) {
+    } else if (tid < MARG_STRIDE_) {
       marg[int64_t(g) * MARG_STRIDE_ + tid] = int32_t(sm.marg[tid]);
     }
-    // slot 15 is never an edge (n_bins <= 15): it carries the real value of one value-row unit
-    if (tid < 16)
-      edges_out[int64_t(g) * 16 + tid] =
+    // slots 30 / 31 are never edges (n_bins <= 31): 31 carries the real value of one value-row unit
+    if (tid < EDGE_STRIDE_)
+      edges_out[int64_t(g) * EDGE_STRIDE_ + tid] =
           tid == EDGE_SCALE_SLOT ? (val_mode == 2 ? ldexp(1.0, -fx_shift) : 1.0) : sm.edges[tid];
   }
 }
@@ -548,6 +554,36 @@ __global__ void k_expand_onehot_fp4(const uint32_t* __restrict__ bins_packed, in
   }
 }
 
+// One byte per cell (n_bins 16..31): one gene per 32-row block, rows 0..30 = bins 1..31, row 31 zero.
+// Every lane turns 16 cells (16 bytes) into 16 bytes per bin row.
+__global__ void k_expand_onehot_wide(const uint8_t* __restrict__ bins, int64_t pitch_bytes, int G,
+                                     int8_t* __restrict__ onehot, int64_t kp, int n_blocks) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int64_t chunks = (kp + 511) / 512;
+  for (int blk = blockIdx.y; blk < n_blocks; blk += gridDim.y) {
+    for (int64_t ch = int64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); ch < chunks;
+         ch += int64_t(gridDim.x) * warps_per_cta) {
+      const int64_t cell0 = ch * 512 + lane * 16;
+      if (cell0 >= kp) continue;
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (blk < G && cell0 + 16 <= pitch_bytes)
+        w = *reinterpret_cast<const uint4*>(bins + int64_t(blk) * pitch_bytes + cell0);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+      int8_t* obase = onehot + int64_t(blk) * 32 * kp + cell0;
+#pragma unroll
+      for (int b = 0; b < 31; ++b) {
+        const uint32_t pat = uint32_t(b + 1) * 0x01010101u;
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __vcmpeq4(ws[i], pat) & 0x01010101u;
+        *reinterpret_cast<uint4*>(obase + int64_t(b) * kp) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      *reinterpret_cast<uint4*>(obase + int64_t(31) * kp) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 // ================================================================ count-data fast path
 // For non-negative integer data with values <= 255 (scRNA-seq counts, the documented input) the
 // order statistics follow from a per-gene VALUE histogram, and the cell-major -> gene-major regroup
@@ -603,7 +639,7 @@ __global__ void k_hist2d(const T* __restrict__ values, const int32_t* __restrict
 // One warp per gene.  Lane l owns the 8 histogram slots v = 8l .. 8l+7 (c[i] = #cells with value
 // 8l+i; c[0] of lane 0 is ignored).  Writes the value -> bin table (and value -> doubled rank when
 // rank_lut != nullptr) and the per-gene outputs of discretize_genes.
-template <typename T>
+template <typename T, int NE>
 __device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bins,
                               const double* __restrict__ q_table, int64_t n_cells,
                               uint8_t* lut, uint32_t* rank_lut,
@@ -645,9 +681,9 @@ __device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bin
     s2 += __shfl_xor_sync(0xffffffffu, s2, d);
   }
   if (lane == 0) { gsum[g] = s1; gsq[g] = s2; }
-  double edge[14];
+  double edge[NE];
 #pragma unroll
-  for (int t = 0; t < 14; ++t) edge[t] = DBL_MAX;
+  for (int t = 0; t < NE; ++t) edge[t] = DBL_MAX;
   int k = 0, n_edges = 0;
   if (m > 0) {
     k = int(nun) < n_bins ? int(nun) : n_bins;          // metrics.py:59
@@ -668,9 +704,9 @@ __device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bin
       return found;
     };
 #pragma unroll
-    for (int t = 0; t < 14; ++t) {
+    for (int t = 0; t < NE; ++t) {
       if (t < n_edges) {                                 // warp-uniform
-        const double q = q_table[k * 16 + t];
+        const double q = q_table[k * QT_DIM_ + t];
         const double vi = __dmul_rn(double(m - 1), q);
         int64_t ra, rb; double gam;
         if (vi >= double(m - 1)) { ra = rb = m - 1; gam = __dadd_rn(vi, 1.0); }
@@ -684,34 +720,34 @@ __device__ void gene_lut_warp(const uint32_t (&c)[8], int lane, int g, int n_bin
     }
   }
   // lookup table + marginals
-  uint32_t mg[16];
+  uint32_t mg[NE + 2];
 #pragma unroll
-  for (int a = 0; a < 16; ++a) mg[a] = 0;
+  for (int a = 0; a < NE + 2; ++a) mg[a] = 0;
   uint32_t packed[2] = {0, 0};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const double vd = double(lane * 8 + i);
     int bin = 1;
 #pragma unroll
-    for (int t = 0; t < 14; ++t) bin += (t < n_edges && edge[t] <= vd) ? 1 : 0;
+    for (int t = 0; t < NE; ++t) bin += (t < n_edges && edge[t] <= vd) ? 1 : 0;
     if (lane * 8 + i == 0) bin = 0;
     packed[i >> 2] |= uint32_t(bin) << ((i & 3) * 8);
 #pragma unroll
-    for (int a = 1; a < 16; ++a) mg[a] += (a == bin) ? c[i] : 0u;
+    for (int a = 1; a < NE + 2; ++a) mg[a] += (a == bin) ? c[i] : 0u;
   }
   *reinterpret_cast<uint2*>(lut + lane * 8) = make_uint2(packed[0], packed[1]);
 #pragma unroll
-  for (int a = 1; a < 16; ++a)
+  for (int a = 1; a < NE + 2; ++a)
     for (int d = 16; d >= 1; d >>= 1) mg[a] += __shfl_xor_sync(0xffffffffu, mg[a], d);
   if (lane == 0) {
     n_bins_per_gene[g] = m == 0 ? 1 : (k <= 1 ? 2 : k + 1);   // metrics.py:55-57,62,67
     marg[int64_t(g) * MARG_STRIDE_] = int32_t(m);
 #pragma unroll
-    for (int a = 1; a < 16; ++a) marg[int64_t(g) * MARG_STRIDE_ + a] = int32_t(mg[a]);
+    for (int a = 1; a < MARG_STRIDE_; ++a) marg[int64_t(g) * MARG_STRIDE_ + a] = a < NE + 2 ? int32_t(mg[a < NE + 2 ? a : 0]) : 0;
 #pragma unroll
-    for (int t = 0; t < 14; ++t) edges_out[int64_t(g) * 16 + t] = edge[t];
-    edges_out[int64_t(g) * 16 + 14] = DBL_MAX;
-    edges_out[int64_t(g) * 16 + EDGE_SCALE_SLOT] = 1.0;   // one value-row unit = 1 (counts, ranks)
+    for (int t = 0; t < EDGE_STRIDE_; ++t)
+      edges_out[int64_t(g) * EDGE_STRIDE_ + t] = t < NE ? edge[t < NE ? t : 0] : DBL_MAX;
+    edges_out[int64_t(g) * EDGE_STRIDE_ + EDGE_SCALE_SLOT] = 1.0;   // one value-row unit = 1 (counts, ranks)
   }
 }
 
@@ -871,7 +907,7 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
 // ---------------------------------------------------------------- k_rows_to_bins
 constexpr int RB_THREADS = 256;
 
-template <typename T>
+template <typename T, bool WIDE = false>
 __global__ void __launch_bounds__(RB_THREADS, 4)
 k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, int64_t n_cells, int G,
                int n_bins, const double* __restrict__ q_table, uint32_t* __restrict__ bins_packed,
@@ -893,8 +929,8 @@ k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, i
       for (int i = 0; i < 8; ++i) {
         c[i] = (lane * 8 + i) ? ghist[int64_t(g) * VH + lane * 8 + i] : 0u;
       }
-      gene_lut_warp<T>(c, lane, g, n_bins, q_table, n_cells, lut, ranks ? rlut : nullptr,
-                       n_bins_per_gene, marg, edges_out, gsum, gsq);
+      gene_lut_warp<T, WIDE ? 30 : 14>(c, lane, g, n_bins, q_table, n_cells, lut, ranks ? rlut : nullptr,
+                                       n_bins_per_gene, marg, edges_out, gsum, gsq);
     }
     __syncthreads();
     // ---- one sweep of the row: packed bins and, when they are not `raw` itself, value rows
@@ -907,16 +943,31 @@ k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, i
     for (int64_t i = tid; i < n16; i += RB_THREADS) {
       const uint4 w = row[i];
       const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-      uint32_t pk[2] = {0u, 0u};
+      if constexpr (WIDE) {
+        // one byte per cell: the bins of 16 cells are 16 bytes
+        uint32_t o[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t x = ws[k];
-        if (x == 0u) continue;
+        for (int k = 0; k < 4; ++k) {
+          uint32_t acc = 0u;
+          if (ws[k] != 0u) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          pk[k >> 1] |= uint32_t(lut[(x >> (8 * b)) & 0xffu]) << (((k & 1) * 4 + b) * 4);
+            for (int b = 0; b < 4; ++b) acc |= uint32_t(lut[(ws[k] >> (8 * b)) & 0xffu]) << (8 * b);
+          }
+          o[k] = acc;
+        }
+        reinterpret_cast<uint4*>(brow)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      } else {
+        uint32_t pk[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t x = ws[k];
+          if (x == 0u) continue;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            pk[k >> 1] |= uint32_t(lut[(x >> (8 * b)) & 0xffu]) << (((k & 1) * 4 + b) * 4);
+        }
+        brow[i] = make_uint2(pk[0], pk[1]);
       }
-      brow[i] = make_uint2(pk[0], pk[1]);
       if (detect) {
         uint32_t o[4];
 #pragma unroll
@@ -1003,7 +1054,7 @@ __global__ void k_gene_entropy(const uint32_t* __restrict__ hist, int G, int64_t
 // hold q0_g = rint(-o_g * 2^e_g), written by a row fill before the stored entries are scattered.
 // edges[g][14] carries q0_g (cosine, which is not shift-invariant, subtracts it again) and
 // edges[g][15] the unit 2^-e_g.
-constexpr int EDGE_OFFSET_SLOT = 14;   // GV_EDGE_OFFSET_SLOT
+constexpr int EDGE_OFFSET_SLOT = GV_EDGE_OFFSET_SLOT;
 
 __device__ __forceinline__ unsigned long long ordered_key(double v) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -1057,8 +1108,8 @@ __global__ void k_signed_params(SignedGene* __restrict__ sg, int G, int total_bi
       q0 = q0 > cap ? cap : q0;
     }
     sg[g].offset = o; sg[g].shift = shift; sg[g].q0 = q0;
-    edges_out[int64_t(g) * 16 + EDGE_OFFSET_SLOT] = q0 ? double(q0) : DBL_MAX;
-    edges_out[int64_t(g) * 16 + EDGE_SCALE_SLOT] = ldexp(1.0, -shift);
+    edges_out[int64_t(g) * EDGE_STRIDE_ + EDGE_OFFSET_SLOT] = q0 ? double(q0) : DBL_MAX;
+    edges_out[int64_t(g) * EDGE_STRIDE_ + EDGE_SCALE_SLOT] = ldexp(1.0, -shift);
   }
 }
 
@@ -1267,7 +1318,7 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   size_t off = 0;
   auto take = [&](size_t bytes) { void* p = ws + off; off += al256(bytes); return p; };
   unsigned long long* flags = static_cast<unsigned long long*>(take(64));
-  double* qtab = static_cast<double*>(take(16 * 16 * 8));
+  double* qtab = static_cast<double*>(take(QT_DIM_ * QT_DIM_ * 8));
   const size_t front = off;
   const VT* values = static_cast<const VT*>(a.values);
   const CT* col_idx = reinterpret_cast<const CT*>(a.col_idx);
@@ -1277,9 +1328,10 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
   const bool ranks = val_rows != nullptr && a.val_mode == 3;
 
   GV_CUDA_TRY(cudaMemsetAsync(flags, 0, 64, st));
-  GV_CUDA_TRY(cudaMemcpyAsync(qtab, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st));
+  GV_CUDA_TRY(cudaMemcpyAsync(qtab, a.q_table, QT_DIM_ * QT_DIM_ * 8, cudaMemcpyHostToDevice, st));
   unsigned long long hflags[2] = {0, 0};
-  const int64_t kcells = a.bins_pitch_bytes * 2;     // cells covered by a packed-bin row
+  const bool wide = a.n_bins > 15;                   // one byte per cell in the bin matrix
+  const int64_t kcells = wide ? a.bins_pitch_bytes : a.bins_pitch_bytes * 2;     // cells covered by a bin row
 
   // ---------------- count-data fast path (tried first unless the caller forces the general one;
   // fixed-point value rows are for data that are not counts, so they go straight to the general path)
@@ -1323,7 +1375,8 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
           GV_CUDA_TRY(cudaMemsetAsync(val_rows + used * a.val_pitch, 0,
                                       size_t(a.val_rows_alloc - used) * a.val_pitch, st));
       }
-      k_rows_to_bins<T><<<G < sms * 8 ? G : sms * 8, RB_THREADS, 0, st>>>(
+      auto kr = wide ? k_rows_to_bins<T, true> : k_rows_to_bins<T, false>;
+      kr<<<G < sms * 8 ? G : sms * 8, RB_THREADS, 0, st>>>(
           raw, kcells, kcells, a.n_cells, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
           int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
           a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, ghist);
@@ -1389,12 +1442,17 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     if (rc != GV_OK) return rc;
     g_cell = s_cell; g_val = s_val;
   }
-  k_gene_bins<T><<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, 0, st>>>(
-      gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
-      int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq,
-      (signed_rows || signed_ranks) ? nullptr : val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs,
-      a.n_cells);
-  GV_LAUNCH_CHECK();
+  {
+    auto kg = wide ? k_gene_bins<T, true> : k_gene_bins<T, false>;
+    const size_t gsm = wide ? sizeof(GeneSmem<64>) : sizeof(GeneSmem<32>);
+    GV_CUDA_TRY(cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsm)));
+    kg<<<G < sms * 16 ? (G > 0 ? G : 1) : sms * 16, GB_THREADS, gsm, st>>>(
+        gene_ptr, g_cell, g_val, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
+        int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq,
+        (signed_rows || signed_ranks) ? nullptr : val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs,
+        a.n_cells);
+    GV_LAUNCH_CHECK();
+  }
   if (signed_ranks) {
     // second regroup with every stored entry (the buffers of the first one are free again), sorted
     SignedGene* sg = static_cast<SignedGene*>(take(size_t(G) * sizeof(SignedGene)));
@@ -1754,7 +1812,7 @@ static int shard_bins_impl(const DiscretizeArgs& a, const uint8_t* raw, const ui
   HistSrcs srcs;
   srcs.n = n_hists;
   for (int p = 0; p < n_hists; ++p) srcs.h[p] = hists[p];
-  GV_CUDA_TRY(cudaMemcpyAsync(qtab_dev, a.q_table, 16 * 16 * 8, cudaMemcpyHostToDevice, st));
+  GV_CUDA_TRY(cudaMemcpyAsync(qtab_dev, a.q_table, QT_DIM_ * QT_DIM_ * 8, cudaMemcpyHostToDevice, st));
   k_sum_hists<<<sms * 4, 256, 0, st>>>(srcs, int64_t(G) * VH, ghist_total);
   GV_LAUNCH_CHECK();
   if (val_rows != nullptr && a.val_rows_alloc > G)
@@ -1772,7 +1830,8 @@ static int shard_bins_impl(const DiscretizeArgs& a, const uint8_t* raw, const ui
 int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
                         uint32_t* ghist_total, double* qtab_dev, cudaStream_t st) {
   if (n_hists < 1 || n_hists > TP_MAX_PEERS) return set_error(GV_ERR_ARG, "shard bins: 1..8 histograms");
-  if (a.n_bins < 1 || a.n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
+  if (a.n_bins < 1 || a.n_bins > 15)
+    return set_error(GV_ERR_UNSUPPORTED, "the sharded front end covers n_bins in [1,15] (4-bit bins)");
   if (a.val_rows != nullptr && (a.val_mode != 0 || a.val_limbs != 1 || a.val_rows != raw ||
                                 a.val_pitch != a.bins_pitch_bytes * 2))
     return set_error(GV_ERR_ARG, "shard bins: value rows must be the dense count rows themselves (one digit)");
@@ -1783,9 +1842,10 @@ int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint3
 }
 
 int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
-  if (a.n_bins < 1 || a.n_bins > 15) return set_error(GV_ERR_ARG, "n_bins must be in [1,15]");
-  if (a.bins_pitch_bytes % 16 != 0 || int64_t(a.bins_pitch_bytes) * 2 < a.n_cells)
-    return set_error(GV_ERR_ARG, "bins pitch must be a multiple of 16 bytes covering n_cells/2");
+  if (a.n_bins < 1 || a.n_bins > GV_MAX_BINS) return set_error(GV_ERR_ARG, "n_bins must be in [1,31]");
+  if (a.bins_pitch_bytes % 16 != 0 || int64_t(a.bins_pitch_bytes) * (a.n_bins > 15 ? 1 : 2) < a.n_cells)
+    return set_error(GV_ERR_ARG, "bins pitch must be a multiple of 16 bytes covering n_cells (n_cells/2 when "
+                                 "n_bins <= 15)");
   if (a.value_dtype == GV_F32) return discretize_impl<float>(a, st);
   if (a.value_dtype == GV_F64) return discretize_impl<double>(a, st);
   if (a.value_dtype == GV_COUNTS_U8_COL16) return discretize_impl<float, true>(a, st);
@@ -1796,7 +1856,7 @@ int discretize_dispatch(const DiscretizeArgs& a, cudaStream_t st) {
 // Sized for packed-bin rows of the engine's pitch (n_cells rounded up to 256 cells).
 size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value_dtype, int sorted) {
   const size_t vs = value_dtype == GV_F64 ? 8 : 4;
-  const size_t front = al256(64) + al256(16 * 16 * 8);
+  const size_t front = al256(64) + al256(QT_DIM_ * QT_DIM_ * 8);
   const size_t kcells = (size_t(n_cells > 0 ? n_cells : 1) + 255) / 256 * 256;
   const size_t counts = al256(size_t(G) * kcells) + al256(size_t(G) * VH * 4);
   const size_t entropy = al256(size_t(G) * VH * 4);
@@ -1831,6 +1891,16 @@ int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, 
   }
   if (operand_format != GV_OPERAND_INT8) return set_error(GV_ERR_ARG, "unknown operand format");
   if (kp % 128 != 0) return set_error(GV_ERR_ARG, "expand: K extent must be a multiple of 128");
+  if (rows_per_gene == 32) {
+    if (pitch_bytes % 16 != 0 || pitch_bytes < kp)
+      return set_error(GV_ERR_ARG, "expand: bins pitch must cover the padded K extent (one byte per cell)");
+    const int64_t wchunks = (kp + 511) / 512;
+    dim3 wgrid((unsigned)((wchunks + 7) / 8), (unsigned)(n_blocks < 65535 ? n_blocks : 65535));
+    k_expand_onehot_wide<<<wgrid, 256, 0, st>>>(static_cast<const uint8_t*>(bins_packed), pitch_bytes, G,
+                                                static_cast<int8_t*>(onehot), kp, n_blocks);
+    GV_LAUNCH_CHECK();
+    return GV_OK;
+  }
   if (pitch_bytes % 16 != 0 || pitch_bytes * 2 < kp)
     return set_error(GV_ERR_ARG, "expand: bins pitch must cover the padded K extent");
   const int64_t chunks = (kp + 1023) / 1024;
@@ -1841,7 +1911,7 @@ int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, 
     case 8:  k_expand_onehot<8><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
     case 10: k_expand_onehot<10><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
     case 16: k_expand_onehot<16><<<grid, 256, 0, st>>>(bp, pitch_bytes / 4, G, oh, kp, n_blocks); break;
-    default: return set_error(GV_ERR_ARG, "expand: rows_per_gene must be 5, 8, 10 or 16");
+    default: return set_error(GV_ERR_ARG, "expand: rows_per_gene must be 5, 8, 10, 16 or 32");
   }
   GV_LAUNCH_CHECK();
   return GV_OK;

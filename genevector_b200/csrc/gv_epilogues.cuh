@@ -13,7 +13,8 @@
 
 namespace gv {
 
-constexpr int MARG_STRIDE = 16;  // int32 per gene: [0] = #cells with x>0, [a] = #cells in bin a
+constexpr int MARG_STRIDE = 32;  // int32 per gene: [0] = #cells with x>0, [a] = #cells in bin a (GV_MARG_STRIDE)
+constexpr int EDGE_STRIDE = 32;  // float64 per gene (GV_EDGE_STRIDE); slot 30 = value-row integer of a zero cell
 
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(GRAM_EPI_BAR), "n"(GRAM_EPI_WARPS * 32) : "memory");
@@ -127,7 +128,7 @@ struct MiEpi {
       const int sj = within / B, b = within - sj * B;
       const int gj = ((et.col0 >> 5) + blk) * GPB + sj;
       if (gj < p.G) {
-        if (1 + b < MARG_STRIDE) m = p.marg[int64_t(gj) * MARG_STRIDE + 1 + b];  // B=16: bin 16 never occurs
+        if (1 + b < MARG_STRIDE) m = p.marg[int64_t(gj) * MARG_STRIDE + 1 + b];  // B=32: bin 32 never occurs
         if (b == 0) meta->cg_nnz[blk * GPB + sj] = p.marg[int64_t(gj) * MARG_STRIDE];
       } else if (b == 0) {
         meta->cg_nnz[blk * GPB + sj] = 0;
@@ -240,7 +241,7 @@ struct MomentParams {
   const int64_t* gsum;   // [G] Sum_c x            (sign / pearson / cosine)
   const int64_t* gsq;    // [G] Sum_c x^2          (sign / pearson / cosine)
   const int32_t* marg;   // [G][MARG_STRIDE], [0] = #cells with x>0 (jaccard)
-  const double* edges;   // [G][16] or nullptr: slot 14 = value-row integer of a zero cell (cosine)
+  const double* edges;   // [G][32] or nullptr: slot 30 = value-row integer of a zero cell (cosine)
   int8_t* sgn;           // [G][ld_sgn]  (MOM_SIGN)
   int64_t ld_sgn;
   float* out;            // [G][ld_out]  (other kinds)
@@ -291,7 +292,7 @@ struct MomentEpi {
   // value-row integer of the gene's zero cells (genes with negative values are stored shifted)
   __device__ int64_t zero_offset(int g) const {
     if (p.edges == nullptr) return 0;
-    const double o = p.edges[int64_t(g) * 16 + 14];
+    const double o = p.edges[int64_t(g) * EDGE_STRIDE + 30];
     return o < 1e300 ? int64_t(o) : 0;
   }
   __device__ void prepare(const EpiTile& et) {

@@ -7,7 +7,9 @@
 
 namespace gv {
 
-constexpr int MARG_STRIDE_ = 16;   // must equal MARG_STRIDE in gv_epilogues.cuh / GV_MARG_STRIDE
+constexpr int MARG_STRIDE_ = GV_MARG_STRIDE;   // int32 per gene in `marg`
+constexpr int EDGE_STRIDE_ = GV_EDGE_STRIDE;   // float64 per gene in `edges`
+constexpr int QT_DIM_ = GV_QTABLE_DIM;         // the quantile-fraction table is [QT_DIM_][QT_DIM_]
 
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* file, int line);
@@ -17,7 +19,7 @@ struct DiscretizeArgs {
   const void* values; int value_dtype;
   const int32_t* col_idx; const int64_t* row_ptr;
   int64_t n_cells; int n_genes; int64_t nnz; int n_bins;
-  const double* q_table;            // host, [16][16]
+  const double* q_table;            // host, [32][32]
   void* bins_packed; int64_t bins_pitch_bytes;
   int32_t* n_bins_per_gene; int32_t* marg; double* edges;
   int64_t* gsum; int64_t* gsq;

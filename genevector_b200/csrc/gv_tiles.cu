@@ -169,8 +169,9 @@ int mi_tiles_dispatch(const void* onehot, int64_t op_rows, int64_t kp, int rows_
     case 8:  return launch_cg<MiEpi<8>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case 10: return launch_cg<MiEpi<10>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
     case 16: return launch_cg<MiEpi<16>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
+    case 32: return launch_cg<MiEpi<32>>(cta_group, onehot, op_rows, kp, tiles, n_tiles, p, sync_ws, st);
   }
-  return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10 or 16");
+  return set_error(GV_ERR_ARG, "rows_per_gene must be 5, 8, 10, 16 or 32");
 }
 
 int gram_dump_dispatch(const void* operand, int64_t op_rows, int64_t kp, const int32_t* tiles,

@@ -35,7 +35,7 @@ def _align(n: int, a: int = _A) -> int:
 def quantile_table() -> np.ndarray:
     """numpy's own quantile fractions (metrics.py:64 + np.percentile's division by 100)."""
     q = np.zeros((_lib.GV_QTABLE_DIM, _lib.GV_QTABLE_DIM), dtype=np.float64)
-    for k in range(2, 16):
+    for k in range(2, _lib.GV_MAX_BINS + 1):
         q[k, :k - 1] = np.linspace(0, 100, k + 1)[1:-1] / 100
     return q
 
@@ -90,11 +90,11 @@ class BinBlock:
     n_genes: int
     n_bins: int
     kp: int                      # K extent padded to 128
-    bins_pitch: int              # bytes per gene row of the packed bins
+    bins_pitch: int              # bytes per gene row of the bins: kp / 2 (two cells per byte) or kp (n_bins > 15)
     bins: torch.Tensor           # uint8 [G][bins_pitch]
-    marg: torch.Tensor           # int32 [G][16]
+    marg: torch.Tensor           # int32 [G][32]
     n_bins_per_gene: torch.Tensor  # int32 [G]
-    edges: torch.Tensor          # float64 [G][16]
+    edges: torch.Tensor          # float64 [G][32]
     gsum: torch.Tensor           # int64 [G]
     gsq: torch.Tensor            # int64 [G]
     val_rows: Optional[torch.Tensor]   # int8 [value_rows(G, n_limbs)][kp] or None
@@ -119,6 +119,8 @@ class BinBlock:
     def x_disc(self) -> np.ndarray:
         """Unpack to the reference's layout: int32 [n_cells][n_genes] (tests / small cases)."""
         b = self.bins.cpu().numpy()
+        if self.n_bins > 15:                      # one byte per cell
+            return np.ascontiguousarray(b[:, :self.n_cells].T.astype(np.int32))
         lo, hi = b & 0x0F, b >> 4
         full = np.empty((self.n_genes, b.shape[1] * 2), dtype=np.int32)
         full[:, 0::2], full[:, 1::2] = lo, hi
@@ -128,15 +130,17 @@ class BinBlock:
 HEADER_BYTES = 256   # int64[0] = n_limbs, [1] = limb_bits, [2] = data flag bits, [3] = max value, [4] = val_mode
 
 
-def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1):
+def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1, n_bins: int = 10):
     """Byte offsets of the sections of the broadcast block.  The value rows come last, so a
-    two-digit block is the one-digit block plus a tail."""
+    two-digit block is the one-digit block plus a tail.  Bins take half a byte per cell, a whole one
+    when n_bins > 15."""
     kp = _align(max(n_cells, 1), 256)      # a 128-byte K slice of the FP4 operand is 256 cells
-    pitch = kp // 2
+    pitch = kp if n_bins > 15 else kp // 2
+    ms, es = _lib.GV_MARG_STRIDE, _lib.GV_EDGE_STRIDE
     off, lay = 0, {}
     for name, nbytes in (("header", HEADER_BYTES), ("bins", n_genes * pitch),
-                         ("marg", n_genes * 16 * 4), ("nbpg", n_genes * 4),
-                         ("edges", n_genes * 16 * 8), ("gsum", n_genes * 8), ("gsq", n_genes * 8),
+                         ("marg", n_genes * ms * 4), ("nbpg", n_genes * 4),
+                         ("edges", n_genes * es * 8), ("gsum", n_genes * 8), ("gsq", n_genes * 8),
                          ("val", (value_rows(n_genes, n_limbs) * kp) if val_mode >= 0 else 0)):
         lay[name] = (off, nbytes)
         off += _align(nbytes)
@@ -144,7 +148,7 @@ def block_layout(n_cells: int, n_genes: int, val_mode: int, n_limbs: int = 1):
 
 
 def _views(buf, n_cells, n_genes, n_bins, val_mode, n_limbs, limb_bits, flags=(0, 0)) -> BinBlock:
-    kp, pitch, lay, _ = block_layout(n_cells, n_genes, val_mode, n_limbs)
+    kp, pitch, lay, _ = block_layout(n_cells, n_genes, val_mode, n_limbs, n_bins)
 
     def v(name, dtype, shape):
         o, nb = lay[name]
@@ -152,9 +156,10 @@ def _views(buf, n_cells, n_genes, n_bins, val_mode, n_limbs, limb_bits, flags=(0
 
     return BinBlock(
         buf=buf, n_cells=n_cells, n_genes=n_genes, n_bins=n_bins, kp=kp, bins_pitch=pitch,
-        bins=v("bins", torch.uint8, (n_genes, pitch)), marg=v("marg", torch.int32, (n_genes, 16)),
+        bins=v("bins", torch.uint8, (n_genes, pitch)),
+        marg=v("marg", torch.int32, (n_genes, _lib.GV_MARG_STRIDE)),
         n_bins_per_gene=v("nbpg", torch.int32, (n_genes,)),
-        edges=v("edges", torch.float64, (n_genes, 16)), gsum=v("gsum", torch.int64, (n_genes,)),
+        edges=v("edges", torch.float64, (n_genes, _lib.GV_EDGE_STRIDE)), gsum=v("gsum", torch.int64, (n_genes,)),
         gsq=v("gsq", torch.int64, (n_genes,)),
         val_rows=v("val", torch.int8, (value_rows(n_genes, n_limbs), kp)) if val_mode >= 0 else None,
         val_mode=val_mode, n_limbs=n_limbs, limb_bits=limb_bits, data_flags=flags)
@@ -517,8 +522,8 @@ class Engine:
         with fixed-point rows (mode 2) when the data are not integers; 1 detection indicator
         (jaccard); 2 fixed point; 3 doubled average ranks (spearman).  n_limbs fixes the digit count
         (no retry).  The block's val_mode / n_limbs say what was produced."""
-        if not 1 <= n_bins <= 15:
-            raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
+        if not 1 <= n_bins <= _lib.GV_MAX_BINS:
+            raise GvError("discretize", -1, f"n_bins must be in [1, {_lib.GV_MAX_BINS}]")
         if csr.values.dtype not in (torch.float32, torch.float64) and not csr.packed:
             raise GvError("discretize", -1, "values must be float32 or float64")
         with torch.cuda.device(self.device):
@@ -547,7 +552,7 @@ class Engine:
             q = quantile_table()
             mode = val_mode
             while True:
-                kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, mode, L)
+                kp, pitch, lay, total = block_layout(csr.n_cells, csr.n_genes, mode, L, n_bins)
                 b = buf if (buf is not None and buf.numel() >= total) else \
                     torch.empty(total, dtype=torch.uint8, device=self.device)
                 assert b.device == self.device
@@ -852,7 +857,7 @@ class Engine:
         an asynchronous call whose handle is left in blk.pending, so that the caller can expand the
         one-hot operand (which needs the bins only) while they are still on the wire."""
         import torch.distributed as dist
-        _, _, lay, total1 = block_layout(n_cells, n_genes, val_mode, 1)
+        _, _, lay, total1 = block_layout(n_cells, n_genes, val_mode, 1, n_bins)
         if blk_or_none is not None:
             buf = blk_or_none.buf
         else:
@@ -880,7 +885,7 @@ class Engine:
             else:
                 dist.broadcast(buf[val_off:total1], src=src, group=group)
         if L > 1:
-            _, _, _, total_l = block_layout(n_cells, n_genes, val_mode, L)
+            _, _, _, total_l = block_layout(n_cells, n_genes, val_mode, L, n_bins)
             if blk_or_none is None:
                 big = torch.empty(total_l, dtype=torch.uint8, device=self.device)
                 big[:total1].copy_(buf)
@@ -1013,7 +1018,7 @@ class Engine:
         when the data do not qualify (every rank decides the same from the combined data flags)."""
         import ctypes as C
         if not 1 <= n_bins <= 15:
-            raise GvError("discretize", -1, "n_bins must be in [1, 15] (bins are stored in 4 bits)")
+            return None                      # one byte per cell (n_bins 16..31): the broadcast front end
         pb = self._peer_block(n_cells, n_genes, rank, world, pool)
         if pb is None:
             return None

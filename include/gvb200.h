@@ -29,13 +29,14 @@
 extern "C" {
 #endif
 
-#define GV_ABI_VERSION 5
-#define GV_MARG_STRIDE 16 /* int32 per gene in `marg` */
-#define GV_EDGE_STRIDE 16 /* float64 per gene in `edges` */
-#define GV_EDGE_SCALE_SLOT 15 /* edges[g][15]: real value of one unit of the gene's value-row integer */
-#define GV_EDGE_OFFSET_SLOT 14 /* edges[g][14]: value-row integer of a zero cell (DBL_MAX = 0): only
+#define GV_ABI_VERSION 6
+#define GV_MAX_BINS 31    /* n_bins of discretize_genes: 1..31 */
+#define GV_MARG_STRIDE 32 /* int32 per gene in `marg` */
+#define GV_EDGE_STRIDE 32 /* float64 per gene in `edges` (at most 30 edges) */
+#define GV_EDGE_SCALE_SLOT 31 /* edges[g][31]: real value of one unit of the gene's value-row integer */
+#define GV_EDGE_OFFSET_SLOT 30 /* edges[g][30]: value-row integer of a zero cell (DBL_MAX = 0): only
                                   genes with negative values are stored shifted (val_mode 2) */
-#define GV_QTABLE_DIM 16  /* q_table_host is [16][16] float64 */
+#define GV_QTABLE_DIM 32  /* q_table_host is [32][32] float64 */
 
 typedef enum gv_status {
   GV_OK = 0,
@@ -91,12 +92,13 @@ int gv_device_check(void);
  *   values/col_idx/row_ptr : CSR arrays (canonical: no duplicate entries); value_dtype GV_F32/GV_F64
  *   q_table_host[k][t-1]   : np.linspace(0,100,k+1)[1:-1][t-1] / 100 for k = 2..n_bins (host memory;
  *                            numpy's own table so that the quantile fractions match bit for bit)
- *   bins_packed            : out, uint8 [n_genes][bins_pitch_bytes]; cell c of gene g is nibble
- *                            (c & 1) of byte c >> 1 (low nibble first); value 0..n_bins.
- *                            bins_pitch_bytes % 16 == 0 and 2*bins_pitch_bytes >= padded K extent.
+ *   bins_packed            : out, uint8 [n_genes][bins_pitch_bytes]; value 0..n_bins.  n_bins <= 15: two
+ *                            cells per byte, cell c of gene g is nibble (c & 1) of byte c >> 1 (low
+ *                            nibble first), 2*bins_pitch_bytes >= padded K extent.  n_bins 16..31: one
+ *                            byte per cell, bins_pitch_bytes >= padded K extent.  bins_pitch_bytes % 16 == 0.
  *   n_bins_per_gene        : out, int32 [n_genes]  (second return value of discretize_genes)
- *   marg                   : out, int32 [n_genes][16]; [0] = #cells with x > 0, [a] = #cells in bin a
- *   edges                  : out, float64 [n_genes][16] bin edges (unused slots = DBL_MAX); slot
+ *   marg                   : out, int32 [n_genes][32]; [0] = #cells with x > 0, [a] = #cells in bin a
+ *   edges                  : out, float64 [n_genes][32] bin edges (unused slots = DBL_MAX); slot
  *                            GV_EDGE_SCALE_SLOT holds the value-row scale (1.0, or 2^-e_g for val_mode 2)
  *   gsum, gsq              : out, int64 [n_genes]  Sum x and Sum x^2 over cells of the value-row integer
  *   val_rows (optional)    : out, int8 [val_rows_alloc][val_pitch] K-major operand of gv_moment_tiles:
@@ -121,7 +123,7 @@ int gv_device_check(void);
  *                            sorted = 1 when val_mode is 3 (the rank rows of non-count data need a
  *                            per-gene sort: twice the regroup scratch)
  *   path / path_used_host  : gv_disc_path to use; the one taken is written to *path_used_host (optional)
- * n_bins must be in [1, 15] (bins are stored in 4 bits). */
+ * n_bins must be in [1, 31] (GV_MAX_BINS). */
 size_t gv_discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int n_genes, int value_dtype, int sorted);
 int gv_discretize_csr(const void* values, int value_dtype, const int32_t* col_idx,
                       const int64_t* row_ptr, int64_t n_cells, int n_genes, int64_t nnz, int n_bins,
@@ -179,14 +181,14 @@ int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,
                     double* entropy_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- operand layout
- * rows_per_gene B for a given n_bins: 5 (n_bins<=5), 8 (<=8), 10 (<=10), 16 (<=15).
+ * rows_per_gene B for a given n_bins: 5 (n_bins<=5), 8 (<=8), 10 (<=10), 16 (<=15), 32 (<=31).
  * The one-hot operand has 32-row blocks of floor(32/B) genes x B non-zero bins (+ zero rows). */
 int gv_rows_per_gene(int n_bins);
 /* number of 32-row blocks / operand rows for n_genes */
 int64_t gv_onehot_rows(int n_genes, int rows_per_gene);
 /* operand rows of the value matrix for n_limbs digits per gene (32-row blocks of 32/n_limbs genes) */
 int64_t gv_value_rows(int n_genes, int n_limbs);
-/* packed 4-bit bins -> one-hot operand rows.  kp = K extent in cells.
+/* packed bins (4-bit, or bytes when rows_per_gene is 32) -> one-hot operand rows.  kp = K extent in cells.
  *   GV_OPERAND_INT8: int8 [gv_onehot_rows][kp], kp % 128 == 0
  *   GV_OPERAND_FP4 : uint8 [gv_onehot_rows][kp / 2], kp % 256 == 0 */
 int gv_expand_onehot(const void* bins_packed, int64_t bins_pitch_bytes, int n_genes,

@@ -218,6 +218,26 @@ def main():
     # 6. wider bins
     X = synth_counts(400, 30, seed=5).toarray()
     make_case(refm, "synth_counts_400x30_b15", X * 3.0, 15)
+    # 7. n_bins 16..31 (one byte per cell in the bin matrix, 32 operand rows per gene)
+    make_case(refm, "synth_counts_400x30_b16", X * 3.0, 16)
+    make_case(refm, "lognorm_f32_300x40_b20", Xl.astype(np.float32), 20)
+    rng = np.random.RandomState(7)
+    Xp = rng.poisson(20, size=(500, 24)).astype(np.float32)
+    Xp[rng.rand(500, 24) < 0.35] = 0
+    Xp[:, 3] = 0                                        # an all-zero gene
+    Xp[:, 4] = np.where(Xp[:, 4] > 0, 7, 0)             # one unique value
+    make_case(refm, "poisson20_500x24_b31", Xp, 31)
+    # 8. gene pairs whose covariance is EXACTLY zero while np.corrcoef returns rounding noise
+    #    (-4.4e-17 and the like): the reference signs those scores with the noise, the exact integer
+    #    covariance here gives sign 0 ("Sign at zero covariance")
+    a = np.array([1, 2, 3, 3, 2, 3, 3, 2, 2]); b = np.array([0, 4, 3, 2, 2, 0, 2, 4, 4])
+    c = np.array([4, 1, 3, 2, 4, 4, 3, 0, 0]); d = np.array([0, 3, 2, 0, 4, 2, 0, 0, 0])
+    e = np.array([1, 2, 1, 2, 0, 0, 0, 0, 0]); f = np.array([1, 1, 2, 2, 0, 0, 0, 0, 0])
+    base = np.stack([a, b, c, d, e, f], axis=1)
+    rng = np.random.RandomState(11)
+    Xz = np.concatenate([np.tile(base, (30, 1)), rng.poisson(2, size=(270, 6))], axis=1).astype(np.float32)
+    g = make_case(refm, "zero_cov_270x12_b10", Xz, 10)
+    assert int(g["n_sign_ambiguous"]) > 0, "the constructed case lost its zero-covariance pairs"
 
 
 if __name__ == "__main__":

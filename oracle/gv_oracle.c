@@ -97,10 +97,10 @@ static int bin_of(double v, const double* edges, int n_edges) {
 }
 
 /* Dense [n_cells][n_genes] C-order input, dtype 0 = float32, 1 = float64.
- * x_disc int32 [n_cells][n_genes], n_bins_per_gene int32 [n_genes], edges (optional) [n_genes][16]. */
+ * x_disc int32 [n_cells][n_genes], n_bins_per_gene int32 [n_genes], edges (optional) [n_genes][32]. */
 int gvo_discretize_dense(const void* X, int dtype, int64_t n_cells, int64_t n_genes, int n_bins,
                          int32_t* x_disc, int32_t* n_bins_per_gene, double* edges_out) {
-  if (n_bins < 1 || n_bins > 16) return -1;
+  if (n_bins < 1 || n_bins > 31) return -1;
   memset(x_disc, 0, sizeof(int32_t) * (size_t)n_cells * (size_t)n_genes);
   int rc = 0;
 #pragma omp parallel for schedule(dynamic, 8)
@@ -113,8 +113,8 @@ int gvo_discretize_dense(const void* X, int dtype, int64_t n_cells, int64_t n_ge
                                   : ((const double*)X)[c * n_genes + g];
       if (v > 0) s[m++] = v;                          /* metrics.py:53-54 */
     }
-    double edges[16];
-    for (int t = 0; t < 16; ++t) edges[t] = INFINITY;
+    double edges[32];
+    for (int t = 0; t < 32; ++t) edges[t] = INFINITY;
     if (m == 0) {
       n_bins_per_gene[g] = 1;                         /* metrics.py:55-57 */
     } else {
@@ -128,7 +128,7 @@ int gvo_discretize_dense(const void* X, int dtype, int64_t n_cells, int64_t n_ge
         if (v > 0) x_disc[c * n_genes + g] = bin_of(v, edges, ne);
       }
     }
-    if (edges_out) memcpy(edges_out + g * 16, edges, sizeof(edges));
+    if (edges_out) memcpy(edges_out + g * 32, edges, sizeof(edges));
     free(s);
   }
   (void)cmp_f32;
@@ -140,7 +140,7 @@ int gvo_discretize_dense(const void* X, int dtype, int64_t n_cells, int64_t n_ge
 int gvo_discretize_csr(const void* values, int dtype, const int32_t* col_idx, const int64_t* row_ptr,
                        int64_t n_cells, int64_t n_genes, int n_bins, uint8_t* bins_gm,
                        int32_t* n_bins_per_gene, double* edges_out) {
-  if (n_bins < 1 || n_bins > 16) return -1;
+  if (n_bins < 1 || n_bins > 31) return -1;
   const int64_t nnz = row_ptr[n_cells];
   int64_t* gptr = (int64_t*)calloc((size_t)n_genes + 1, sizeof(int64_t));
   int64_t* cur = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_genes + 1));
@@ -161,8 +161,8 @@ int gvo_discretize_csr(const void* values, int dtype, const int32_t* col_idx, co
 #pragma omp parallel for schedule(dynamic, 8)
   for (int64_t g = 0; g < n_genes; ++g) {
     const int64_t m = gptr[g + 1] - gptr[g];
-    double edges[16];
-    for (int t = 0; t < 16; ++t) edges[t] = INFINITY;
+    double edges[32];
+    for (int t = 0; t < 32; ++t) edges[t] = INFINITY;
     if (m == 0) {
       n_bins_per_gene[g] = 1;
     } else {
@@ -176,7 +176,7 @@ int gvo_discretize_csr(const void* values, int dtype, const int32_t* col_idx, co
       for (int64_t p = gptr[g]; p < gptr[g + 1]; ++p)
         bins_gm[g * n_cells + gc[p]] = (uint8_t)bin_of(gv[p], edges, ne);
     }
-    if (edges_out) memcpy(edges_out + g * 16, edges, sizeof(edges));
+    if (edges_out) memcpy(edges_out + g * 32, edges, sizeof(edges));
   }
   free(gptr); free(cur); free(gv); free(gc);
   return 0;

@@ -82,9 +82,9 @@ def _dense(X):
 
 
 # --------------------------------------------------------------------------- discretisation
-def quantile_table(n_bins_max: int = 15) -> np.ndarray:
+def quantile_table(n_bins_max: int = 31) -> np.ndarray:
     """q[k][t-1] = np.linspace(0,100,k+1)[1:-1][t-1] / 100 (metrics.py:64 + np.percentile's /100)."""
-    q = np.zeros((16, 16), dtype=np.float64)
+    q = np.zeros((32, 32), dtype=np.float64)
     for k in range(2, n_bins_max + 1):
         q[k, :k - 1] = np.linspace(0, 100, k + 1)[1:-1] / 100
     return q
@@ -122,7 +122,7 @@ def discretize_genes_c(X, n_bins: int = 10, return_edges: bool = False):
     n_cells, n_genes = X.shape
     X_disc = np.zeros((n_cells, n_genes), dtype=np.int32)
     nb = np.zeros(n_genes, dtype=np.int32)
-    edges = np.zeros((n_genes, 16), dtype=np.float64)
+    edges = np.zeros((n_genes, 32), dtype=np.float64)
     rc = lib().gvo_discretize_dense(X.ctypes.data, 0 if X.dtype == np.float32 else 1, n_cells,
                                     n_genes, n_bins, X_disc.ctypes.data, nb.ctypes.data,
                                     edges.ctypes.data)
@@ -143,7 +143,7 @@ def discretize_csr_c(X, n_bins: int = 10):
     n_cells, n_genes = X.shape
     bins = np.zeros((n_genes, n_cells), dtype=np.uint8)
     nb = np.zeros(n_genes, dtype=np.int32)
-    edges = np.zeros((n_genes, 16), dtype=np.float64)
+    edges = np.zeros((n_genes, 32), dtype=np.float64)
     rc = lib().gvo_discretize_csr(vals.ctypes.data, 0 if vals.dtype == np.float32 else 1,
                                   idx.ctypes.data, ptr.ctypes.data, n_cells, n_genes, n_bins,
                                   bins.ctypes.data, nb.ctypes.data, edges.ctypes.data)

@@ -43,7 +43,9 @@ def test_argument_checks_do_not_need_a_gpu():
     lib = _lib.load()
     assert lib.gv_rows_per_gene(10) == 10 and lib.gv_rows_per_gene(5) == 5
     assert lib.gv_rows_per_gene(7) == 8 and lib.gv_rows_per_gene(15) == 16
-    assert lib.gv_rows_per_gene(16) < 0 and b"n_bins" in lib.gv_last_error()
+    assert lib.gv_rows_per_gene(16) == 32 and lib.gv_rows_per_gene(31) == 32
+    assert lib.gv_rows_per_gene(32) < 0 and b"n_bins" in lib.gv_last_error()
+    assert lib.gv_onehot_rows(100, 32) == 3200
     assert lib.gv_onehot_rows(20000, 10) == 6667 * 32
     assert lib.gv_onehot_rows(7, 5) == 64
     assert lib.gv_tile_m(1) == 128 and lib.gv_tile_m(2) == 256 and lib.gv_tile_m(3) < 0

@@ -46,8 +46,8 @@ def _worker(rank, world, port, tmp):
         packed[:] = padded[:, 0::2] | (padded[:, 1::2] << 4)
         blk.bins.copy_(torch.from_numpy(packed))
         blk.n_bins_per_gene.copy_(torch.from_numpy(nb))
-        marg = np.zeros((n_genes, 16), dtype=np.int32)
-        for a in range(1, 16):
+        marg = np.zeros((n_genes, 32), dtype=np.int32)
+        for a in range(1, 32):
             marg[:, a] = (bins_gm == a).sum(axis=1)
         marg[:, 0] = (bins_gm > 0).sum(axis=1)
         blk.marg.copy_(torch.from_numpy(marg))

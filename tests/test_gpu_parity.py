@@ -45,7 +45,7 @@ def test_discretize_bit_exact_vs_reference(engine, case, path):
         assert np.array_equal(e_got[g, :ne], e_want[g, :ne]), (g, e_got[g, :ne], e_want[g, :ne])
     # marginals: bin counts and the non-zero count
     marg = blk.marg.cpu().numpy()
-    for a in range(1, 16):
+    for a in range(1, 32):
         assert np.array_equal(marg[:, a], (want == a).sum(axis=0)), a
     assert np.array_equal(marg[:, 0], (want > 0).sum(axis=0))
 
@@ -63,7 +63,8 @@ def test_discretize_matches_reference_api(engine):
 # ------------------------------------------------------------------ joint counts
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "ref_poisson_500x20_b5",
-                                  "synth_counts_700x96_b10", "synth_counts_400x30_b15"])
+                                  "synth_counts_700x96_b10", "synth_counts_400x30_b15",
+                                  "synth_counts_400x30_b16", "poisson20_500x24_b31", "lognorm_f32_300x40_b20"])
 def test_joint_counts_bit_exact(engine, case, cg):
     """Raw tcgen05 accumulators == the reference's joint histogram (non-zero bins) for every
     gene pair, and the zero-bin row/column + total follow from the marginals exactly."""
@@ -131,7 +132,8 @@ def test_mi_matches_reference(engine, case, cg):
 
 
 @pytest.mark.parametrize("case", ["ref_poisson_500x50_b10", "ref_poisson_500x20_b5",
-                                  "synth_counts_700x96_b10", "synth_counts_400x30_b15"])
+                                  "synth_counts_700x96_b10", "synth_counts_400x30_b15",
+                                  "synth_counts_400x30_b16", "poisson20_500x24_b31", "zero_cov_270x12_b10"])
 def test_signed_mi_matches_reference(engine, case):
     from genevector_b200.metrics import compute_mi_b200
     z = load_golden(case)
@@ -147,6 +149,28 @@ def test_signed_mi_matches_reference(engine, case):
     # mapping semantics the reference's consumers rely on (data.py:383-388)
     assert genes[0] in sm and genes[1] in sm[genes[0]] and genes[0] not in sm[genes[0]]
     assert abs(sm[genes[0]][genes[1]] - z["mi_signed_round5"][0, 1]) <= ROUND_TOL
+
+
+def test_sign_at_exactly_zero_covariance(engine):
+    """Constructed golden case: three gene pairs whose covariance is exactly zero while the reference's
+    float64 np.corrcoef returns rounding noise (-4e-17 ...) and signs the score with it.  The exact integer
+    covariance here gives sign 0, so the default rule (np.sign semantics) scores those pairs 0 -- the
+    documented deviation -- and |MI| is what BASELINE.md section 5 compares there: the
+    "rust" rule (+1 unless negative) returns it.  Every other pair equals the reference."""
+    from genevector_b200.metrics import compute_mi_b200
+    z = load_golden("zero_cov_270x12_b10")
+    genes = [f"GENE{i}" for i in range(12)]
+    amb = (z["int_sign"] == 0) & (z["corr_sign"] != 0)
+    assert int(amb.sum()) == 6 and set(map(tuple, np.argwhere(np.triu(amb)))) == {(0, 1), (0, 4), (1, 5)}
+    assert (z["mi_raw"][amb] > 0.4).all()
+    dflt = compute_mi_b200(z["X"], genes, signed=True).matrix.astype(np.float64)
+    assert not dflt[amb].any()
+    rust = compute_mi_b200(z["X"], genes, signed=True, sign_rule="rust").matrix.astype(np.float64)
+    assert np.abs(rust[amb] - z["mi_raw"][amb]).max() <= MI_TOL
+    want = z["corr_sign"] * z["mi_raw"]
+    assert np.abs(dflt - want)[~amb].max() <= MI_TOL
+    blk = engine.discretize(engine.upload_csr(z["X"]), 10, val_mode=0)
+    assert np.array_equal(engine.sign_matrix(blk).cpu().numpy()[:, :12], z["int_sign"])
 
 
 def test_sign_matrix_exact(engine):

@@ -151,8 +151,8 @@ def test_sharded_front_end_kernels_reproduce_the_bin_block(engine, world, signed
         for rank in range(world):
             bins = torch.empty((n_genes, pitch), dtype=torch.uint8, device=dev)
             nbpg = torch.empty(n_genes, dtype=torch.int32, device=dev)
-            marg = torch.empty((n_genes, 16), dtype=torch.int32, device=dev)
-            edges = torch.empty((n_genes, 16), dtype=torch.float64, device=dev)
+            marg = torch.empty((n_genes, 32), dtype=torch.int32, device=dev)
+            edges = torch.empty((n_genes, 32), dtype=torch.float64, device=dev)
             gsum = torch.empty(n_genes, dtype=torch.int64, device=dev)
             gsq = torch.empty_like(gsum)
             tot = torch.empty((n_genes, 256), dtype=torch.int32, device=dev)
