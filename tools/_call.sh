@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_runtime.py -m gpu -x -q -s > gpurun_out/r02_gpu_tests7.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r02_gpu_tests7.log; grep "entropy + scores" gpurun_out/r02_gpu_tests7.log
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_gpu_tests8.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/r02_gpu_tests8.log
