@@ -908,7 +908,7 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
 constexpr int RB_THREADS = 256;
 
 template <typename T, bool WIDE = false>
-__global__ void __launch_bounds__(RB_THREADS, 4)
+__global__ void __launch_bounds__(RB_THREADS, 3)
 k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, int64_t n_cells, int G,
                int n_bins, const double* __restrict__ q_table, uint32_t* __restrict__ bins_packed,
                int64_t pitch_words, int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
@@ -940,8 +940,9 @@ k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, i
     const bool detect = val_rows != nullptr && val_mode == 1;
     const int64_t vrow0 = val_rows != nullptr ? val_row0(g, val_mode == 1 ? 1 : n_limbs) : 0;
     const uint32_t dmask = (1u << limb_bits) - 1u;
-    for (int64_t i = tid; i < n16; i += RB_THREADS) {
-      const uint4 w = row[i];
+    // 16 cells per thread and step; four independent 16-byte loads are in flight per thread before the
+    // first is consumed (3 CTAs x 256 threads x 64 bytes = 48 KB per SM: what HBM latency x bandwidth asks)
+    auto process = [&](const int64_t i, const uint4 w) {
       const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
       if constexpr (WIDE) {
         // one byte per cell: the bins of 16 cells are 16 bytes
@@ -993,7 +994,16 @@ k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, i
               make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+    };
+    int64_t i = tid;
+    for (; i + 3 * RB_THREADS < n16; i += 4 * RB_THREADS) {
+      const uint4 w0 = row[i], w1 = row[i + RB_THREADS], w2 = row[i + 2 * RB_THREADS], w3 = row[i + 3 * RB_THREADS];
+      process(i, w0);
+      process(i + RB_THREADS, w1);
+      process(i + 2 * RB_THREADS, w2);
+      process(i + 3 * RB_THREADS, w3);
     }
+    for (; i < n16; i += RB_THREADS) process(i, row[i]);
     __syncthreads();
   }
 }

@@ -216,35 +216,66 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (leader && lane == 0) {
+    // One thread issues every tcgen05.mma of the CTA pair, and ncu's source page shows that this thread,
+    // not the operand supply, bounds the streaming loop (profiles/r02_ncu_mi_c4_fp4_stalls.txt: 115 SASS
+    // instructions per stage, 2.5 % of the warp's samples on each of them, 12 % waiting for data).  So the
+    // loop is unrolled over the pipeline stages: with the stage a compile-time constant, barrier
+    // addresses and shared-memory descriptors are immediates off uniform registers, nothing is
+    // recomputed per stage, and the first MMA of a tile is the only one that carries a predicate.
+    // The stage counter keeps running across tiles (k_blocks need not be a multiple of STAGES): a
+    // switch enters the unrolled body at the current stage (Duff's device).  The whole warp runs the
+    // loop converged and one elected lane issues: inside a single-lane branch the compiler keeps the
+    // operands in vector registers and moves them to uniform ones around every instruction.
+    if (leader) {
+      const bool elected = elect_one();
       int s = 0; uint32_t ph = 0; int it = 0;
+      const uint64_t desc0 = smem_desc_k128(smem_base);                 // A tile of stage 0
+      constexpr uint64_t STAGE_D = uint64_t(Cfg::STAGE_BYTES >> 4);     // in 16-byte address units
+      constexpr uint64_t A_D = uint64_t(Cfg::A_BYTES >> 4);
+      const uint32_t sfa = tmem_base + Cfg::SFA_COL, sfb = tmem_base + Cfg::SFB_COL;
+      (void)sfa; (void)sfb;
+      const int K = ga.k_blocks;
       for (int t = cluster_id; t < ga.n_tiles; t += n_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc) * GRAM_TILE_N;
-        for (int kb = 0; kb < ga.k_blocks; ++kb) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
-          const uint64_t adesc = smem_desc_k128(sa);
-          const uint64_t bdesc = smem_desc_k128(sa + Cfg::A_BYTES);
-#pragma unroll
-          for (int k = 0; k < GRAM_BK / 32; ++k) {
-            // advance 32 bytes (one K=32 step) inside the 128-byte swizzle row: +2 in the
-            // 16-byte-granular start-address field
-            if constexpr (Epi::OPERAND_FP4)
-              mma_mxf4<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
-                           tmem_base + Cfg::SFA_COL, tmem_base + Cfg::SFB_COL, (kb | k) != 0 ? 1u : 0u);
-            else
-              mma_i8<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC,
-                         (kb | k) != 0 ? 1u : 0u);
+        int kb = 0;
+#define GV_MMA_ONE(AD, BD, ACCUM)                                                                    \
+        do {                                                                                         \
+          if constexpr (Epi::OPERAND_FP4) mma_mxf4<CG>(d_tmem, (AD), (BD), Cfg::IDESC, sfa, sfb, (ACCUM)); \
+          else mma_i8<CG>(d_tmem, (AD), (BD), Cfg::IDESC, (ACCUM));                                  \
+        } while (0)
+#define GV_MMA_STAGE(S)                                                                              \
+        case (S):                                                                                    \
+          if constexpr ((S) < Cfg::STAGES) {                                                         \
+            mbar_wait(bars + 8u * (S), ph);                                                          \
+            tc_fence_after();                                                                        \
+            const uint64_t adesc = desc0 + uint64_t(S) * STAGE_D;                                    \
+            const uint64_t bdesc = adesc + A_D;                                                      \
+            /* +2 in the 16-byte-granular start-address field = 32 bytes = one K step of the swizzle row */ \
+            if (elected) {                                                                           \
+              GV_MMA_ONE(adesc, bdesc, kb != 0 ? 1u : 0u);                                           \
+              GV_MMA_ONE(adesc + 2, bdesc + 2, 1u);                                                  \
+              GV_MMA_ONE(adesc + 4, bdesc + 4, 1u);                                                  \
+              GV_MMA_ONE(adesc + 6, bdesc + 6, 1u);                                                  \
+              mma_commit<CG>(bars + 8u * (Cfg::STAGES + (S)));    /* frees the smem slot (both CTAs) */ \
+            }                                                                                        \
+            if constexpr ((S) + 1 == Cfg::STAGES) ph ^= 1u;                                          \
+            if (++kb == K) { s = ((S) + 1) % Cfg::STAGES; goto tile_done; }                          \
           }
-          mma_commit<CG>(empty_bar(s));                       // frees the smem slot (both CTAs)
-          if (kb == ga.k_blocks - 1) mma_commit<CG>(tfull_bar(acc));  // accumulator ready
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+        static_assert(GRAM_BK / 32 == 4, "four K steps per stage");
+        switch (s) {
+          for (;;) {
+            GV_MMA_STAGE(0) GV_MMA_STAGE(1) GV_MMA_STAGE(2) GV_MMA_STAGE(3)
+            GV_MMA_STAGE(4) GV_MMA_STAGE(5) GV_MMA_STAGE(6) GV_MMA_STAGE(7)
+          }
         }
+      tile_done:
+        if (elected) mma_commit<CG>(tfull_bar(acc));             // accumulator ready
+#undef GV_MMA_STAGE
+#undef GV_MMA_ONE
       }
     }
   } else if (warp >= 4) {
@@ -266,7 +297,10 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       et.col0 = tc.y;
       et.tmem_acc = tmem_base + uint32_t(acc) * GRAM_TILE_N;
       epi.prepare(et);                       // tile metadata -> smem (overlaps the MMA)
-      mbar_wait(tfull_bar(acc), acc_ph);
+      // one warp waits for the accumulator; the other seven sleep on the named barrier instead of
+      // polling the mbarrier (they woke on every barrier event of the SM: 2.5e10 polls per C4 launch)
+      if (ew == 0) mbar_wait(tfull_bar(acc), acc_ph);
+      asm volatile("bar.sync %0, %1;" ::"n"(GRAM_EPI_BAR), "n"(GRAM_EPI_WARPS * 32) : "memory");
       tc_fence_after();
       epi.run(et);
       tc_fence_before();

@@ -17,6 +17,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
+// One lane of a converged warp (the others get false).  The warp keeps running converged around it, so
+// everything the elected lane's tcgen05 instructions consume stays in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -482,3 +482,29 @@ def test_count_packer_matches_numpy_and_refuses_what_does_not_fit():
             c = base_c.copy()
             c[pos] = badc
             assert pack(base_v, c)[0] == 0, (pos, badc)
+
+
+def test_rounding_conventions_agree():
+    """The three places a score is rounded to 5 decimals -- the mapping (Python round, like the reference's
+    round(mi, 5), metrics.py:139), ScoreMatrix.items() / rounded() / the cache writer (np.round) and
+    gv_build_training_tensors (rint(x * 1e5) / 1e5 on the device) -- give the same float64 for every float32
+    score: x * 1e5 is exact in float64 for a float32 x, so each is the correctly rounded decimal."""
+    from genevector_b200.scores import ScoreMatrix
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([rng.uniform(-3.5, 3.5, 200000).astype(np.float32),
+                           (np.arange(-2000, 2000) * 1e-5 + 5e-6).astype(np.float32),      # near the ties
+                           np.float32([0.5, 0.125, 1e-6, -1e-6, 0.000005, 2.5e-5, 3.4599998])])
+    x64 = vals.astype(np.float64)
+    a = np.array([round(float(v), 5) for v in x64])
+    b = np.round(x64, 5)
+    c = np.rint(x64 * 1e5) / 1e5
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    n = 300
+    M = vals[:n * n].reshape(n, n).copy()
+    M = ((M + M.T) / 2).astype(np.float32)
+    np.fill_diagonal(M, 0)
+    genes = [f"G{i}" for i in range(n)]
+    sm = ScoreMatrix(M, genes)
+    row = dict(sm["G7"].items())
+    assert all(sm["G7"][g] == row[g] for g in genes if g != "G7")
+    assert np.array_equal(sm.rounded()[7], np.array([0.0 if g == "G7" else sm["G7"][g] for g in genes]))
