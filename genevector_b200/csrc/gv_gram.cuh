@@ -154,7 +154,10 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The warp runs converged; one elected lane issues the loads and the barrier arrives (see the MMA
+    // warp below for why not a single-lane branch).
+    {
+      const bool elected = elect_one();
       const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
       int s = 0; uint32_t ph = 0;
       unsigned int wave = 0;
@@ -165,16 +168,19 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           // wave_sync[0] counts arrivals; wave_sync[1] != 0 means the lockstep was given up: a cluster
           // that waited a full second for the others (they are not co-resident: something else holds
           // SMs) sets it and every cluster runs on unsynchronised -- slower, never a hang or a trap
-          volatile unsigned int* ws = reinterpret_cast<volatile unsigned int*>(ga.wave_sync);
-          atomicAdd(ga.wave_sync, 1u);
-          const unsigned int target = unsigned(n_clusters) * (wave + 1u);
-          if (ws[1] == 0u && ws[0] < target) {
-            const uint64_t t0 = global_timer_ns();
-            while (ws[0] < target && ws[1] == 0u) {
-              __nanosleep(128);
-              if (global_timer_ns() - t0 > 1000000000ull) ws[1] = 1u;
+          if (elected) {
+            volatile unsigned int* ws = reinterpret_cast<volatile unsigned int*>(ga.wave_sync);
+            atomicAdd(ga.wave_sync, 1u);
+            const unsigned int target = unsigned(n_clusters) * (wave + 1u);
+            if (ws[1] == 0u && ws[0] < target) {
+              const uint64_t t0 = global_timer_ns();
+              while (ws[0] < target && ws[1] == 0u) {
+                __nanosleep(128);
+                if (global_timer_ns() - t0 > 1000000000ull) ws[1] = 1u;
+              }
             }
           }
+          __syncwarp();
         }
         if (t >= ga.n_tiles) break;
         const int2 tc = ga.tiles[t];
@@ -189,26 +195,28 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint32_t fb = full0 + 8u * s;   // leader's barrier (cluster address if CG==2)
-          if constexpr (CG == 2) {
-            tma_load_2d_pair(&tmap, fb, sa, kb * GRAM_BK, arow);
-            if constexpr (Epi::ACTIVE_ROWS == 32) {
-              tma_load_2d_pair(&tmap_b, fb, sb, kb * GRAM_BK, brow);
+          if (elected) {
+            if constexpr (CG == 2) {
+              tma_load_2d_pair(&tmap, fb, sa, kb * GRAM_BK, arow);
+              if constexpr (Epi::ACTIVE_ROWS == 32) {
+                tma_load_2d_pair(&tmap_b, fb, sb, kb * GRAM_BK, brow);
+              } else {
+                // one 3-D box: 128 bytes of K x ACTIVE rows x B_BLOCKS blocks, landing back to back
+                tma_load_3d_pair(&tmap_b, fb, sb, kb * GRAM_BK, 0, brow >> 5);
+              }
+              if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES * CG);
+              else        mbar_arrive_cluster(fb);
             } else {
-              // one 3-D box: 128 bytes of K x ACTIVE rows x B_BLOCKS blocks, landing back to back
-              tma_load_3d_pair(&tmap_b, fb, sb, kb * GRAM_BK, 0, brow >> 5);
+              tma_load_2d(&tmap, fb, sa, kb * GRAM_BK, arow);
+              if constexpr (Epi::ACTIVE_ROWS == 32) {
+                // TMA boxes are at most 256 rows; 256 rows here and the box is 128 rows
+                tma_load_2d(&tmap_b, fb, sb, kb * GRAM_BK, brow);
+                tma_load_2d(&tmap_b, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
+              } else {
+                tma_load_3d(&tmap_b, fb, sb, kb * GRAM_BK, 0, brow >> 5);
+              }
+              mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES);
             }
-            if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES * CG);
-            else        mbar_arrive_cluster(fb);
-          } else {
-            tma_load_2d(&tmap, fb, sa, kb * GRAM_BK, arow);
-            if constexpr (Epi::ACTIVE_ROWS == 32) {
-              // TMA boxes are at most 256 rows; 256 rows here and the box is 128 rows
-              tma_load_2d(&tmap_b, fb, sb, kb * GRAM_BK, brow);
-              tma_load_2d(&tmap_b, fb, sb + Cfg::A_BYTES, kb * GRAM_BK, brow + 128);
-            } else {
-              tma_load_3d(&tmap_b, fb, sb, kb * GRAM_BK, 0, brow >> 5);
-            }
-            mbar_arrive_expect_tx(full_bar(s), Cfg::TX_BYTES);
           }
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
