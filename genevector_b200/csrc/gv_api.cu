@@ -154,12 +154,12 @@ int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_i
 
 int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, const double* q_table_host,
                   const void* raw, const void* const* hists_host, int n_hists, uint32_t* ghist_total,
-                  double* qtab_dev, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,
+                  double* qtab_dev, void* lut_ws, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,
                   int32_t* marg, double* edges, int64_t* gsum, int64_t* gsq, int value_rows,
                   int64_t val_rows_alloc, int val_limb_bits, void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
-  if (!q_table_host || !raw || !hists_host || !ghist_total || !qtab_dev || !bins_packed || !n_bins_per_gene ||
+  if (!q_table_host || !raw || !hists_host || !ghist_total || !qtab_dev || !lut_ws || !bins_packed || !n_bins_per_gene ||
       !marg || !edges || !gsum || !gsq || n_genes <= 0 || n_cells < 0)
     return set_error(GV_ERR_ARG, "gv_shard_bins: bad argument");
   if (bins_pitch_bytes % 64 != 0 || bins_pitch_bytes * 2 < n_cells)
@@ -175,7 +175,8 @@ int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, con
   if (value_rows && val_rows_alloc < gv_value_rows(n_genes, 1))
     return set_error(GV_ERR_ARG, "gv_shard_bins: val_rows_alloc < gv_value_rows(n_genes, 1)");
   return shard_bins_dispatch(a, static_cast<const uint8_t*>(raw), reinterpret_cast<const uint32_t* const*>(hists_host),
-                             n_hists, ghist_total, qtab_dev, static_cast<cudaStream_t>(stream));
+                             n_hists, ghist_total, qtab_dev, static_cast<uint8_t*>(lut_ws),
+                             static_cast<cudaStream_t>(stream));
 }
 
 int gv_gene_entropy(const void* values, int value_dtype, const int32_t* col_idx,

@@ -904,34 +904,50 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
   }
 }
 
+// ---------------------------------------------------------------- k_gene_luts
+// One warp per gene: value histogram -> the per-gene outputs of discretize_genes and the value -> bin
+// table (value -> doubled rank for the rank rows), written to global memory for the row sweep.  Kept out
+// of k_rows_to_bins: there one warp built the table while the other seven of the CTA waited, a serial
+// third of every gene's time.
+template <typename T, int NE>
+__global__ void __launch_bounds__(256)
+k_gene_luts(const uint32_t* __restrict__ ghist, int G, int n_bins, const double* __restrict__ q_table,
+            int64_t n_cells, uint8_t* __restrict__ lut_all, uint32_t* __restrict__ rlut_all,
+            int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg, double* __restrict__ edges_out,
+            int64_t* __restrict__ gsum, int64_t* __restrict__ gsq) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
+    uint32_t c[8];
+    const uint4* hp = reinterpret_cast<const uint4*>(ghist + int64_t(g) * VH + lane * 8);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    c[0] = lane ? h0.x : 0u; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w;
+    c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
+    gene_lut_warp<T, NE>(c, lane, g, n_bins, q_table, n_cells, lut_all + int64_t(g) * VH,
+                         rlut_all ? rlut_all + int64_t(g) * VH : nullptr, n_bins_per_gene, marg, edges_out,
+                         gsum, gsq);
+  }
+}
+
 // ---------------------------------------------------------------- k_rows_to_bins
 constexpr int RB_THREADS = 256;
 
 template <typename T, bool WIDE = false>
 __global__ void __launch_bounds__(RB_THREADS, 3)
-k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, int64_t n_cells, int G,
-               int n_bins, const double* __restrict__ q_table, uint32_t* __restrict__ bins_packed,
-               int64_t pitch_words, int32_t* __restrict__ n_bins_per_gene, int32_t* __restrict__ marg,
-               double* __restrict__ edges_out, int64_t* __restrict__ gsum, int64_t* __restrict__ gsq,
+k_rows_to_bins(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t kp, int G,
+               uint32_t* __restrict__ bins_packed, int64_t pitch_words,
                int8_t* __restrict__ val_rows, int64_t val_pitch, int val_mode, int limb_bits,
-               int n_limbs, const uint32_t* __restrict__ ghist) {
-  // ghist [G][256]: the per-gene value histogram from k_transpose_counts; the row is swept once
-  __shared__ __align__(8) uint8_t lut[VH];
+               int n_limbs, const uint8_t* __restrict__ lut_all, const uint32_t* __restrict__ rlut_all) {
+  // lut_all [G][256] / rlut_all [G][256]: the per-gene tables from k_gene_luts; the row is swept once
+  __shared__ __align__(16) uint8_t lut[VH];
   __shared__ uint32_t rlut[VH];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int64_t n16 = kp / 16;
   const bool ranks = val_rows != nullptr && val_mode == 3;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const uint4* row = reinterpret_cast<const uint4*>(raw + int64_t(g) * raw_pitch);
-    if (warp == 0) {
-      uint32_t c[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        c[i] = (lane * 8 + i) ? ghist[int64_t(g) * VH + lane * 8 + i] : 0u;
-      }
-      gene_lut_warp<T, WIDE ? 30 : 14>(c, lane, g, n_bins, q_table, n_cells, lut, ranks ? rlut : nullptr,
-                                       n_bins_per_gene, marg, edges_out, gsum, gsq);
-    }
+    if (tid < VH / 4) reinterpret_cast<uint32_t*>(lut)[tid] = reinterpret_cast<const uint32_t*>(lut_all + int64_t(g) * VH)[tid];
+    if (ranks) rlut[tid] = rlut_all[int64_t(g) * VH + tid];
     __syncthreads();
     // ---- one sweep of the row: packed bins and, when they are not `raw` itself, value rows
     uint2* brow = reinterpret_cast<uint2*>(bins_packed + int64_t(g) * pitch_words);
@@ -1352,6 +1368,8 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     uint8_t* raw = raw_is_val ? reinterpret_cast<uint8_t*>(val_rows)
                               : static_cast<uint8_t*>(take(size_t(G) * size_t(kcells)));
     uint32_t* ghist = static_cast<uint32_t*>(take(size_t(G) * VH * 4));
+    uint8_t* lut_all = static_cast<uint8_t*>(take(size_t(G) * VH));
+    uint32_t* rlut_all = ranks ? static_cast<uint32_t*>(take(size_t(G) * VH * 4)) : nullptr;
     if (off > a.workspace_bytes) return set_error(GV_ERR_ARG, "discretize: workspace too small");
     GV_CUDA_TRY(cudaMemsetAsync(ghist, 0, size_t(G) * VH * 4, st));
     auto kt = k_transpose_counts<T, VT, CT>;
@@ -1385,11 +1403,14 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
           GV_CUDA_TRY(cudaMemsetAsync(val_rows + used * a.val_pitch, 0,
                                       size_t(a.val_rows_alloc - used) * a.val_pitch, st));
       }
+      auto kl = wide ? k_gene_luts<T, 30> : k_gene_luts<T, 14>;
+      kl<<<(G + 7) / 8, 256, 0, st>>>(ghist, G, a.n_bins, qtab, a.n_cells, lut_all, rlut_all, a.n_bins_per_gene,
+                                      a.marg, a.edges, a.gsum, a.gsq);
+      GV_LAUNCH_CHECK();
       auto kr = wide ? k_rows_to_bins<T, true> : k_rows_to_bins<T, false>;
       kr<<<G < sms * 8 ? G : sms * 8, RB_THREADS, 0, st>>>(
-          raw, kcells, kcells, a.n_cells, G, a.n_bins, qtab, static_cast<uint32_t*>(a.bins_packed),
-          int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
-          a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, ghist);
+          raw, kcells, kcells, G, static_cast<uint32_t*>(a.bins_packed), int64_t(a.bins_pitch_bytes / 4),
+          val_rows, a.val_pitch, a.val_mode, a.val_limb_bits, n_limbs, lut_all, rlut_all);
       GV_LAUNCH_CHECK();
       if (a.path_used) *a.path_used = GV_PATH_COUNTS;
       return GV_OK;
@@ -1814,7 +1835,7 @@ int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t*
 
 template <typename T>
 static int shard_bins_impl(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
-                           uint32_t* ghist_total, double* qtab_dev, cudaStream_t st) {
+                           uint32_t* ghist_total, double* qtab_dev, uint8_t* lut_all, cudaStream_t st) {
   const int G = a.n_genes;
   const int sms = device_sm_count();
   const int64_t kcells = a.bins_pitch_bytes * 2;
@@ -1827,10 +1848,12 @@ static int shard_bins_impl(const DiscretizeArgs& a, const uint8_t* raw, const ui
   GV_LAUNCH_CHECK();
   if (val_rows != nullptr && a.val_rows_alloc > G)
     GV_CUDA_TRY(cudaMemsetAsync(val_rows + int64_t(G) * a.val_pitch, 0, size_t(a.val_rows_alloc - G) * a.val_pitch, st));
+  k_gene_luts<T, 14><<<(G + 7) / 8, 256, 0, st>>>(ghist_total, G, a.n_bins, qtab_dev, a.n_cells, lut_all, nullptr,
+                                                  a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq);
+  GV_LAUNCH_CHECK();
   k_rows_to_bins<T><<<G < sms * 8 ? G : sms * 8, RB_THREADS, 0, st>>>(
-      raw, kcells, kcells, a.n_cells, G, a.n_bins, qtab_dev, static_cast<uint32_t*>(a.bins_packed),
-      int64_t(a.bins_pitch_bytes / 4), a.n_bins_per_gene, a.marg, a.edges, a.gsum, a.gsq, val_rows,
-      a.val_pitch, a.val_mode, a.val_limb_bits, 1, ghist_total);
+      raw, kcells, kcells, G, static_cast<uint32_t*>(a.bins_packed), int64_t(a.bins_pitch_bytes / 4), val_rows,
+      a.val_pitch, a.val_mode, a.val_limb_bits, 1, lut_all, nullptr);
   GV_LAUNCH_CHECK();
   return GV_OK;
 }
@@ -1838,7 +1861,7 @@ static int shard_bins_impl(const DiscretizeArgs& a, const uint8_t* raw, const ui
 // raw: this rank's complete dense rows [G][kcells] (== val_rows when value rows are wanted: count
 // digits, one per gene); hists: every rank's partial histogram (peer pointers).
 int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
-                        uint32_t* ghist_total, double* qtab_dev, cudaStream_t st) {
+                        uint32_t* ghist_total, double* qtab_dev, uint8_t* lut_all, cudaStream_t st) {
   if (n_hists < 1 || n_hists > TP_MAX_PEERS) return set_error(GV_ERR_ARG, "shard bins: 1..8 histograms");
   if (a.n_bins < 1 || a.n_bins > 15)
     return set_error(GV_ERR_UNSUPPORTED, "the sharded front end covers n_bins in [1,15] (4-bit bins)");
@@ -1846,8 +1869,9 @@ int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint3
                                 a.val_pitch != a.bins_pitch_bytes * 2))
     return set_error(GV_ERR_ARG, "shard bins: value rows must be the dense count rows themselves (one digit)");
   if (a.value_dtype == GV_F32 || a.value_dtype == GV_COUNTS_U8_COL16)
-    return shard_bins_impl<float>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
-  if (a.value_dtype == GV_F64) return shard_bins_impl<double>(a, raw, hists, n_hists, ghist_total, qtab_dev, st);
+    return shard_bins_impl<float>(a, raw, hists, n_hists, ghist_total, qtab_dev, lut_all, st);
+  if (a.value_dtype == GV_F64)
+    return shard_bins_impl<double>(a, raw, hists, n_hists, ghist_total, qtab_dev, lut_all, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 
@@ -1868,7 +1892,8 @@ size_t discretize_workspace_bytes(int64_t nnz, int64_t n_cells, int G, int value
   const size_t vs = value_dtype == GV_F64 ? 8 : 4;
   const size_t front = al256(64) + al256(QT_DIM_ * QT_DIM_ * 8);
   const size_t kcells = (size_t(n_cells > 0 ? n_cells : 1) + 255) / 256 * 256;
-  const size_t counts = al256(size_t(G) * kcells) + al256(size_t(G) * VH * 4);
+  const size_t counts = al256(size_t(G) * kcells) + al256(size_t(G) * VH * 4) + al256(size_t(G) * VH) +
+                        al256(size_t(G) * VH * 4);
   const size_t entropy = al256(size_t(G) * VH * 4);
   size_t general = al256(size_t(G) * 4) + al256(size_t(G) * 8) + al256(size_t(G + 1) * 8) +
                    al256(size_t(nnz) * 4) + al256(size_t(nnz) * vs) + al256(size_t(G) * sizeof(SignedGene));

@@ -168,16 +168,16 @@ gram_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           // wave_sync[0] counts arrivals; wave_sync[1] != 0 means the lockstep was given up: a cluster
           // that waited a full second for the others (they are not co-resident: something else holds
           // SMs) sets it and every cluster runs on unsynchronised -- slower, never a hang or a trap
-          if (elected) {
-            volatile unsigned int* ws = reinterpret_cast<volatile unsigned int*>(ga.wave_sync);
-            atomicAdd(ga.wave_sync, 1u);
-            const unsigned int target = unsigned(n_clusters) * (wave + 1u);
-            if (ws[1] == 0u && ws[0] < target) {
-              const uint64_t t0 = global_timer_ns();
-              while (ws[0] < target && ws[1] == 0u) {
-                __nanosleep(128);
-                if (global_timer_ns() - t0 > 1000000000ull) ws[1] = 1u;
-              }
+          volatile unsigned int* ws = reinterpret_cast<volatile unsigned int*>(ga.wave_sync);
+          if (elected) atomicAdd(ga.wave_sync, 1u);
+          __syncwarp();
+          // every lane polls (one broadcast load per poll): the warp stays converged
+          const unsigned int target = unsigned(n_clusters) * (wave + 1u);
+          if (ws[1] == 0u && ws[0] < target) {
+            const uint64_t t0 = global_timer_ns();
+            while (ws[0] < target && ws[1] == 0u) {
+              __nanosleep(128);
+              if (global_timer_ns() - t0 > 1000000000ull) ws[1] = 1u;
             }
           }
           __syncwarp();

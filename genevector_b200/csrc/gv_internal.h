@@ -44,7 +44,7 @@ int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t*
                              uint32_t* ghist_local, unsigned long long* flags_dev,
                              unsigned long long* flags_host, cudaStream_t st);
 int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
-                        uint32_t* ghist_total, double* qtab_dev, cudaStream_t st);
+                        uint32_t* ghist_total, double* qtab_dev, uint8_t* lut_all, cudaStream_t st);
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,
                            void* onehot, int64_t kp, int n_blocks, int operand_format,
                            cudaStream_t st);

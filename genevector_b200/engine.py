@@ -965,7 +965,7 @@ class Engine:
         off = dict(lay)
         cur = total1
         for name, nbytes in (("ghist", n_genes * 256 * 4), ("ghist_total", n_genes * 256 * 4),
-                             ("flags", 256), ("qtab", 2048)):
+                             ("flags", 256), ("qtab", 8192), ("luts", n_genes * 256)):
             off[name] = (cur, nbytes)
             cur += _align(nbytes)
         self._peer_epoch += 1
@@ -1067,7 +1067,8 @@ class Engine:
             vrows = value_rows(n_genes, 1)
             self._call("gv_shard_bins", dt, n_cells, n_genes, n_bins, q.ctypes.data,
                        pb.own_ptr + pb.off["val"][0], hists, world, pb.own_ptr + pb.off["ghist_total"][0],
-                       pb.own_ptr + pb.off["qtab"][0], blk.bins.data_ptr(), pitch, blk.n_bins_per_gene.data_ptr(),
+                       pb.own_ptr + pb.off["qtab"][0], pb.own_ptr + pb.off["luts"][0], blk.bins.data_ptr(), pitch,
+                       blk.n_bins_per_gene.data_ptr(),
                        blk.marg.data_ptr(), blk.edges.data_ptr(), blk.gsum.data_ptr(), blk.gsq.data_ptr(),
                        1 if signed else 0, vrows, lb, stream.cuda_stream)
             blk.path_used = _lib.GV_PATH_COUNTS

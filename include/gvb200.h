@@ -159,14 +159,14 @@ int gv_csr_check(const void* col_idx, int value_dtype, const int64_t* row_ptr, i
  * genes from this rank's complete `raw`: the same outputs as gv_discretize_csr on the count path.
  * value_rows = 1: `raw` itself is the one-digit INT8 value-row operand (needs every value <= 127 and
  * val_rows_alloc = gv_value_rows(n_genes, 1) rows allocated; rows >= n_genes are zeroed).
- * qtab_dev: 2 KB of device scratch. */
+ * qtab_dev: 8 KB of device scratch; lut_ws: n_genes * 256 bytes of device scratch (value -> bin tables). */
 int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,
                        int64_t n_cells_local, int n_genes, int64_t blk_begin, int64_t blk_end,
                        void* const* raw_dests_host, int n_dests, int own_index, int64_t raw_pitch,
                        uint32_t* ghist_local, void* flags_dev, uint64_t* data_flags_out_host, void* stream);
 int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, const double* q_table_host,
                   const void* raw, const void* const* hists_host, int n_hists, uint32_t* ghist_total,
-                  double* qtab_dev, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,
+                  double* qtab_dev, void* lut_ws, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,
                   int32_t* marg, double* edges, int64_t* gsum, int64_t* gsq, int value_rows,
                   int64_t val_rows_alloc, int val_limb_bits, void* stream);
 

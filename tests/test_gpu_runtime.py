@@ -156,9 +156,10 @@ def test_sharded_front_end_kernels_reproduce_the_bin_block(engine, world, signed
             gsum = torch.empty(n_genes, dtype=torch.int64, device=dev)
             gsq = torch.empty_like(gsum)
             tot = torch.empty((n_genes, 256), dtype=torch.int32, device=dev)
-            qd = torch.empty(2048, dtype=torch.uint8, device=dev)
+            qd = torch.empty(8192, dtype=torch.uint8, device=dev)
+            luts = torch.empty(n_genes * 256, dtype=torch.uint8, device=dev)
             _lib.call("gv_shard_bins", _lib.GV_F32, n_cells, n_genes, n_bins, q.ctypes.data, raws[rank].data_ptr(),
-                      hp, world, tot.data_ptr(), qd.data_ptr(), bins.data_ptr(), pitch, nbpg.data_ptr(),
+                      hp, world, tot.data_ptr(), qd.data_ptr(), luts.data_ptr(), bins.data_ptr(), pitch, nbpg.data_ptr(),
                       marg.data_ptr(), edges.data_ptr(), gsum.data_ptr(), gsq.data_ptr(), 1 if signed else 0,
                       vrows, lb, st)
             torch.cuda.synchronize(dev)
