@@ -50,7 +50,7 @@ SIGNATURES = {
                                  _vp, _sz, _i32, _vp, _vp]),
     "gv_csr_check": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "gv_shard_transpose": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _vp, _i32, _i32, _i64, _vp, _vp, _vp,
-                                  _vp]),
+                                  _i32, _vp]),
     "gv_shard_bins": (_i32, [_i32, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                              _vp, _vp, _i32, _i64, _i32, _vp]),
     "gv_gene_entropy": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),

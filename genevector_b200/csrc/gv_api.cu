@@ -133,7 +133,8 @@ int gv_csr_check(const void* col_idx, int value_dtype, const int64_t* row_ptr, i
 int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,
                        int64_t n_cells_local, int n_genes, int64_t blk_begin, int64_t blk_end,
                        void* const* raw_dests_host, int n_dests, int own_index, int64_t raw_pitch,
-                       uint32_t* ghist_local, void* flags_dev, uint64_t* data_flags_out_host, void* stream) {
+                       uint32_t* ghist_local, void* flags_dev, uint64_t* data_flags_out_host, int phase,
+                       void* stream) {
   int rc = check_device();
   if (rc != GV_OK) return rc;
   if (!row_ptr_local || !raw_dests_host || !ghist_local || !flags_dev || !data_flags_out_host || n_genes <= 0 ||
@@ -143,12 +144,16 @@ int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_i
     if (!raw_dests_host[p]) return set_error(GV_ERR_ARG, "gv_shard_transpose: null destination");
   if (n_cells_local > (blk_end - blk_begin) * 128)
     return set_error(GV_ERR_ARG, "gv_shard_transpose: more local cells than the block range holds");
+  if (phase < 0 || phase > 3) return set_error(GV_ERR_ARG, "gv_shard_transpose: phase is a 2-bit mask");
   unsigned long long hf[2] = {0, 0};
   rc = shard_transpose_dispatch(values, value_dtype, col_idx, row_ptr_local, n_cells_local, n_genes, blk_begin,
                                 blk_end, raw_dests_host, n_dests, own_index, raw_pitch, ghist_local,
-                                static_cast<unsigned long long*>(flags_dev), hf, static_cast<cudaStream_t>(stream));
-  data_flags_out_host[0] = hf[0];
-  data_flags_out_host[1] = hf[1];
+                                static_cast<unsigned long long*>(flags_dev), hf, phase,
+                                static_cast<cudaStream_t>(stream));
+  if (phase & 2) {
+    data_flags_out_host[0] = hf[0];
+    data_flags_out_host[1] = hf[1];
+  }
   return rc;
 }
 

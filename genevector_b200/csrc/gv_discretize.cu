@@ -1756,7 +1756,7 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, 
                                 int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
                                 void* const* raw_dests, int n_dests, int own_index, int64_t raw_pitch,
                                 uint32_t* ghist_local, unsigned long long* flags_dev,
-                                unsigned long long* flags_host, cudaStream_t st) {
+                                unsigned long long* flags_host, int phase, cudaStream_t st) {
   using VT = typename std::conditional<PACKED, uint8_t, T>::type;
   using CT = typename std::conditional<PACKED, uint16_t, int32_t>::type;
   const VT* values = static_cast<const VT*>(values_v);
@@ -1770,8 +1770,13 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, 
     dests.n = 1;
     dests.raw[0] = static_cast<uint8_t*>(raw_dests[own_index]);
   }
-  GV_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 64, st));
-  GV_CUDA_TRY(cudaMemsetAsync(ghist_local, 0, size_t(G) * VH * 4, st));
+  // phase bit 0: first chunk of this rank's cells (histogram and flags start from zero); bit 1: last
+  // chunk (flags are read back and the stream is synchronised).  A rank may feed its block of cells in
+  // several chunks, each one's transposition and peer copies running under the upload of the next.
+  if (phase & 1) {
+    GV_CUDA_TRY(cudaMemsetAsync(flags_dev, 0, 64, st));
+    GV_CUDA_TRY(cudaMemsetAsync(ghist_local, 0, size_t(G) * VH * 4, st));
+  }
   const int64_t n_blocks = blk_end - blk_begin;
   if (n_blocks > 0) {
     auto kt = k_transpose_counts<T, VT, CT>;
@@ -1806,8 +1811,10 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, 
       if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     }
   }
-  GV_CUDA_TRY(cudaMemcpyAsync(flags_host, flags_dev, 16, cudaMemcpyDeviceToHost, st));
-  GV_CUDA_TRY(cudaStreamSynchronize(st));      // the peer stores / copies are complete
+  if (phase & 2) {
+    GV_CUDA_TRY(cudaMemcpyAsync(flags_host, flags_dev, 16, cudaMemcpyDeviceToHost, st));
+    GV_CUDA_TRY(cudaStreamSynchronize(st));      // the peer stores / copies are complete
+  }
   return GV_OK;
 }
 
@@ -1815,21 +1822,21 @@ int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t*
                              int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
                              void* const* raw_dests, int n_dests, int own_index, int64_t raw_pitch,
                              uint32_t* ghist_local, unsigned long long* flags_dev,
-                             unsigned long long* flags_host, cudaStream_t st) {
+                             unsigned long long* flags_host, int phase, cudaStream_t st) {
   if (n_dests < 1 || n_dests > TP_MAX_PEERS) return set_error(GV_ERR_ARG, "shard transpose: 1..8 destinations");
   if (own_index < 0 || own_index >= n_dests) return set_error(GV_ERR_ARG, "shard transpose: own_index out of range");
   if (raw_pitch % TP_CB != 0 || blk_begin < 0 || blk_end < blk_begin || blk_end * TP_CB > raw_pitch)
     return set_error(GV_ERR_ARG, "shard transpose: cell blocks outside the dense rows");
   if (value_dtype == GV_F32)
     return shard_transpose_impl<float>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
-                                       n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, st);
+                                       n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, phase, st);
   if (value_dtype == GV_F64)
     return shard_transpose_impl<double>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end, raw_dests,
-                                        n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, st);
+                                        n_dests, own_index, raw_pitch, ghist_local, flags_dev, flags_host, phase, st);
   if (value_dtype == GV_COUNTS_U8_COL16)
     return shard_transpose_impl<float, true>(values, col_idx, row_ptr, n_cells_local, G, blk_begin, blk_end,
                                              raw_dests, n_dests, own_index, raw_pitch, ghist_local, flags_dev,
-                                             flags_host, st);
+                                             flags_host, phase, st);
   return set_error(GV_ERR_ARG, "value dtype must be GV_F32 or GV_F64");
 }
 

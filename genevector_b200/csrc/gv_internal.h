@@ -42,7 +42,7 @@ int shard_transpose_dispatch(const void* values, int value_dtype, const int32_t*
                              int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
                              void* const* raw_dests, int n_dests, int own_index, int64_t raw_pitch,
                              uint32_t* ghist_local, unsigned long long* flags_dev,
-                             unsigned long long* flags_host, cudaStream_t st);
+                             unsigned long long* flags_host, int phase, cudaStream_t st);
 int shard_bins_dispatch(const DiscretizeArgs& a, const uint8_t* raw, const uint32_t* const* hists, int n_hists,
                         uint32_t* ghist_total, double* qtab_dev, uint8_t* lut_all, cudaStream_t st);
 int expand_onehot_dispatch(const void* bins_packed, int64_t pitch_bytes, int G, int rows_per_gene,

@@ -361,7 +361,12 @@ class Engine:
         # worker threads of the pageable upload (0 = from the core count; one process per GPU shares
         # the host cores with its peers)
         lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-        self.copy_threads = int(os.environ.get("GV_COPY_THREADS", "0")) or max(2, min(8, (os.cpu_count() or 8) // max(lw, 1)))
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+        env_threads = int(os.environ.get("GV_COPY_THREADS", "0"))
+        # every rank of the box uploads at once (sharded front end): a share of the cores each;
+        # one process alone (single GPU, or rank 0 of the broadcast front end): up to 16 of them
+        self.copy_threads = env_threads or max(2, min(8, ncpu // max(lw, 1)))
+        self.copy_threads_alone = env_threads or max(2, min(16, ncpu - 2))
         # how pageable arrays are read: "staged" (worker threads copy into a pinned ring) or
         # "registered" (the caller's pages are page-locked in place: no CPU pass over the data, which is
         # what the ranks of a box want when they all upload at once)
@@ -371,6 +376,9 @@ class Engine:
         self.defer_release = False
         # pack count data while staging (GV_PACK_UPLOADS=0 turns it off); bytes of the last upload
         self.pack_uploads = os.environ.get("GV_PACK_UPLOADS", "1") != "0"
+        # chunks a rank's block of cells is uploaded in by the sharded front end (1 = no overlap)
+        self.front_chunks = int(os.environ.get("GV_FRONT_CHUNKS", "4"))
+        self.front_chunk_nnz = max(1, int(os.environ.get("GV_FRONT_CHUNK_NNZ", str(4 << 20))))   # entries per chunk, at least
         self.last_upload_bytes = 0
 
     # kernels launched by each entry point (memsets / copies not counted)
@@ -403,7 +411,8 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def upload_csr(self, X, pinned: bool = False, rows: Optional[tuple] = None, pack: bool = False) -> CsrDevice:
+    def upload_csr(self, X, pinned: bool = False, rows: Optional[tuple] = None, pack: bool = False,
+                   alone: bool = True) -> CsrDevice:
         """scipy CSR (host) -> device tensors.  Integer dtypes are converted to the smallest float
         type that holds them exactly (discretisation arithmetic is identical: see DESIGN.md).
         The arrays are pageable host memory (the reference hands over adata.X, data.py:171): they go
@@ -415,7 +424,8 @@ class Engine:
         pack: count data (float32 integers <= 255, at most 65,536 genes) are packed to uint8 values +
         uint16 column indices by the staging pass itself (3 bytes per entry cross the PCIe link instead
         of 8); data that do not fit are uploaded as they are.  Packed matrices feed the count path of the
-        discretisation only (the MI / matrix-target calls); other consumers upload with pack=False."""
+        discretisation only (the MI / matrix-target calls); other consumers upload with pack=False.
+        alone: no other process of the box is uploading at the same time (more staging threads)."""
         import time
         import scipy.sparse as sp
         t_up = time.perf_counter()
@@ -444,6 +454,7 @@ class Engine:
         if e0:
             ptr = ptr - e0
         data = np.ascontiguousarray(data)
+        threads = self.copy_threads_alone if alone else self.copy_threads
         with torch.cuda.device(self.device):
             st = self._stream()
             dp = torch.empty(ptr.shape, dtype=torch.int64, device=self.device)
@@ -454,10 +465,10 @@ class Engine:
                 dc = torch.empty(cols.shape, dtype=torch.uint16, device=self.device)
                 fits = np.zeros(1, dtype=np.int32)
                 _lib.call("gv_upload_packed_counts", dv.data_ptr(), dc.data_ptr(), data.ctypes.data, cols.ctypes.data,
-                          data.size, self.copy_threads, fits.ctypes.data, st)
+                          data.size, threads, fits.ctypes.data, st)
                 packed = bool(fits[0])
                 if packed:
-                    _lib.call("gv_upload_pageable", dp.data_ptr(), ptr.ctypes.data, ptr.nbytes, self.copy_threads, st)
+                    _lib.call("gv_upload_pageable", dp.data_ptr(), ptr.ctypes.data, ptr.nbytes, threads, st)
                     self.last_upload_bytes = int(data.size * 3 + ptr.nbytes)
                     self._timed_host("upload_csr: host side of the copies (packed counts)", t_st)
             if not packed:
@@ -476,7 +487,7 @@ class Engine:
                         self._upload_tokens.append((tok.value, src))      # src stays alive until released
                 else:
                     _lib.call("gv_upload_pageable", dst.data_ptr(), src.ctypes.data, src.nbytes,
-                              self.copy_threads, st)
+                              threads, st)
             if not packed:
                 self._timed_host("upload_csr: host side of the copies", t_st)
             csr = CsrDevice(dv, dc, dp, r1 - r0, n_genes, packed)
@@ -490,7 +501,7 @@ class Engine:
                     Xc = X.copy()
                     Xc.sum_duplicates()             # sorts the indices and merges duplicate entries
                     Xc._has_canonical_format = True
-                    return self.upload_csr(Xc, rows=rows, pack=pack)
+                    return self.upload_csr(Xc, rows=rows, pack=pack, alone=alone)
         if not self.defer_release:
             self.release_uploads()
         self._timed_host("upload_csr (host side: staging + canonical check)", t_up)
@@ -954,12 +965,10 @@ class Engine:
     def _peer_block(self, n_cells, n_genes, rank, world, pool):
         """Allocate (once per shape) this rank's peer-visible block and map the other ranks'."""
         import ctypes as C
-        if not hasattr(self, "_peer_blocks"):
-            self._peer_blocks, self._peer_epoch = {}, 0
-        key = (n_cells, n_genes, world)
-        if key in self._peer_blocks:
-            return self._peer_blocks[key]
-        if len(self._peer_blocks) >= 4:
+        key = (n_cells, n_genes, world, self.device.index)
+        if key in pool.peer_blocks:
+            return pool.peer_blocks[key]
+        if len(pool.peer_blocks) >= 4:
             return None
         kp, pitch, lay, total1 = block_layout(n_cells, n_genes, 0, 1)
         off = dict(lay)
@@ -968,8 +977,8 @@ class Engine:
                              ("flags", 256), ("qtab", 8192), ("luts", n_genes * 256)):
             off[name] = (cur, nbytes)
             cur += _align(nbytes)
-        self._peer_epoch += 1
-        epoch = self._peer_epoch
+        pool.peer_epoch += 1
+        epoch = pool.peer_epoch
         own, ok = C.c_void_p(), 1
         handle = (C.c_uint8 * 64)()
         try:
@@ -1006,26 +1015,27 @@ class Engine:
         if not ok:
             # some rank cannot allocate or map peer memory: every rank drops the sharded front end
             self._shard_disabled = True
-            self._peer_blocks[key] = None
+            pool.peer_blocks[key] = None
             return None
         tensor = torch.as_tensor(_DevPtr(own.value, cur), device=self.device)
         pb = PeerBlock(own.value, cur, ptrs, off, tensor)
-        self._peer_blocks[key] = pb
+        pool.peer_blocks[key] = pb
         return pb
 
-    def _shard_front(self, csr_local, blk_range, n_cells, n_genes, n_bins, signed, rank, world, pool):
+    def _shard_front(self, chunks, n_cells, n_genes, n_bins, signed, rank, world, pool):
         """Sharded discretisation: returns the BinBlock (views into this rank's peer block), or None
-        when the data do not qualify (every rank decides the same from the combined data flags)."""
+        when the data do not qualify (every rank decides the same from the combined data flags).
+        chunks: iterable of (CsrDevice of a run of this rank's cells, (first block, end block)), consumed
+        lazily -- a chunk's transposition and peer copies are enqueued before the next chunk is produced,
+        so they run under its upload."""
         import ctypes as C
         if not 1 <= n_bins <= 15:
             return None                      # one byte per cell (n_bins 16..31): the broadcast front end
         pb = self._peer_block(n_cells, n_genes, rank, world, pool)
         if pb is None:
             return None
-        if not hasattr(self, "_front_seq"):
-            self._front_seq = 0
-        self._front_seq += 1
-        step = self._front_seq
+        pool.front_seq += 1
+        step = pool.front_seq
         kp, pitch, lay, _ = block_layout(n_cells, n_genes, 0, 1)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
@@ -1039,11 +1049,22 @@ class Engine:
                 ev[0].record(stream)
             dests = (C.c_void_p * world)(*[p + pb.off["val"][0] for p in pb.ptrs])
             flags = np.zeros(2, dtype=np.uint64)
-            dt = csr_local.dtype_code
-            _lib.call("gv_shard_transpose", csr_local.values.data_ptr(), dt, csr_local.col_idx.data_ptr(),
-                      csr_local.row_ptr.data_ptr(), csr_local.n_cells, n_genes, blk_range[0], blk_range[1],
-                      dests, world, rank, kp, pb.own_ptr + pb.off["ghist"][0], pb.own_ptr + pb.off["flags"][0],
-                      flags.ctypes.data, stream.cuda_stream)
+            dt, first, prev = _lib.GV_F32, True, None
+
+            def transpose(item, phase):
+                c, (c0, c1) = item
+                _lib.call("gv_shard_transpose", c.values.data_ptr(), c.dtype_code, c.col_idx.data_ptr(),
+                          c.row_ptr.data_ptr(), c.n_cells, n_genes, c0, c1, dests, world, rank, kp,
+                          pb.own_ptr + pb.off["ghist"][0], pb.own_ptr + pb.off["flags"][0], flags.ctypes.data,
+                          phase, stream.cuda_stream)
+                return _lib.GV_F64 if c.dtype_code == _lib.GV_F64 else _lib.GV_F32
+
+            for item in chunks:                  # producing the next chunk (its upload) overlaps the previous one
+                if prev is not None:
+                    dt = transpose(prev, 1 if first else 0)
+                    first = False
+                prev = item
+            dt = transpose(prev, (1 if first else 0) | 2)
             pool.scratch_store(11, int(flags[0]))
             pool.scratch_store(12, int(flags[1]))
             pool.scratch_store(10, step)
@@ -1113,7 +1134,7 @@ class Engine:
                 e0, e1 = int(csr.row_ptr[r0]), int(csr.row_ptr[r1])
                 self._sched_cache[key] = CsrDevice(csr.values[e0:e1], csr.col_idx[e0:e1],
                                                    (csr.row_ptr[r0:r1 + 1] - e0).contiguous(), r1 - r0, n_genes)
-            blk = self._shard_front(self._sched_cache[key], (b0, b1), n_cells, n_genes, n_bins, signed, rank,
+            blk = self._shard_front([(self._sched_cache[key], (b0, b1))], n_cells, n_genes, n_bins, signed, rank,
                                     world, pool)
             if blk is not None:
                 return self._mi_after_front(blk, signed, rank, world, out, None, "numpy")
@@ -1140,8 +1161,19 @@ class Engine:
         pool = get_pool()
         n_cells, n_genes = X.shape
         b0, b1, r0, r1 = self.shard_cells(n_cells, rank, world)
-        csr_local = self.upload_csr(X, rows=(r0, r1), pack=True)
-        blk = self._shard_front(csr_local, (b0, b1), n_cells, n_genes, n_bins, signed, rank, world, pool)
+        # the rank's cells go up in a few chunks of whole 128-cell blocks: the exchange of a chunk runs
+        # under the (host-bound) upload of the next
+        nnz_local = int(X.indptr[r1]) - int(X.indptr[r0])
+        n_chunks = max(1, min(self.front_chunks, (b1 - b0), nnz_local // self.front_chunk_nnz))
+
+        def chunks():
+            for c in range(n_chunks):
+                c0, c1 = b0 + (b1 - b0) * c // n_chunks, b0 + (b1 - b0) * (c + 1) // n_chunks
+                if c1 > c0 or n_chunks == 1:
+                    yield (self.upload_csr(X, rows=(min(n_cells, c0 * 128), min(n_cells, c1 * 128)), pack=True,
+                                           alone=False), (c0, c1))
+
+        blk = self._shard_front(chunks(), n_cells, n_genes, n_bins, signed, rank, world, pool)
         if blk is None:
             if required:
                 raise GvError("mi_from_host_sharded", -4, "the data do not qualify for the sharded front end "

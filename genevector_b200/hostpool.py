@@ -78,7 +78,8 @@ class SharedResultPool:
         self.seq = 0
         self.slots = {}           # slot -> (generation, _Mapping)
         self._unlinked = set()
-        self._views = []          # (weakref to the array handed out, slot) -- diagnostic only
+        # state of the sharded front end that lives and dies with this control segment (engine.py)
+        self.peer_blocks, self.peer_epoch, self.front_seq = {}, 0, 0
         self.ctl = None
         if rank == 0:
             self.ctl = _Mapping(base + ".ctl", _CTL_WORDS * 8, True, False)
@@ -220,7 +221,13 @@ def get_pool(group=None, cuda: bool = True) -> SharedResultPool:
     """The pool of a process group.  The first call is a setup hand-shake (one broadcast of the segment
     base name, like the creation of the NCCL communicator itself); no later call uses the group."""
     import torch.distributed as dist
-    key = id(group) if group is not None else None
+    if group is not None:
+        key = id(group)
+    else:
+        try:                                  # a re-initialised default group gets a pool of its own
+            key = ("world", id(dist.distributed_c10d._get_default_group()))
+        except Exception:
+            key = ("world", dist.get_world_size())
     if key in _pools:
         return _pools[key]
     rank, world = dist.get_rank(group), dist.get_world_size(group)

@@ -152,8 +152,11 @@ int gv_csr_check(const void* col_idx, int value_dtype, const int64_t* row_ptr, i
  * pushed to every peer by one 2-D peer copy per destination (copy engines over NVLink / NVSwitch).  The block ranges of the ranks must tile [0, raw_pitch / 128).
  * ghist_local (uint32 [n_genes][256]) receives this rank's part of the per-gene value histogram;
  * flags_dev: 64 bytes of device scratch; data_flags_out_host as gv_discretize_csr (the caller combines
- * them over the ranks: OR of [0], max of [1]).  Synchronous: when it returns, this rank's stores have
- * landed in every destination.
+ * them over the ranks: OR of [0], max of [1]).  A rank may feed its cells in several chunks (each a run
+ * of whole blocks with its own CSR arrays), so that a chunk's transposition and peer copies run under the
+ * upload of the next: phase bit 0 marks the first chunk (histogram and flags are zeroed), bit 1 the last
+ * (the flags are read back and the stream is synchronised: when that call returns, all of this rank's
+ * rows have landed in every destination); phase 3 = everything in one call.
  * After every rank has returned from it (host hand-shake, gv_flag_*), gv_shard_bins sums the ranks'
  * histograms (hists_host: n_hists device pointers, peers' via gv_ipc_open) into ghist_total and bins all
  * genes from this rank's complete `raw`: the same outputs as gv_discretize_csr on the count path.
@@ -163,7 +166,8 @@ int gv_csr_check(const void* col_idx, int value_dtype, const int64_t* row_ptr, i
 int gv_shard_transpose(const void* values, int value_dtype, const int32_t* col_idx, const int64_t* row_ptr_local,
                        int64_t n_cells_local, int n_genes, int64_t blk_begin, int64_t blk_end,
                        void* const* raw_dests_host, int n_dests, int own_index, int64_t raw_pitch,
-                       uint32_t* ghist_local, void* flags_dev, uint64_t* data_flags_out_host, void* stream);
+                       uint32_t* ghist_local, void* flags_dev, uint64_t* data_flags_out_host, int phase,
+                       void* stream);
 int gv_shard_bins(int value_dtype, int64_t n_cells, int n_genes, int n_bins, const double* q_table_host,
                   const void* raw, const void* const* hists_host, int n_hists, uint32_t* ghist_total,
                   double* qtab_dev, void* lut_ws, void* bins_packed, int64_t bins_pitch_bytes, int32_t* n_bins_per_gene,

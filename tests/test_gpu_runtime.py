@@ -141,7 +141,7 @@ def test_sharded_front_end_kernels_reproduce_the_bin_block(engine, world, signed
             flags = np.zeros(2, dtype=np.uint64)
             _lib.call("gv_shard_transpose", loc.values.data_ptr(), _lib.GV_F32, loc.col_idx.data_ptr(),
                       loc.row_ptr.data_ptr(), loc.n_cells, n_genes, b0, b1, dests, world, rank, kp,
-                      hists[rank].data_ptr(), fl.data_ptr(), flags.ctypes.data, st)
+                      hists[rank].data_ptr(), fl.data_ptr(), flags.ctypes.data, 3, st)
             f0 |= int(flags[0])
             f1 = max(f1, int(flags[1]))
         assert f0 == 0 and f1 == int(X.data.max())
@@ -303,9 +303,11 @@ def test_sharded_public_calls_on_all_visible_gpus():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least two GPUs")
+    env = dict(os.environ, GV_FRONT_CHUNK_NNZ="20000")       # small matrices too go up in several chunks
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29731",
-                        os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
+                        os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900,
+                       env=env)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"dist_check_world{n}.log"), "w") as f:
         f.write(r.stdout + "\n---- stderr ----\n" + r.stderr[-20000:])
