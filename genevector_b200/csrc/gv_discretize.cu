@@ -760,7 +760,7 @@ constexpr int TP_STRIDE = TP_CB + 4;       // tile row stride: 33 words, conflic
 constexpr int TP_GR = 704;                 // genes per range
 constexpr int TP_THREADS = 512;
 constexpr int TP_WARPS = TP_THREADS / 32;
-constexpr int TP_ROWS_PER_WARP = TP_CB / TP_WARPS;   // 8, taken 4 at a time
+constexpr int TP_ROWS_PER_WARP = TP_CB / TP_WARPS;   // 8, all in flight at once
 constexpr int TP_HV = 16;                  // values below this are counted in shared memory
 constexpr size_t TP_TILE_BYTES = size_t(TP_GR) * TP_STRIDE;
 constexpr size_t TP_HIST_BYTES = size_t(TP_GR) * TP_HV;   // one byte per (gene, value): <= 128 cells
@@ -791,8 +791,9 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
   extern __shared__ __align__(16) uint8_t tp_smem[];
   uint8_t* tile = tp_smem;
   uint32_t* hcnt = reinterpret_cast<uint32_t*>(tp_smem + TP_TILE_BYTES);
-  int64_t* cur_s = reinterpret_cast<int64_t*>(tp_smem + TP_TILE_BYTES + TP_HIST_BYTES);
-  int64_t* end_s = cur_s + TP_CB;
+  // per-row cursors, relative to the block's first entry (a block holds at most 128 x G entries)
+  uint32_t* cur_s = reinterpret_cast<uint32_t*>(tp_smem + TP_TILE_BYTES + TP_HIST_BYTES);
+  uint32_t* end_s = cur_s + TP_CB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned f = 0;
   unsigned long long vmax = 0;
@@ -801,36 +802,40 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
 
   for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     const int64_t c0 = blk * TP_CB;
+    const int64_t base = row_ptr[c0 < n_cells ? c0 : n_cells];
+    const VT* __restrict__ vals_b = values + base;
+    const CT* __restrict__ cols_b = col_idx + base;
     if (tid < TP_CB) {
       const int64_t r = c0 + tid;
-      cur_s[tid] = r < n_cells ? row_ptr[r] : 0;
-      end_s[tid] = r < n_cells ? row_ptr[r + 1] : 0;
+      cur_s[tid] = r < n_cells ? uint32_t(row_ptr[r] - base) : 0u;
+      end_s[tid] = r < n_cells ? uint32_t(row_ptr[r + 1] - base) : 0u;
     }
     __syncthreads();
     for (int g0 = 0; g0 < G; g0 += TP_GR) {
       const int g1 = g0 + TP_GR < G ? g0 + TP_GR : G;
-      // ---- scatter this range's entries of my rows into the tile (4 rows in flight per warp)
-#pragma unroll 1
-      for (int rg = 0; rg < TP_ROWS_PER_WARP; rg += 4) {
-        int64_t cur[4], end[4];
+      // ---- scatter this range's entries of my rows into the tile: all eight rows of the warp are in
+      // flight at once (16 independent loads per lane and step; the walk is latency-bound)
+      {
+        constexpr int rg = 0;
+        uint32_t cur[TP_ROWS_PER_WARP], end[TP_ROWS_PER_WARP];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < TP_ROWS_PER_WARP; ++k) {
           const int rl = warp + (rg + k) * TP_WARPS;
           cur[k] = cur_s[rl]; end[k] = end_s[rl];
         }
         bool more = true;
         while (more) {
-          int32_t cc[4]; T vv[4];
+          int32_t cc[TP_ROWS_PER_WARP]; T vv[TP_ROWS_PER_WARP];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int64_t e = cur[k] + lane;
+          for (int k = 0; k < TP_ROWS_PER_WARP; ++k) {
+            const uint32_t e = cur[k] + lane;
             const bool ok = e < end[k];
-            cc[k] = ok ? int32_t(col_idx[e]) : 0x7fffffff;
-            vv[k] = ok ? T(values[e]) : T(0);
+            cc[k] = ok ? int32_t(cols_b[e]) : 0x7fffffff;
+            vv[k] = ok ? T(vals_b[e]) : T(0);
           }
           more = false;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < TP_ROWS_PER_WARP; ++k) {
             const bool in = cc[k] < g1;
             const int32_t prev = __shfl_up_sync(0xffffffffu, cc[k], 1);
             if (in) {
@@ -860,7 +865,7 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
         }
         if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) cur_s[warp + (rg + k) * TP_WARPS] = cur[k];
+          for (int k = 0; k < TP_ROWS_PER_WARP; ++k) cur_s[warp + (rg + k) * TP_WARPS] = cur[k];
         }
       }
       __syncthreads();

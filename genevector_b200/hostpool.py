@@ -55,8 +55,8 @@ class _Mapping:
 
     def unlink(self):
         try:
-            os.unlink("/dev/shm" + self.name)
-        except OSError:
+            _lib.call("gv_shm_close", None, 0, 0, self.name.encode())     # shm_unlink only
+        except Exception:
             pass
 
     def close(self):

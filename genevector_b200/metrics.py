@@ -80,8 +80,6 @@ def _run_to_host(eng, n_genes, gene_names, run, front=None):
     (hostpool.py); every rank copies the rectangles of its own tiles into it and, after a per-rank
     completion flag, every rank returns the full matrix.  No reduce, no gather."""
     import time
-    import torch
-    from .engine import HostSink
     rank, world = _dist_info()
     t0 = time.perf_counter()
     eng.defer_release = True
