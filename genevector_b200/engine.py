@@ -376,8 +376,10 @@ class Engine:
         self.defer_release = False
         # pack count data while staging (GV_PACK_UPLOADS=0 turns it off); bytes of the last upload
         self.pack_uploads = os.environ.get("GV_PACK_UPLOADS", "1") != "0"
-        # chunks a rank's block of cells is uploaded in by the sharded front end (1 = no overlap)
-        self.front_chunks = int(os.environ.get("GV_FRONT_CHUNKS", "4"))
+        # chunks a rank's block of cells is uploaded in by the sharded front end (1 = one piece; more
+        # overlap a chunk's exchange with the next chunk's upload -- measured: no gain at 2 or 8 GPUs,
+        # the per-chunk hand-overs cost what the overlap saves)
+        self.front_chunks = int(os.environ.get("GV_FRONT_CHUNKS", "1"))
         self.front_chunk_nnz = max(1, int(os.environ.get("GV_FRONT_CHUNK_NNZ", str(4 << 20))))   # entries per chunk, at least
         self.last_upload_bytes = 0
 
