@@ -766,14 +766,7 @@ constexpr size_t TP_TILE_BYTES = size_t(TP_GR) * TP_STRIDE;
 constexpr size_t TP_HIST_BYTES = size_t(TP_GR) * TP_HV;   // one byte per (gene, value): <= 128 cells
 constexpr size_t TP_SMEM = TP_TILE_BYTES + TP_HIST_BYTES + 2 * TP_CB * sizeof(int64_t);
 
-// Destinations of the dense rows: this GPU's own buffer and, for the sharded front end, the same
-// buffer of every peer GPU of the box (peer-mapped device memory: the stores travel over NVLink /
-// NVSwitch, so the transposition of a rank's block of cells IS its part of the all-gather).
-constexpr int TP_MAX_PEERS = 8;
-struct RawDests {
-  uint8_t* raw[TP_MAX_PEERS];
-  int n;
-};
+constexpr int TP_MAX_PEERS = 8;            // ranks of one box in the sharded front end
 
 // row_ptr / n_cells describe the CSR rows this launch owns (all of them, or a rank's block of cells);
 // blk_offset is the index of its first 128-cell block in the whole matrix (column offset in `raw`).
@@ -784,7 +777,7 @@ template <typename T, typename VT = T, typename CT = int32_t>
 __global__ void __launch_bounds__(TP_THREADS, 2)
 k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx,
                    const int64_t* __restrict__ row_ptr, int64_t n_cells, int G,
-                   const RawDests dests, int64_t raw_pitch, int64_t n_blocks, int64_t blk_offset,
+                   uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t n_blocks, int64_t blk_offset,
                    uint32_t* __restrict__ ghist, unsigned long long* __restrict__ flags) {
   // ghist [G][256]: per-gene value histogram, accumulated on the way (small values in packed byte
   // counters in shared memory, flushed once per (cell block, gene range); the rest directly)
@@ -874,8 +867,7 @@ k_transpose_counts(const VT* __restrict__ values, const CT* __restrict__ col_idx
         uint32_t* w = reinterpret_cast<uint32_t*>(tile + gl * TP_STRIDE) + lane;
         const uint32_t x = *w;
         *w = 0u;
-        const int64_t o = int64_t(g0 + gl) * raw_pitch + (blk_offset * TP_CB + c0) + 4 * lane;
-        for (int p = 0; p < dests.n; ++p) *reinterpret_cast<uint32_t*>(dests.raw[p] + o) = x;
+        *reinterpret_cast<uint32_t*>(raw + int64_t(g0 + gl) * raw_pitch + (blk_offset * TP_CB + c0) + 4 * lane) = x;
       }
       // ---- flush the packed byte counters of this (cell block, gene range)
       for (int gl = tid; gl < g1 - g0; gl += TP_THREADS) {
@@ -1381,10 +1373,7 @@ static int discretize_impl(const DiscretizeArgs& a, cudaStream_t st) {
     GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
     const int64_t n_blocks = kcells / TP_CB;
     const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
-    RawDests dests;
-    dests.n = 1;
-    dests.raw[0] = raw;
-    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, a.row_ptr, a.n_cells, G, dests,
+    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, a.row_ptr, a.n_cells, G, raw,
                                                      kcells, n_blocks, 0, ghist, flags);
     GV_LAUNCH_CHECK();
     GV_CUDA_TRY(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
@@ -1750,12 +1739,11 @@ static cudaStream_t* peer_streams(int device) {
 }
 
 // own_index: which of raw_dests is this rank's own buffer.  The rank's block of cells is transposed into
-// its own dense rows; the slab [G][its cells] then goes to every peer.  Two ways (GV_SHARD_PUSH):
-//   "dma" (default)  one 2-D peer copy per destination on its own stream (copy engines over NVLink:
-//                    full-rate 25 KB rows, the SMs are free again after the 0.5 ms transposition)
-//   "stores"         the transposition kernel stores every 128-byte line to all destinations itself
-//                    (measured on 8 GPUs: 53 ms for 3.5 GB per GPU -- 4-byte peer stores from a
-//                    latency-bound kernel do not fill NVLink; kept for the comparison)
+// its own dense rows; the slab [G][its cells] then goes to every peer as one 2-D peer copy per
+// destination on its own stream (copy engines over NVLink: full-rate 25 KB rows, and the SMs are free
+// again after the 0.5 ms transposition).  Storing every 128-byte line to all destinations from inside the
+// transposition kernel was the first version: 3.9 ms at 2 GPUs but 53 ms at 8 (4-byte peer stores from a
+// latency-bound kernel do not fill NVLink) against 9 ms for the copies -- measured, removed.
 template <typename T, bool PACKED = false>
 static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, const int64_t* row_ptr,
                                 int64_t n_cells_local, int G, int64_t blk_begin, int64_t blk_end,
@@ -1766,15 +1754,7 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, 
   using CT = typename std::conditional<PACKED, uint16_t, int32_t>::type;
   const VT* values = static_cast<const VT*>(values_v);
   const CT* col_idx = reinterpret_cast<const CT*>(col_idx_v);
-  static const bool push_stores = getenv("GV_SHARD_PUSH") != nullptr && getenv("GV_SHARD_PUSH")[0] == 's';
-  RawDests dests;
-  if (push_stores) {
-    dests.n = n_dests;
-    for (int p = 0; p < n_dests; ++p) dests.raw[p] = static_cast<uint8_t*>(raw_dests[p]);
-  } else {
-    dests.n = 1;
-    dests.raw[0] = static_cast<uint8_t*>(raw_dests[own_index]);
-  }
+  uint8_t* own_raw = static_cast<uint8_t*>(raw_dests[own_index]);
   // phase bit 0: first chunk of this rank's cells (histogram and flags start from zero); bit 1: last
   // chunk (flags are read back and the stream is synchronised).  A rank may feed its block of cells in
   // several chunks, each one's transposition and peer copies running under the upload of the next.
@@ -1788,10 +1768,10 @@ static int shard_transpose_impl(const void* values_v, const int32_t* col_idx_v, 
     GV_CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TP_SMEM)));
     const int sms = device_sm_count();
     const int64_t tgrid = n_blocks < int64_t(sms) * 2 ? n_blocks : int64_t(sms) * 2;
-    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, row_ptr, n_cells_local, G, dests, raw_pitch,
+    kt<<<unsigned(tgrid), TP_THREADS, TP_SMEM, st>>>(values, col_idx, row_ptr, n_cells_local, G, own_raw, raw_pitch,
                                                      n_blocks, blk_begin, ghist_local, flags_dev);
     GV_LAUNCH_CHECK();
-    if (!push_stores && n_dests > 1) {
+    if (n_dests > 1) {
       int device = 0;
       GV_CUDA_TRY(cudaGetDevice(&device));
       cudaStream_t* ps = peer_streams(device);
