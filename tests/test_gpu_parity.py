@@ -562,7 +562,7 @@ def test_bench_lines_carry_the_contract_keys(extra):
     import sys
     from conftest import ROOT
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "C2", "--steps", "2",
-                        "--warmup", "1", "--no-cpu-baseline"] + extra, capture_output=True, text=True, timeout=600)
+                        "--warmup", "3", "--no-cpu-baseline"] + extra, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -577,3 +577,9 @@ def test_bench_lines_carry_the_contract_keys(extra):
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in d["roofline"], key
     assert 0 < d["roofline"]["frac"] < 1.05 and "workload" in d["config"]
+    if "--target" not in extra:
+        # the e2e leg is the reference-facing plugin call
+        assert "target_mi" in d["e2e"]["note"] and d["e2e"]["h2d_bytes_per_step"] < d["e2e"]["host_csr_bytes"]
+    if not extra:
+        r8 = d["roofline_int8"]                      # the metric's own dtype, from a short INT8 pass
+        assert r8["achieved"] > 0 and 0 < r8["frac"] < 1.05 and "kind::i8" in r8["peak_note"]

@@ -1,3 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_runtime.py tests/test_gpu_fullsize.py -m gpu -q -x > gpurun_out/r02_gpu_tests13.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02_gpu_tests13.log
-python tools/disc_bench.py C4 3 0 | tail -2
-python tools/disc_bench.py C5 3 0 | tail -1
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_gpu_tests_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02_gpu_tests_final.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py > gpurun_out/r02_bench_default_final.json 2> gpurun_out/r02_bench_default_final.err; echo "bench rc=$?"; python tools/show_bench.py gpurun_out/r02_bench_default_final.json
+python bench.py --impl reference > gpurun_out/r02_bench_reference_final.json 2>/dev/null; head -c 700 gpurun_out/r02_bench_reference_final.json
