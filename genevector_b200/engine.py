@@ -1149,22 +1149,19 @@ class Engine:
             import time
             self.host_timings.setdefault(name, []).append((time.perf_counter() - t0) * 1e3)
 
-    def mi_from_host_sharded(self, X, n_bins=10, signed=False, rank=0, world=1, sign_rule="numpy",
-                             sink=None, required=False) -> bool:
-        """Sharded front end from a host scipy CSR: every rank uploads its own block of cells over its
-        own PCIe link, transposes it into every rank's dense rows over NVLink (peer stores) and bins
-        all genes locally; no NCCL call.  Returns False when the data do not qualify (not count data
-        <= 127 / 255, peer memory unavailable): the caller then takes the broadcast path."""
+    def _front_from_host_sharded(self, X, n_bins, value_rows_wanted, rank, world, required):
+        """Upload this rank's block of cells and run the sharded front end; the BinBlock, or None when
+        the data do not qualify (the caller then takes the broadcast path on every rank alike)."""
         from .hostpool import get_pool
         if self.resolve_front("sharded" if required else "auto", world) != "sharded":
             if required:
-                raise GvError("mi_from_host_sharded", -4, "the sharded front end is not available here")
-            return False
+                raise GvError("sharded front end", -4, "the sharded front end is not available here")
+            return None
         pool = get_pool()
         n_cells, n_genes = X.shape
         b0, b1, r0, r1 = self.shard_cells(n_cells, rank, world)
-        # the rank's cells go up in a few chunks of whole 128-cell blocks: the exchange of a chunk runs
-        # under the (host-bound) upload of the next
+        # the rank's cells may go up in a few chunks of whole 128-cell blocks (the exchange of a chunk
+        # then runs under the upload of the next; GV_FRONT_CHUNKS, default one piece)
         nnz_local = int(X.indptr[r1]) - int(X.indptr[r0])
         n_chunks = max(1, min(self.front_chunks, (b1 - b0), nnz_local // self.front_chunk_nnz))
 
@@ -1175,13 +1172,34 @@ class Engine:
                     yield (self.upload_csr(X, rows=(min(n_cells, c0 * 128), min(n_cells, c1 * 128)), pack=True,
                                            alone=False), (c0, c1))
 
-        blk = self._shard_front(chunks(), n_cells, n_genes, n_bins, signed, rank, world, pool)
+        blk = self._shard_front(chunks(), n_cells, n_genes, n_bins, value_rows_wanted, rank, world, pool)
+        if blk is None and required:
+            raise GvError("sharded front end", -4, "the data do not qualify for the sharded front end "
+                          "(count data <= 127 with value rows / 255 without, in canonical CSR)")
+        return blk
+
+    def mi_from_host_sharded(self, X, n_bins=10, signed=False, rank=0, world=1, sign_rule="numpy",
+                             sink=None, required=False) -> bool:
+        """Sharded front end from a host scipy CSR: every rank uploads its own block of cells over its
+        own PCIe link, transposes it, the slabs are exchanged by peer copies over NVLink and every rank
+        bins all genes locally; no NCCL call.  Returns False when the data do not qualify (not count data
+        <= 127 / 255, peer memory unavailable): the caller then takes the broadcast path."""
+        blk = self._front_from_host_sharded(X, n_bins, signed, rank, world, required)
         if blk is None:
-            if required:
-                raise GvError("mi_from_host_sharded", -4, "the data do not qualify for the sharded front end "
-                              "(count data <= 127 signed / 255 unsigned in canonical CSR)")
             return False
         self._mi_after_front(blk, signed, rank, world, None, sink, sign_rule)
+        return True
+
+    def target_from_host_sharded(self, X, kind: int, rank=0, world=1, sink=None) -> bool:
+        """Pearson / cosine on the sharded front end: its dense count rows (counts <= 127) are the
+        one-digit value-row operand of the co-moment contraction.  False = take the broadcast path
+        (Jaccard and Spearman need detection / rank rows, larger counts more digits)."""
+        if kind not in (_lib.GV_MOM_PEARSON, _lib.GV_MOM_COSINE):
+            return False
+        blk = self._front_from_host_sharded(X, 10, True, rank, world, False)
+        if blk is None:
+            return False
+        self.moment_scores(blk, kind, rank=rank, world=world, sink=sink)
         return True
 
     def target_from_csr(self, csr: Optional[CsrDevice], kind: int, ranks: bool = False,

@@ -185,6 +185,8 @@ def _moment_target(X, gene_names, kind, device=None, ranks=False):
         raise ValueError("gene_names must have one entry per column of X")
 
     def run(sink):
+        if world > 1 and not ranks and eng.target_from_host_sharded(X, kind, rank=rank, world=world, sink=sink):
+            return
         csr = eng.upload_csr(X, pack=True) if rank == 0 else None
         eng.target_from_csr(csr, kind, ranks=ranks, n_cells=n_cells, n_genes=n_genes, rank=rank, world=world,
                             sink=sink)

@@ -12,7 +12,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 from genevector_b200.engine import get_engine  # noqa: E402
-from genevector_b200.metrics import compute_mi_b200, target_pearson, target_spearman  # noqa: E402
+from genevector_b200.metrics import compute_mi_b200, target_cosine, target_pearson, target_spearman  # noqa: E402
 from genevector_b200.synth import synth_counts, gene_names  # noqa: E402
 from genevector_b200 import _lib  # noqa: E402
 
@@ -35,6 +35,7 @@ def main():
     calls = [(f"signed_mi[{f}]", (lambda M, f=f: compute_mi_b200(M, genes, signed=True, front=f))) for f in fronts]
     calls += [("mi_unsigned", lambda M: compute_mi_b200(M, genes, signed=False)),
               ("pearson", lambda M: target_pearson(M, genes)),
+              ("cosine", lambda M: target_cosine(M, genes)),
               ("spearman", lambda M: target_spearman(M, genes))]
     ok = True
     for name, fn in calls:
@@ -45,7 +46,8 @@ def main():
                 if name.startswith("signed_mi") or name == "mi_unsigned":
                     want = eng.mi_from_csr(c, N, G, signed=name.startswith("signed"))
                 else:
-                    want = eng.target_from_csr(c, _lib.GV_MOM_PEARSON, ranks=(name == "spearman"))
+                    want = eng.target_from_csr(c, _lib.GV_MOM_COSINE if name == "cosine" else _lib.GV_MOM_PEARSON,
+                                               ranks=(name == "spearman"))
                 same = np.array_equal(np.asarray(got).view(np.uint32), want.cpu().numpy().view(np.uint32))
                 ok &= same
                 print(f"world={world} rank={rank} {name:22s} {tag:8s} call {rep}: identical to single rank: {same}",
