@@ -508,3 +508,53 @@ def test_rounding_conventions_agree():
     row = dict(sm["G7"].items())
     assert all(sm["G7"][g] == row[g] for g in genes if g != "G7")
     assert np.array_equal(sm.rounded()[7], np.array([0.0 if g == "G7" else sm["G7"][g] for g in genes]))
+
+
+def test_shared_result_pool_slots_are_held_recycled_grown_and_bounded():
+    """hostpool.SharedResultPool (one rank, not page-locked: no CUDA here): a result slot stays held while
+    any numpy view of it is alive, is handed out again after the last view dies, is replaced by a larger
+    segment when the next matrix does not fit, and at most eight results can be alive at once."""
+    import gc
+    import os
+    from genevector_b200.hostpool import SharedResultPool
+    base = f"/gvb200_test_{os.getpid()}"
+    pool = SharedResultPool(0, 1, base, cuda=False, timeout_ms=2000)
+    try:
+        seq, slot, m = pool.begin(100 * 100 * 4)
+        m.array(np.float32, (100, 100))[:] = 3.0
+        pool.finish(seq, slot)
+        a = pool.matrix(slot, 100)
+        assert a.shape == (100, 100) and float(a.sum()) == 30000.0
+        row = a[7]                                  # a derived view keeps the slot held
+        del a
+        gc.collect()
+        seq2, slot2, _ = pool.begin(100 * 100 * 4)
+        assert slot2 != slot, "a slot with a live view was handed out again"
+        pool.finish(seq2, slot2)
+        pool.release(slot2, pool.slots[slot2][0])   # nobody took a view of it
+        assert float(row.sum()) == 300.0
+        del row
+        gc.collect()
+        seq3, slot3, m3 = pool.begin(100 * 100 * 4)
+        assert slot3 == slot, "the released slot is recycled"
+        pool.finish(seq3, slot3)
+        pool.release(slot3, pool.slots[slot3][0])
+        gen_before = pool.slots[slot][0]
+        seq4, slot4, m4 = pool.begin(300 * 300 * 4)  # does not fit: same slot, new generation
+        assert slot4 == slot and pool.slots[slot][0] == gen_before + 1 and m4.nbytes >= 300 * 300 * 4
+        pool.finish(seq4, slot4)
+        held = [pool.matrix(slot4, 300)]
+        for _ in range(7):
+            sq, sl, _ = pool.begin(64)
+            pool.finish(sq, sl)
+            held.append(pool.matrix(sl, 4))
+        with pytest.raises(RuntimeError, match="still referenced"):
+            pool.begin(64)
+        del held
+        gc.collect()
+        sq, sl, _ = pool.begin(64)                   # everything was released again
+        pool.finish(sq, sl)
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith(base[1:] + ".s")], "result segments are unlinked"
+    finally:
+        pool.close()
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith(base[1:])]

@@ -1,4 +1,6 @@
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_gpu_tests_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02_gpu_tests_final.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py > gpurun_out/r02_bench_default_final.json 2> gpurun_out/r02_bench_default_final.err; echo "bench rc=$?"; python tools/show_bench.py gpurun_out/r02_bench_default_final.json
-python bench.py --impl reference > gpurun_out/r02_bench_reference_final.json 2>/dev/null; head -c 700 gpurun_out/r02_bench_reference_final.json
+export GV_COOPERATIVE=0
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-int8-pass --operand int8"
+$CMD > gpurun_out/r02_prof_plain.log 2>&1 && ncu --set full --clock-control none --kernel-name-base demangled -k regex:MiEpi -c 1 -o gpurun_out/r02_mi_c4_int8_v2 $CMD > gpurun_out/r02_prof_ncu2.log 2>&1; echo "mi int8 rc=$?"
+CMD="python tools/disc_bench.py C4 1 0"
+$CMD > gpurun_out/r02_prof_plain.log 2>&1 && ncu --set full --clock-control none -k "regex:k_transpose_counts|k_rows_to_bins" -s 2 -c 2 -o gpurun_out/r02_disc_c4_v4 $CMD > gpurun_out/r02_prof_ncu3.log 2>&1; echo "disc rc=$?"
+ls -la gpurun_out/r02_mi_c4_int8_v2.ncu-rep gpurun_out/r02_disc_c4_v4.ncu-rep
