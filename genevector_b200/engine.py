@@ -5,13 +5,18 @@ buffers and for the NCCL broadcast; every compute step is a call into libgvb200.
 (include/gvb200.h).  No step has a CPU or PyTorch fallback.
 
 Pipeline for all-pairs (signed) MI on one rank:
-    CSR (host) --H2D--> gv_discretize_csr  -> packed 4-bit bins + marginals (+ INT8 value rows)
+    CSR (pageable host arrays) --gv_upload_packed_counts / gv_upload_pageable--> device
+                        gv_discretize_csr  -> packed bins + marginals (+ INT8 value rows)
                         gv_moment_tiles    -> int8 Pearson-sign matrix           (signed only)
-                        gv_expand_onehot   -> INT8 one-hot operand (K-major)
-                        gv_mi_tiles        -> float32 score matrix [G][G]
-With several ranks (one process per GPU, torch.distributed/NCCL): rank 0 discretises, one
-broadcast replicates the bin block, every rank expands locally and takes a contiguous slice of
-the upper-triangular tile schedule; no other collective.
+                        gv_expand_onehot   -> FP4 / INT8 one-hot operand (K-major)
+                        gv_mi_tiles        -> float32 score matrix [G][G], launched in a few pieces whose
+                                              result rectangles stream to the host matrix (gv_copy_rect_d2h)
+With several ranks (one process per GPU of one box) every rank takes a contiguous slice of the
+upper-triangular tile schedule and writes its result rectangles into the one shared host matrix
+(hostpool.py).  The discretised matrix reaches every rank by one of two front ends: "broadcast"
+(rank 0 discretises, one NCCL broadcast of the bin block) or "sharded" (every rank uploads and
+transposes its own block of cells, the slabs are exchanged by peer copies over NVLink, every rank bins
+all genes locally: gv_shard_transpose / gv_shard_bins, no NCCL call).
 """
 from __future__ import annotations
 
