@@ -22,6 +22,20 @@ def test_library_exports_every_declared_symbol():
     assert lib.gv_abi_version() == _lib.GV_ABI_VERSION
 
 
+def test_ctypes_signatures_have_the_arity_the_header_declares():
+    """Every function of include/gvb200.h is bound with as many arguments as it declares (a mismatch would
+    shift every later argument of a call)."""
+    from genevector_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gvb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decls = re.findall(r"\b(gv_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(decls) >= 40
+    for name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert len(_lib.SIGNATURES[name][1]) == n, name
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device every compute entry point refuses; nothing routes to the oracle."""
     import torch
