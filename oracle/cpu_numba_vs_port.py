@@ -1,4 +1,4 @@
-"""the reference's own Numba pair kernel (unmodified, JIT-warmed, driven through the
+"""TEST INFRASTRUCTURE (lives under oracle/ because it runs the oracle).  BASELINE.md section 4: the reference's own Numba pair kernel (unmodified, JIT-warmed, driven through the
 dummy-column wrapper that neutralises its index bug) timed beside the C/OpenMP port of src/lib.rs that
 bench.py uses as its CPU arm.  Build container only (needs /root/reference); the GPU box has no reference
 tree, so this is a builder-run number kept in profiles/."""
@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gen_golden  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from genevector_b200.synth import synth_counts  # noqa: E402
