@@ -228,7 +228,7 @@ def tile_slice(op_rows: int, cta_group: int, band: int, rank: int = 0, world: in
 
 
 def host_pieces(op_rows: int, cta_group: int, band: int, genes_per_block: int, n_genes: int,
-                rank: int = 0, world: int = 1, chunks: int = 6):
+                rank: int = 0, world: int = 1, chunks: int = 8):
     """How a rank's slice of the schedule is launched so that its results can stream to the host
     under the computation: a list of (t0, t1, rects) with t0 / t1 tile offsets inside the slice and
     rects = [(row0, row1, col0, col1), ...] the gene rectangles of the result matrix that are final
@@ -237,7 +237,11 @@ def host_pieces(op_rows: int, cta_group: int, band: int, genes_per_block: int, n
     world == 1: pieces end at band boundaries and a tile of band b only writes rows of bands >= b, so
     the rows of the finished bands are final: one contiguous block of full rows per piece.
     world > 1: a piece is a run of whole tile columns of bands (see _cut_points); per band it owns
-    the rectangle (band rows) x (its columns) and the mirror image below the band."""
+    the rectangle (band rows) x (its columns) and the mirror image below the band.
+
+    Pieces halve in size (1/2, 1/4, ... of the slice): the copy of a piece runs under the next piece's
+    kernel, only the last piece's copy is exposed, and late bands are short, so an equal split would
+    leave ~40 % of the matrix rows to the exposed copy; the halving split leaves a few per cent."""
     th, tile_m = schedule_host(op_rows, cta_group, band)
     b = rank_bounds(th, tile_m, band, world)
     lo, hi = b[rank], b[rank + 1]
@@ -252,7 +256,7 @@ def host_pieces(op_rows: int, cta_group: int, band: int, genes_per_block: int, n
 
     if world == 1:
         starts = np.flatnonzero(np.diff(band_id, prepend=-1))
-        inner = sorted({int(starts[np.abs(starts - n * k // chunks).argmin()]) for k in range(1, chunks)} - {0})
+        inner = sorted({int(starts[np.abs(starts - (n - (n >> k))).argmin()]) for k in range(1, chunks)} - {0, n})
         ends = inner + [n]
         out, t0, g0 = [], 0, 0
         for t1 in ends:
@@ -261,7 +265,7 @@ def host_pieces(op_rows: int, cta_group: int, band: int, genes_per_block: int, n
             t0, g0 = t1, g1
         return out
     inside = cuts[(cuts > lo) & (cuts < hi)]
-    inner = sorted({int(inside[np.abs(inside - (lo + n * k // chunks)).argmin()])
+    inner = sorted({int(inside[np.abs(inside - (hi - (n >> k))).argmin()])
                     for k in range(1, chunks)}) if len(inside) else []
     ends = inner + [hi]
     out, t0 = [], lo
@@ -734,7 +738,7 @@ class Engine:
         main.wait_event(done)
 
     def moment_scores(self, blk: BinBlock, kind: int, out: Optional[torch.Tensor] = None,
-                      rank: int = 0, world: int = 1, sink=None, host_chunks: int = 4) -> torch.Tensor:
+                      rank: int = 0, world: int = 1, sink=None, host_chunks: int = 6) -> torch.Tensor:
         """float32 [G][G] Pearson / cosine / Jaccard matrix (zero diagonal).  sink: see mi_scores."""
         assert blk.val_rows is not None
         with torch.cuda.device(self.device):
@@ -760,7 +764,7 @@ class Engine:
 
     def mi_scores(self, blk: BinBlock, onehot: torch.Tensor, B: int,
                   sgn: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                  rank: int = 0, world: int = 1, out_host=None, host_chunks: int = 6,
+                  rank: int = 0, world: int = 1, out_host=None, host_chunks: int = 8,
                   sink=None) -> torch.Tensor:
         """float32 [G][G] MI (times the Pearson sign when `sgn` is given).
 
