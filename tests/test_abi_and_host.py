@@ -111,7 +111,8 @@ def test_rank_slices_partition_the_schedule():
 @pytest.mark.parametrize("n_genes,B,cg,band,world", [(700, 10, 2, 8, 1), (700, 10, 2, 8, 3), (1500, 10, 2, 3, 4),
                                                      (1100, 5, 1, 8, 2), (2600, 16, 2, 8, 8), (900, 8, 1, 2, 5),
                                                      (96, 10, 2, 8, 2)])
-def test_host_pieces_are_exactly_what_the_tiles_write(n_genes, B, cg, band, world):
+@pytest.mark.parametrize("chunks", [3, 8])
+def test_host_pieces_are_exactly_what_the_tiles_write(n_genes, B, cg, band, world, chunks):
     """The rectangles a rank copies to the shared host matrix (engine.host_pieces) are exactly the
     entries its tiles write (pair (i, j), its mirror and the diagonal), every entry of the matrix is
     owned by exactly one rank, and a piece's rectangles are final once its tiles have run."""
@@ -124,9 +125,10 @@ def test_host_pieces_are_exactly_what_the_tiles_write(n_genes, B, cg, band, worl
     owner = np.zeros((n_genes, n_genes), dtype=np.int32)
     for rank in range(world):
         tiles, _ = tile_slice(op_rows, cg, band, rank, world)
-        pieces = host_pieces(op_rows, cg, band, gpb, n_genes, rank, world, chunks=3)
+        pieces = host_pieces(op_rows, cg, band, gpb, n_genes, rank, world, chunks=chunks)
         assert not pieces or (pieces[0][0] == 0 and pieces[-1][1] == len(tiles))
         assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        assert all(t1 > t0 for t0, t1, _ in pieces) and len(pieces) <= chunks
         written = np.zeros((n_genes, n_genes), dtype=bool)      # by the tiles run so far
         copied = np.zeros((n_genes, n_genes), dtype=np.int32)
         for t0, t1, rects in pieces:
